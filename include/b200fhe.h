@@ -1,0 +1,122 @@
+/* b200fhe — C ABI of the B200-native TFHE gate-evaluation back-end for Iyokan.
+ *
+ * This is the drop-in boundary for Iyokan's gate workers: a host (Iyokan's Task/Worker
+ * scheduler, or iyokan_b200's own levelised netlist engine) keeps every TLWE ciphertext in a
+ * device-resident slot arena and submits the scheduler's ready-gate frontier as ONE batch.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference):
+ *   b200fhe_create / b200fhe_destroy      cufhe::SetGPUNum + Initialize/CleanUp bookkeeping
+ *                                         (thirdparty/cuFHE/include/cufhe_gpu.cuh:53-73)
+ *   b200fhe_load_keys                     cufhe::Initialize(ek): BootstrappingKeyToNTT +
+ *                                         KeySwitchingKeyToDevice
+ *                                         (thirdparty/cuFHE/src/cufhe_gates_gpu.cu:42-47,
+ *                                          src/bootstrap_gpu.cu:89-115, src/keyswitch_gpu.cu:9-15);
+ *                                         inputs are EvalKey::bklvl01 / iksklvl10 as laid out in memory
+ *                                         (TFHEpp include/params.hpp:102-128, cloudkey.hpp:333-357)
+ *   b200fhe_arena_alloc/upload/download   cufhe::Ctxt<P> host/device pairs + CtxtCopyH2D/D2H per gate
+ *                                         (cufhe_gpu.cuh:112-131, cufhe_gates_gpu.cu:145-157)
+ *   b200fhe_gate_batch                    TaskTFHEppGate{AND..MUX,NOT,CONST*}::startSync ->
+ *                                         TFHEpp::Hom* (src/iyokan_tfhepp.hpp:109-144) and
+ *                                         TaskCUFHEGate*::startAsyncImpl -> cufhe::And/.../Mux
+ *                                         (src/iyokan_cufhe.hpp:207-262), one call per FRONTIER
+ *   b200fhe_dff_tick                      TaskDFF::tick, output <- input(0) for every DFF/RAM cell
+ *                                         (src/iyokan.hpp:1395-1402, driven by NetworkRunner::tick :2050-2054)
+ *   b200fhe_query / b200fhe_sync          cufhe::StreamQuery / Synchronize (cufhe_gpu.cuh:60,201)
+ *   b200fhe_last_error                    replaces CuSafeCall's exit(-1) (include/details/error_gpu.cuh:31-66):
+ *                                         nothing in this library exits; the caller maps non-zero to error::die.
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure (see b200fhe_last_error).
+ * All pointers are plain host pointers unless the name says "dev".  The library is not
+ * thread-safe per context; Iyokan calls it from its single scheduler thread
+ * (src/iyokan_tfhepp.cpp:28-47).  One context = one GPU = (in multi-GPU runs) one process.
+ */
+#ifndef B200FHE_H
+#define B200FHE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* 128-bit parameter set (TFHEpp include/params/128bit.hpp) */
+#define B200FHE_N0 636           /* lvl0 dimension; a TLWE lvl0 is 637 uint16 = 1274 bytes */
+#define B200FHE_N1 1024          /* lvl1 ring degree */
+#define B200FHE_TLWE0_LEN 637
+#define B200FHE_TLWE1_LEN 1025
+#define B200FHE_BK_WORDS (636ull * 6 * 2 * 1024)       /* uint32 [n][(k+1)l][k+1][N]  raw TRGSW */
+#define B200FHE_KSK_HALFS (1024ull * 7 * 3 * 637)      /* uint16 [N][t][3][n+1] */
+
+/* Gate opcodes.  ANDNOT = HomANDYN, ORNOT = HomORYN (src/iyokan_tfhepp.hpp:133,136).
+ * MUX computes in2 ? in1 : in0 (HomMUX(out, in(2), in(1), in(0)), iyokan_tfhepp.hpp:140). */
+enum b200fhe_op {
+    B200FHE_AND = 0, B200FHE_NAND = 1, B200FHE_ANDNOT = 2, B200FHE_OR = 3, B200FHE_NOR = 4,
+    B200FHE_ORNOT = 5, B200FHE_XOR = 6, B200FHE_XNOR = 7, B200FHE_MUX = 8, B200FHE_NOT = 9,
+    B200FHE_COPY = 10, B200FHE_CONST0 = 11, B200FHE_CONST1 = 12, B200FHE_ANDNY = 13, B200FHE_ORNY = 14,
+    B200FHE_NUM_OPS = 15
+};
+
+typedef struct b200fhe_ctx b200fhe_ctx;
+
+/* lifetime ------------------------------------------------------------------------------- */
+int b200fhe_create(b200fhe_ctx **out, int device);
+void b200fhe_destroy(b200fhe_ctx *ctx);
+const char *b200fhe_last_error(void);
+/* tuning knob: rotation jobs per CTA (1, 2 or 4); 0 = default */
+int b200fhe_set_jobs_per_cta(b200fhe_ctx *ctx, int g);
+
+/* keys: raw bootstrapping key + key-switching key in the reference's memory layout.
+ * Copies to the device, converts the bootstrapping key to NTT form there. */
+int b200fhe_load_keys(b200fhe_ctx *ctx, const uint32_t *bk_raw, const uint16_t *ksk);
+
+/* ciphertext arena ------------------------------------------------------------------------ */
+int b200fhe_arena_alloc(b200fhe_ctx *ctx, size_t n_slots);
+/* use caller-owned device memory (n_slots * 1280 bytes, zero-initialised) as the arena */
+int b200fhe_arena_attach(b200fhe_ctx *ctx, void *dev_ptr, size_t n_slots);
+size_t b200fhe_arena_slots(const b200fhe_ctx *ctx);
+void *b200fhe_arena_dev_ptr(const b200fhe_ctx *ctx);
+/* tlwe_host is [n][637] uint16, densely packed (the reference's std::array<uint16_t,637>) */
+int b200fhe_upload(b200fhe_ctx *ctx, const uint32_t *slot_ids, const uint16_t *tlwe_host, size_t n);
+int b200fhe_download(b200fhe_ctx *ctx, const uint32_t *slot_ids, uint16_t *tlwe_host, size_t n);
+
+/* evaluation (asynchronous on the context's stream) --------------------------------------- */
+/* One frontier: gate i reads slots in0[i], in1[i], in2[i] (unused operands ignored, may be NULL
+ * arrays when no gate needs them) and writes slot out[i].  Gates of one batch must be
+ * independent of each other. */
+int b200fhe_gate_batch(b200fhe_ctx *ctx, const uint8_t *opcode, const uint32_t *in0, const uint32_t *in1,
+                       const uint32_t *in2, const uint32_t *out, size_t n);
+/* dst[i] <- src[i] for all i, as one parallel step (all reads happen before all writes) */
+int b200fhe_dff_tick(b200fhe_ctx *ctx, const uint32_t *src, const uint32_t *dst, size_t n);
+int b200fhe_sync(b200fhe_ctx *ctx);
+int b200fhe_query(b200fhe_ctx *ctx); /* 0 = idle, 1 = busy, <0 = error */
+
+/* End-to-end convenience with HOST operands: uploads, evaluates, downloads (synchronous).
+ * in*_host / out_host are [n][637] uint16; needs an arena of at least 4*n slots. */
+int b200fhe_gates_host(b200fhe_ctx *ctx, const uint8_t *opcode, const uint16_t *in0_host,
+                       const uint16_t *in1_host, const uint16_t *in2_host, uint16_t *out_host, size_t n);
+
+/* pinned host memory helpers (so callers written in any language can stage without torch) */
+int b200fhe_host_alloc(void **ptr, size_t bytes);
+int b200fhe_host_free(void *ptr);
+
+/* instrumentation ------------------------------------------------------------------------- */
+/* kernels launched by this context so far (all kinds) */
+uint64_t b200fhe_launch_count(const b200fhe_ctx *ctx);
+/* device time (ms, CUDA events on the context's stream) spent in the blind-rotation kernel /
+ * key-switch kernel by the most recent b200fhe_gate_batch; valid after b200fhe_sync */
+int b200fhe_last_batch_ms(b200fhe_ctx *ctx, float *blind_rotate_ms, float *keyswitch_ms);
+void *b200fhe_stream(const b200fhe_ctx *ctx);
+
+/* test hooks: stage-level access used by the parity tests --------------------------------- */
+/* blind rotation + sample extraction only: c [n][637] uint16 (already linearly combined)
+ * -> lvl1 TLWE [n][1025] uint32 (GateBootstrappingTLWE2TLWE, gatebootstrapping.hpp:188-197) */
+int b200fhe_test_bootstrap_lvl1(b200fhe_ctx *ctx, const uint16_t *c_host, uint32_t *tlwe1_host, size_t n);
+/* identity key switch only: [n][1025] uint32 -> [n][637] uint16 (keyswitch.hpp:11-52) */
+int b200fhe_test_keyswitch(b200fhe_ctx *ctx, const uint32_t *tlwe1_host, uint16_t *tlwe0_host, size_t n);
+/* NTT-domain bootstrapping key as stored on the device: uint32 [636][6][6][1024] */
+int b200fhe_test_read_bk_ntt(b200fhe_ctx *ctx, uint32_t *out_host, size_t first_i, size_t count_i);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

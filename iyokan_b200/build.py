@@ -1,0 +1,58 @@
+"""In-tree build of the CUDA library and the CPU-side test helpers (explicit nvcc / g++ calls)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+CSRC = ROOT / "iyokan_b200" / "csrc"
+SIM = ROOT / "tests" / "sim"
+
+NVCC_FLAGS = [
+    "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "--expt-relaxed-constexpr", "-shared", "-Xcompiler", "-fPIC",
+]
+
+
+def _newer(target: Path, sources) -> bool:
+    if not target.exists():
+        return False
+    t = target.stat().st_mtime
+    return all(Path(s).stat().st_mtime <= t for s in sources)
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA extension cannot be built (there is no CPU fallback)")
+
+
+def build_cuda(force: bool = False, verbose: bool = False) -> Path:
+    out = CSRC / "libb200fhe.so"
+    srcs = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.h")) + [ROOT / "include" / "b200fhe.h"]
+    if not force and _newer(out, srcs):
+        return out
+    cmd = [_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(out), str(CSRC / "b200fhe.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return out
+
+
+def build_sim(force: bool = False) -> Path:
+    """CPU lock-step simulator of the kernels (test infrastructure, g++)."""
+    out = SIM / "libbr_sim.so"
+    srcs = [SIM / "br_sim.cpp"] + list(CSRC.glob("*.h"))
+    if not force and _newer(out, srcs):
+        return out
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-std=c++17", "-O2", "-fopenmp", "-fPIC", "-shared", "-o", str(out), str(SIM / "br_sim.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return out

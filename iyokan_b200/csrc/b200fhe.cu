@@ -1,0 +1,658 @@
+// b200fhe: sm_100a kernels + C ABI (include/b200fhe.h) of the batched TFHE gate back-end.
+//
+// Kernels (all hand-written CUDA, integer arithmetic, no tensor cores — the path is modular
+// integer math; see DESIGN.md for the roofline of each):
+//   br_kernel<G>     blind rotation of G jobs per CTA (br_phases.h)      — the hot kernel
+//   ks_kernel        sample-extracted lvl1 TLWE(s) -> lvl0 TLWE (ks_phases.h)
+//   unary_kernel     NOT / COPY / CONST and the DFF tick gather-copy
+//   bk_prep_kernel   raw TRGSW bootstrapping key -> NTT-domain 3-limb form (once per key)
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200fhe.h"
+#include "br_phases.h"
+#include "ks_phases.h"
+
+using namespace b200;
+
+// =====================================================================================
+// kernels
+// =====================================================================================
+
+template <int G>
+__global__ void __launch_bounds__(64 * G, (G <= 2 ? 2 : 1))
+br_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ arena,
+          const uint32_t* __restrict__ bk_ntt, const tw_t* __restrict__ tw2f_g, const tw_t* __restrict__ tw2i_g,
+          uint32_t* __restrict__ ubuf, int n_iter)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    BrSmem<G> sm;
+    sm.carve(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = warp >> 1, q = warp & 1;
+
+    for (int k = tid; k < TW2_LEN; k += 64 * G) {
+        sm.tw2f[k] = tw2f_g[k];
+        sm.tw2i[k] = tw2i_g[k];
+    }
+    int job = blockIdx.x * G + g;
+    const bool valid = job < njobs;
+    if (!valid) job = njobs - 1;  // duplicate work, keeps every barrier uniform
+    const BrJob jb = jobs[job];
+
+    uint32_t accr[32], dreg[32], sum[32];
+    br_prologue<G>(sm, jb, arena, g, q, lane, accr);
+    __syncthreads();
+
+    for (int i = 0; i < n_iter; i++) {
+        br_rotate_diff<G>(sm, i, g, q, lane, accr, dreg);
+#pragma unroll 1
+        for (int d = 0; d < GL; d++) {
+            br_fwd_a<G>(sm, g, q, lane, d, dreg);
+            __syncwarp();
+            br_fwd_b<G>(sm, g, q, lane, d);
+        }
+        __syncthreads();
+        br_pointwise<G>(sm, bk_ntt + (size_t)i * BK_COLS * ROWS * N1, tid);
+        __syncthreads();
+#pragma unroll 1
+        for (int l = 0; l < LIMBS; l++) {
+            br_inv_a<G>(sm, g, q, lane, l);
+            __syncwarp();
+            br_inv_b<G>(sm, g, q, lane, l, sum);
+        }
+        br_acc_update<G>(sm, g, q, lane, sum, accr);
+        __syncwarp();
+    }
+    if (valid) br_epilogue<G>(sm, g, q, lane, ubuf + (size_t)job * U_STRIDE);
+}
+
+__global__ void __launch_bounds__(KS_THREADS)
+ks_kernel(const KsJob* __restrict__ jobs, const uint32_t* __restrict__ ubuf,
+          const uint32_t* __restrict__ ksk_words, uint16_t* __restrict__ arena)
+{
+    __shared__ uint16_t codes[N1];
+    __shared__ uint32_t b_sh;
+    const KsJob job = jobs[blockIdx.x];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < N1; i += KS_THREADS) codes[i] = ks_code(ubuf, job, i);
+    if (tid == 0) b_sh = ks_b_rounded(ubuf, job);
+    __syncthreads();
+    const uint32_t w = ks_accumulate(ksk_words, codes, b_sh, job.post, tid);
+    reinterpret_cast<uint32_t*>(arena + (size_t)job.out * SLOT_STRIDE)[tid] = w;
+}
+
+// Reads every source before any destination is written (two launches: gather, scatter) so that
+// a DFF chain Q1 <- D1 = Q0 ticks correctly even when src and dst sets overlap.
+__global__ void __launch_bounds__(KS_THREADS)
+unary_gather_kernel(const UnaryJob* __restrict__ jobs, const uint32_t* __restrict__ arena_words,
+                    uint32_t* __restrict__ stage_words)
+{
+    const UnaryJob job = jobs[blockIdx.x];
+    stage_words[(size_t)blockIdx.x * KS_THREADS + threadIdx.x] = unary_word(job, arena_words, threadIdx.x);
+}
+__global__ void __launch_bounds__(KS_THREADS)
+unary_scatter_kernel(const UnaryJob* __restrict__ jobs, const uint32_t* __restrict__ stage_words,
+                     uint32_t* __restrict__ arena_words)
+{
+    const UnaryJob job = jobs[blockIdx.x];
+    arena_words[(size_t)job.dst * KS_THREADS + threadIdx.x] = stage_words[(size_t)blockIdx.x * KS_THREADS + threadIdx.x];
+}
+
+constexpr int BKPREP_WARPS = 4;
+__global__ void __launch_bounds__(32 * BKPREP_WARPS)
+bk_prep_kernel(const uint32_t* __restrict__ bk_raw, uint32_t* __restrict__ bk_ntt, const tw_t* __restrict__ tw2f,
+               tw_t scale, int ntasks)
+{
+    __shared__ __align__(16) uint32_t tiles[BKPREP_WARPS][TILE_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int task = blockIdx.x * BKPREP_WARPS + warp;
+    if (task >= ntasks) return;  // whole warp exits together; only __syncwarp below
+    const int l = task % LIMBS, q = (task / LIMBS) % 2, r = (task / (2 * LIMBS)) % ROWS, i = task / (2 * LIMBS * ROWS);
+    const uint32_t* raw = bk_raw + ((size_t)(i * ROWS + r) * 2 + q) * N1;
+    uint32_t* out = bk_ntt + ((size_t)(i * BK_COLS + q * LIMBS + l) * ROWS + r) * N1;
+    bk_prep_a(raw, l, lane, tiles[warp]);
+    __syncwarp();
+    bk_prep_b(tiles[warp], tw2f, scale, lane, out);
+}
+
+// test hook helpers: c [n][637] dense -> arena-like [n][640]
+__global__ void pad_tlwe0_kernel(const uint16_t* __restrict__ dense, uint16_t* __restrict__ padded, size_t n)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * SLOT_STRIDE) return;
+    const size_t s = idx / SLOT_STRIDE, k = idx % SLOT_STRIDE;
+    padded[idx] = k < TLWE0_LEN ? dense[s * TLWE0_LEN + k] : (uint16_t)0;
+}
+
+// =====================================================================================
+// host side
+// =====================================================================================
+
+static thread_local std::string g_err;
+static int fail(const std::string& msg)
+{
+    g_err = msg;
+    return 1;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" +  \
+                        std::to_string(__LINE__) + ")");                                           \
+    } while (0)
+
+struct b200fhe_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int G = 2;
+    NttTables* tab = nullptr;
+    tw_t* d_tw2f = nullptr;
+    tw_t* d_tw2i = nullptr;
+    uint32_t* d_bk_ntt = nullptr;   // [636][6][6][1024]
+    uint16_t* d_ksk = nullptr;      // [1024][7][3][640]
+    bool keys = false;
+    uint16_t* d_arena = nullptr;
+    bool arena_owned = false;
+    size_t n_slots = 0;
+    // job staging (pinned host + device), grown on demand
+    size_t cap = 0;
+    BrJob *h_br = nullptr, *d_br = nullptr;
+    KsJob *h_ks = nullptr, *d_ks = nullptr;
+    UnaryJob *h_un = nullptr, *d_un = nullptr;
+    uint32_t* d_ubuf = nullptr;     // [2*cap][U_STRIDE]
+    uint32_t* d_unstage = nullptr;  // [cap][320]
+    cudaEvent_t ev_staged = nullptr, ev_t[3] = {nullptr, nullptr, nullptr};
+    bool staged_pending = false, timed = false;
+    uint64_t launches = 0;
+};
+
+static int set_dev(b200fhe_ctx* c)
+{
+    CK(cudaSetDevice(c->device));
+    return 0;
+}
+
+template <int G>
+static int br_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+{
+    static bool attr_set[64] = {};
+    if (!attr_set[c->device]) {
+        CK(cudaFuncSetAttribute(br_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BrSmem<G>::BYTES));
+        attr_set[c->device] = true;
+    }
+    const int grid = (njobs + G - 1) / G;
+    br_kernel<G><<<grid, 64 * G, BrSmem<G>::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_tw2f,
+                                                                 c->d_tw2i, ubuf, N0);
+    CK(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+static int br_dispatch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+{
+    switch (c->G) {
+    case 1: return br_launch<1>(c, njobs, arena, ubuf, d_jobs);
+    case 2: return br_launch<2>(c, njobs, arena, ubuf, d_jobs);
+    case 4: return br_launch<4>(c, njobs, arena, ubuf, d_jobs);
+    default: return fail("jobs per CTA must be 1, 2 or 4");
+    }
+}
+
+static int ensure_cap(b200fhe_ctx* c, size_t n)
+{
+    if (n <= c->cap) return 0;
+    CK(cudaStreamSynchronize(c->stream));
+    size_t cap = c->cap ? c->cap : 1024;
+    while (cap < n) cap *= 2;
+    if (c->h_br) cudaFreeHost(c->h_br);
+    if (c->h_ks) cudaFreeHost(c->h_ks);
+    if (c->h_un) cudaFreeHost(c->h_un);
+    if (c->d_br) cudaFree(c->d_br);
+    if (c->d_ks) cudaFree(c->d_ks);
+    if (c->d_un) cudaFree(c->d_un);
+    if (c->d_ubuf) cudaFree(c->d_ubuf);
+    if (c->d_unstage) cudaFree(c->d_unstage);
+    c->cap = 0;
+    CK(cudaHostAlloc(&c->h_br, 2 * cap * sizeof(BrJob), cudaHostAllocDefault));
+    CK(cudaHostAlloc(&c->h_ks, cap * sizeof(KsJob), cudaHostAllocDefault));
+    CK(cudaHostAlloc(&c->h_un, cap * sizeof(UnaryJob), cudaHostAllocDefault));
+    CK(cudaMalloc(&c->d_br, 2 * cap * sizeof(BrJob)));
+    CK(cudaMalloc(&c->d_ks, cap * sizeof(KsJob)));
+    CK(cudaMalloc(&c->d_un, cap * sizeof(UnaryJob)));
+    CK(cudaMalloc(&c->d_ubuf, 2 * cap * (size_t)U_STRIDE * 4));
+    CK(cudaMalloc(&c->d_unstage, cap * (size_t)KS_THREADS * 4));
+    c->cap = cap;
+    return 0;
+}
+
+extern "C" {
+
+const char* b200fhe_last_error(void) { return g_err.c_str(); }
+
+int b200fhe_create(b200fhe_ctx** out, int device)
+{
+    if (!out) return fail("null out pointer");
+    *out = nullptr;
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail("no such CUDA device");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(std::string("b200fhe is built for sm_100a only; device is sm_") + std::to_string(prop.major) +
+                    std::to_string(prop.minor));
+    b200fhe_ctx* c = new b200fhe_ctx();
+    c->device = device;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming));
+    for (auto& e : c->ev_t) CK(cudaEventCreate(&e));
+    c->tab = new NttTables();
+    ntt_tables_init(*c->tab);
+    CK(cudaMemcpyToSymbol(c_twf_u, h_twf_u, sizeof(h_twf_u)));
+    CK(cudaMemcpyToSymbol(c_twi_u, h_twi_u, sizeof(h_twi_u)));
+    CK(cudaMalloc(&c->d_tw2f, sizeof(c->tab->tw2f)));
+    CK(cudaMalloc(&c->d_tw2i, sizeof(c->tab->tw2i)));
+    CK(cudaMemcpy(c->d_tw2f, c->tab->tw2f, sizeof(c->tab->tw2f), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_tw2i, c->tab->tw2i, sizeof(c->tab->tw2i), cudaMemcpyHostToDevice));
+    *out = c;
+    return 0;
+}
+
+void b200fhe_destroy(b200fhe_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_tw2f);
+    cudaFree(c->d_tw2i);
+    cudaFree(c->d_bk_ntt);
+    cudaFree(c->d_ksk);
+    if (c->arena_owned) cudaFree(c->d_arena);
+    if (c->h_br) cudaFreeHost(c->h_br);
+    if (c->h_ks) cudaFreeHost(c->h_ks);
+    if (c->h_un) cudaFreeHost(c->h_un);
+    cudaFree(c->d_br);
+    cudaFree(c->d_ks);
+    cudaFree(c->d_un);
+    cudaFree(c->d_ubuf);
+    cudaFree(c->d_unstage);
+    cudaEventDestroy(c->ev_staged);
+    for (auto& e : c->ev_t) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c->tab;
+    delete c;
+}
+
+int b200fhe_set_jobs_per_cta(b200fhe_ctx* c, int g)
+{
+    if (!c) return fail("null context");
+    if (g == 0) g = 2;
+    if (g != 1 && g != 2 && g != 4) return fail("jobs per CTA must be 1, 2 or 4");
+    c->G = g;
+    return 0;
+}
+
+int b200fhe_load_keys(b200fhe_ctx* c, const uint32_t* bk_raw, const uint16_t* ksk)
+{
+    if (!c || !bk_raw || !ksk) return fail("null argument");
+    if (set_dev(c)) return 1;
+    CK(cudaStreamSynchronize(c->stream));
+    const size_t bk_raw_bytes = B200FHE_BK_WORDS * 4;
+    const size_t bk_ntt_bytes = (size_t)N0 * BK_COLS * ROWS * N1 * 4;
+    const size_t ksk_rows = (size_t)N1 * KS_T * 3;
+    if (!c->d_bk_ntt) CK(cudaMalloc(&c->d_bk_ntt, bk_ntt_bytes));
+    if (!c->d_ksk) CK(cudaMalloc(&c->d_ksk, ksk_rows * KSK_ROW * 2));
+    uint32_t* d_raw = nullptr;
+    CK(cudaMalloc(&d_raw, bk_raw_bytes));
+    CK(cudaMemcpyAsync(d_raw, bk_raw, bk_raw_bytes, cudaMemcpyHostToDevice, c->stream));
+    const int ntasks = N0 * ROWS * 2 * LIMBS;
+    bk_prep_kernel<<<(ntasks + BKPREP_WARPS - 1) / BKPREP_WARPS, 32 * BKPREP_WARPS, 0, c->stream>>>(
+        d_raw, c->d_bk_ntt, c->d_tw2f, c->tab->bk_scale, ntasks);
+    CK(cudaGetLastError());
+    c->launches++;
+    // key-switching key: pad every 637-element row to 640 (1280 B, 16-byte aligned rows)
+    CK(cudaMemsetAsync(c->d_ksk, 0, ksk_rows * KSK_ROW * 2, c->stream));
+    CK(cudaMemcpy2DAsync(c->d_ksk, KSK_ROW * 2, ksk, TLWE0_LEN * 2, TLWE0_LEN * 2, ksk_rows, cudaMemcpyHostToDevice,
+                         c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(d_raw));
+    c->keys = true;
+    return 0;
+}
+
+int b200fhe_arena_alloc(b200fhe_ctx* c, size_t n_slots)
+{
+    if (!c || n_slots == 0) return fail("bad arena size");
+    if (set_dev(c)) return 1;
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->arena_owned && c->d_arena) CK(cudaFree(c->d_arena));
+    c->d_arena = nullptr;
+    CK(cudaMalloc(&c->d_arena, n_slots * SLOT_STRIDE * 2));
+    CK(cudaMemset(c->d_arena, 0, n_slots * SLOT_STRIDE * 2));
+    c->arena_owned = true;
+    c->n_slots = n_slots;
+    return 0;
+}
+
+int b200fhe_arena_attach(b200fhe_ctx* c, void* dev_ptr, size_t n_slots)
+{
+    if (!c || !dev_ptr || n_slots == 0) return fail("bad arena");
+    if (set_dev(c)) return 1;
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->arena_owned && c->d_arena) CK(cudaFree(c->d_arena));
+    c->d_arena = reinterpret_cast<uint16_t*>(dev_ptr);
+    c->arena_owned = false;
+    c->n_slots = n_slots;
+    return 0;
+}
+
+size_t b200fhe_arena_slots(const b200fhe_ctx* c) { return c ? c->n_slots : 0; }
+void* b200fhe_arena_dev_ptr(const b200fhe_ctx* c) { return c ? c->d_arena : nullptr; }
+void* b200fhe_stream(const b200fhe_ctx* c) { return c ? (void*)c->stream : nullptr; }
+uint64_t b200fhe_launch_count(const b200fhe_ctx* c) { return c ? c->launches : 0; }
+
+static int check_slots(b200fhe_ctx* c, const uint32_t* ids, size_t n)
+{
+    if (!c->d_arena) return fail("no arena allocated");
+    for (size_t i = 0; i < n; i++)
+        if (ids[i] >= c->n_slots) return fail("slot id out of range");
+    return 0;
+}
+
+// copies runs of consecutive slot ids with one strided copy each
+int b200fhe_upload(b200fhe_ctx* c, const uint32_t* ids, const uint16_t* host, size_t n)
+{
+    if (!c || (n && (!ids || !host))) return fail("null argument");
+    if (set_dev(c) || check_slots(c, ids, n)) return 1;
+    for (size_t i = 0; i < n;) {
+        size_t j = i + 1;
+        while (j < n && ids[j] == ids[j - 1] + 1) j++;
+        CK(cudaMemcpy2DAsync(c->d_arena + (size_t)ids[i] * SLOT_STRIDE, SLOT_STRIDE * 2, host + i * TLWE0_LEN,
+                             TLWE0_LEN * 2, TLWE0_LEN * 2, j - i, cudaMemcpyHostToDevice, c->stream));
+        i = j;
+    }
+    return 0;
+}
+
+int b200fhe_download(b200fhe_ctx* c, const uint32_t* ids, uint16_t* host, size_t n)
+{
+    if (!c || (n && (!ids || !host))) return fail("null argument");
+    if (set_dev(c) || check_slots(c, ids, n)) return 1;
+    for (size_t i = 0; i < n;) {
+        size_t j = i + 1;
+        while (j < n && ids[j] == ids[j - 1] + 1) j++;
+        CK(cudaMemcpy2DAsync(host + i * TLWE0_LEN, TLWE0_LEN * 2, c->d_arena + (size_t)ids[i] * SLOT_STRIDE,
+                             SLOT_STRIDE * 2, TLWE0_LEN * 2, j - i, cudaMemcpyDeviceToHost, c->stream));
+        i = j;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// (sa, sb, off/mu0) of HomGate, TFHEpp include/gate.hpp:59-230
+static bool gate_coef(uint8_t op, int& sa, int& sb, int& off)
+{
+    switch (op) {
+    case OP_NAND:   sa = -1; sb = -1; off = +1; return true;
+    case OP_NOR:    sa = -1; sb = -1; off = -1; return true;
+    case OP_XNOR:   sa = -2; sb = -2; off = -2; return true;
+    case OP_AND:    sa = +1; sb = +1; off = -1; return true;
+    case OP_OR:     sa = +1; sb = +1; off = +1; return true;
+    case OP_XOR:    sa = +2; sb = +2; off = +2; return true;
+    case OP_ANDNY:  sa = -1; sb = +1; off = -1; return true;
+    case OP_ANDNOT: sa = +1; sb = -1; off = -1; return true;
+    case OP_ORNY:   sa = -1; sb = +1; off = +1; return true;
+    case OP_ORNOT:  sa = +1; sb = -1; off = +1; return true;
+    default: return false;
+    }
+}
+
+int b200fhe_gate_batch(b200fhe_ctx* c, const uint8_t* opcode, const uint32_t* in0, const uint32_t* in1,
+                       const uint32_t* in2, const uint32_t* out, size_t n)
+{
+    if (!c) return fail("null context");
+    if (n == 0) return 0;
+    if (!opcode || !out) return fail("null argument");
+    if (!c->keys) return fail("keys not loaded");
+    if (!c->d_arena) return fail("no arena allocated");
+    if (set_dev(c) || ensure_cap(c, n)) return 1;
+    if (c->staged_pending) {
+        CK(cudaEventSynchronize(c->ev_staged));
+        c->staged_pending = false;
+    }
+    size_t nbr = 0, nks = 0, nun = 0;
+    auto slot = [&](const uint32_t* arr, size_t i, uint32_t& dst) -> bool {
+        if (!arr || arr[i] >= c->n_slots) return false;
+        dst = arr[i];
+        return true;
+    };
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t op = opcode[i];
+        uint32_t o, a = 0, b = 0, s = 0;
+        if (!slot(out, i, o)) return fail("output slot out of range");
+        int sa, sb, off;
+        if (gate_coef(op, sa, sb, off)) {
+            if (!slot(in0, i, a) || !slot(in1, i, b)) return fail("input slot missing or out of range");
+            BrJob& j = c->h_br[nbr];
+            j.in[0] = a; j.in[1] = b; j.in[2] = 0;
+            j.sgn[0] = (int8_t)sa; j.sgn[1] = (int8_t)sb; j.sgn[2] = 0; j.pad = 0;
+            j.off = (uint32_t)(off * (int)MU0) & 0xFFFFu;
+            c->h_ks[nks++] = KsJob{(uint32_t)nbr, KS_NONE, o, 0u};
+            nbr++;
+        } else if (op == OP_MUX) {
+            // HomMUX(res, cs=in2, c1=in1, c0=in0), gate.hpp:236-240: (cs + c1 - mu), (-cs + c0 - mu)
+            if (!slot(in0, i, a) || !slot(in1, i, b) || !slot(in2, i, s))
+                return fail("input slot missing or out of range");
+            BrJob& j1 = c->h_br[nbr];
+            j1.in[0] = a; j1.in[1] = b; j1.in[2] = s;
+            j1.sgn[0] = 0; j1.sgn[1] = 1; j1.sgn[2] = 1; j1.pad = 0;
+            j1.off = (0u - MU0) & 0xFFFFu;
+            BrJob& j0 = c->h_br[nbr + 1];
+            j0.in[0] = a; j0.in[1] = b; j0.in[2] = s;
+            j0.sgn[0] = 1; j0.sgn[1] = 0; j0.sgn[2] = -1; j0.pad = 0;
+            j0.off = (0u - MU0) & 0xFFFFu;
+            c->h_ks[nks++] = KsJob{(uint32_t)nbr, (uint32_t)nbr + 1, o, MU0};
+            nbr += 2;
+        } else if (op == OP_NOT || op == OP_COPY) {
+            if (!slot(in0, i, a)) return fail("input slot missing or out of range");
+            c->h_un[nun++] = UnaryJob{a, o, op};
+        } else if (op == OP_CONST0 || op == OP_CONST1) {
+            c->h_un[nun++] = UnaryJob{0u, o, op};
+        } else {
+            return fail("unknown opcode");
+        }
+    }
+    if (nbr) CK(cudaMemcpyAsync(c->d_br, c->h_br, nbr * sizeof(BrJob), cudaMemcpyHostToDevice, c->stream));
+    if (nks) CK(cudaMemcpyAsync(c->d_ks, c->h_ks, nks * sizeof(KsJob), cudaMemcpyHostToDevice, c->stream));
+    if (nun) CK(cudaMemcpyAsync(c->d_un, c->h_un, nun * sizeof(UnaryJob), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->ev_staged, c->stream));
+    c->staged_pending = true;
+
+    // every kernel of a batch reads only slots written by earlier batches, so order is free;
+    // the bootstrap-free ops go first, staged through a scratch buffer.
+    if (nun) {
+        uint32_t* aw = reinterpret_cast<uint32_t*>(c->d_arena);
+        unary_gather_kernel<<<(unsigned)nun, KS_THREADS, 0, c->stream>>>(c->d_un, aw, c->d_unstage);
+        unary_scatter_kernel<<<(unsigned)nun, KS_THREADS, 0, c->stream>>>(c->d_un, c->d_unstage, aw);
+        CK(cudaGetLastError());
+        c->launches += 2;
+    }
+    c->timed = false;
+    if (nbr) {
+        CK(cudaEventRecord(c->ev_t[0], c->stream));
+        if (br_dispatch(c, (int)nbr, c->d_arena, c->d_ubuf, c->d_br)) return 1;
+        CK(cudaEventRecord(c->ev_t[1], c->stream));
+        ks_kernel<<<(unsigned)nks, KS_THREADS, 0, c->stream>>>(c->d_ks, c->d_ubuf,
+                                                               reinterpret_cast<const uint32_t*>(c->d_ksk), c->d_arena);
+        CK(cudaGetLastError());
+        c->launches++;
+        CK(cudaEventRecord(c->ev_t[2], c->stream));
+        c->timed = true;
+    }
+    return 0;
+}
+
+int b200fhe_dff_tick(b200fhe_ctx* c, const uint32_t* src, const uint32_t* dst, size_t n)
+{
+    if (!c) return fail("null context");
+    if (n == 0) return 0;
+    if (!src || !dst) return fail("null argument");
+    if (!c->d_arena) return fail("no arena allocated");
+    if (set_dev(c) || ensure_cap(c, n) || check_slots(c, src, n) || check_slots(c, dst, n)) return 1;
+    if (c->staged_pending) {
+        CK(cudaEventSynchronize(c->ev_staged));
+        c->staged_pending = false;
+    }
+    for (size_t i = 0; i < n; i++) c->h_un[i] = UnaryJob{src[i], dst[i], (uint32_t)OP_COPY};
+    CK(cudaMemcpyAsync(c->d_un, c->h_un, n * sizeof(UnaryJob), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->ev_staged, c->stream));
+    c->staged_pending = true;
+    uint32_t* aw = reinterpret_cast<uint32_t*>(c->d_arena);
+    unary_gather_kernel<<<(unsigned)n, KS_THREADS, 0, c->stream>>>(c->d_un, aw, c->d_unstage);
+    unary_scatter_kernel<<<(unsigned)n, KS_THREADS, 0, c->stream>>>(c->d_un, c->d_unstage, aw);
+    CK(cudaGetLastError());
+    c->launches += 2;
+    return 0;
+}
+
+int b200fhe_sync(b200fhe_ctx* c)
+{
+    if (!c) return fail("null context");
+    if (set_dev(c)) return 1;
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int b200fhe_query(b200fhe_ctx* c)
+{
+    if (!c) return -1;
+    cudaError_t e = cudaStreamQuery(c->stream);
+    if (e == cudaSuccess) return 0;
+    if (e == cudaErrorNotReady) return 1;
+    g_err = cudaGetErrorString(e);
+    return -1;
+}
+
+int b200fhe_last_batch_ms(b200fhe_ctx* c, float* br_ms, float* ks_ms)
+{
+    if (!c) return fail("null context");
+    if (!c->timed) return fail("no timed batch");
+    CK(cudaEventSynchronize(c->ev_t[2]));
+    float a = 0, b = 0;
+    CK(cudaEventElapsedTime(&a, c->ev_t[0], c->ev_t[1]));
+    CK(cudaEventElapsedTime(&b, c->ev_t[1], c->ev_t[2]));
+    if (br_ms) *br_ms = a;
+    if (ks_ms) *ks_ms = b;
+    return 0;
+}
+
+int b200fhe_gates_host(b200fhe_ctx* c, const uint8_t* opcode, const uint16_t* in0_host, const uint16_t* in1_host,
+                       const uint16_t* in2_host, uint16_t* out_host, size_t n)
+{
+    if (!c) return fail("null context");
+    if (n == 0) return 0;
+    if (!opcode || !out_host) return fail("null argument");
+    if (c->n_slots < 4 * n) return fail("arena too small for b200fhe_gates_host (needs 4*n slots)");
+    if (set_dev(c)) return 1;
+    std::vector<uint32_t> ids(4 * n);
+    for (size_t i = 0; i < 4 * n; i++) ids[i] = (uint32_t)i;
+    const uint16_t* ins[3] = {in0_host, in1_host, in2_host};
+    for (int k = 0; k < 3; k++)
+        if (ins[k] && b200fhe_upload(c, ids.data() + k * n, ins[k], n)) return 1;
+    if (b200fhe_gate_batch(c, opcode, ids.data(), ids.data() + n, ids.data() + 2 * n, ids.data() + 3 * n, n)) return 1;
+    return b200fhe_download(c, ids.data() + 3 * n, out_host, n);
+}
+
+int b200fhe_host_alloc(void** ptr, size_t bytes)
+{
+    if (!ptr) return fail("null argument");
+    CK(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return 0;
+}
+int b200fhe_host_free(void* ptr)
+{
+    CK(cudaFreeHost(ptr));
+    return 0;
+}
+
+// ---- test hooks -------------------------------------------------------------------------
+
+int b200fhe_test_bootstrap_lvl1(b200fhe_ctx* c, const uint16_t* c_host, uint32_t* tlwe1_host, size_t n)
+{
+    if (!c || !c_host || !tlwe1_host) return fail("null argument");
+    if (!c->keys) return fail("keys not loaded");
+    if (n == 0) return 0;
+    if (set_dev(c)) return 1;
+    uint16_t *d_dense = nullptr, *d_pad = nullptr;
+    uint32_t* d_u = nullptr;
+    BrJob* d_jobs = nullptr;
+    std::vector<BrJob> jobs(n);
+    for (size_t i = 0; i < n; i++) {
+        jobs[i] = BrJob{{(uint32_t)i, 0u, 0u}, {1, 0, 0}, 0, 0u};
+    }
+    CK(cudaMalloc(&d_dense, n * TLWE0_LEN * 2));
+    CK(cudaMalloc(&d_pad, n * SLOT_STRIDE * 2));
+    CK(cudaMalloc(&d_u, n * (size_t)U_STRIDE * 4));
+    CK(cudaMalloc(&d_jobs, n * sizeof(BrJob)));
+    CK(cudaMemcpyAsync(d_dense, c_host, n * TLWE0_LEN * 2, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_jobs, jobs.data(), n * sizeof(BrJob), cudaMemcpyHostToDevice, c->stream));
+    const size_t tot = n * SLOT_STRIDE;
+    pad_tlwe0_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(d_dense, d_pad, n);
+    c->launches++;
+    if (br_dispatch(c, (int)n, d_pad, d_u, d_jobs)) return 1;
+    CK(cudaMemcpy2DAsync(tlwe1_host, TLWE1_LEN * 4, d_u, U_STRIDE * 4, TLWE1_LEN * 4, n, cudaMemcpyDeviceToHost,
+                         c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_dense);
+    cudaFree(d_pad);
+    cudaFree(d_u);
+    cudaFree(d_jobs);
+    return 0;
+}
+
+int b200fhe_test_keyswitch(b200fhe_ctx* c, const uint32_t* tlwe1_host, uint16_t* tlwe0_host, size_t n)
+{
+    if (!c || !tlwe1_host || !tlwe0_host) return fail("null argument");
+    if (!c->keys) return fail("keys not loaded");
+    if (n == 0) return 0;
+    if (set_dev(c)) return 1;
+    uint32_t* d_u = nullptr;
+    uint16_t* d_out = nullptr;
+    KsJob* d_jobs = nullptr;
+    std::vector<KsJob> jobs(n);
+    for (size_t i = 0; i < n; i++) jobs[i] = KsJob{(uint32_t)i, KS_NONE, (uint32_t)i, 0u};
+    CK(cudaMalloc(&d_u, n * (size_t)U_STRIDE * 4));
+    CK(cudaMalloc(&d_out, n * SLOT_STRIDE * 2));
+    CK(cudaMalloc(&d_jobs, n * sizeof(KsJob)));
+    CK(cudaMemcpy2DAsync(d_u, U_STRIDE * 4, tlwe1_host, TLWE1_LEN * 4, TLWE1_LEN * 4, n, cudaMemcpyHostToDevice,
+                         c->stream));
+    CK(cudaMemcpyAsync(d_jobs, jobs.data(), n * sizeof(KsJob), cudaMemcpyHostToDevice, c->stream));
+    ks_kernel<<<(unsigned)n, KS_THREADS, 0, c->stream>>>(d_jobs, d_u, reinterpret_cast<const uint32_t*>(c->d_ksk), d_out);
+    CK(cudaGetLastError());
+    c->launches++;
+    CK(cudaMemcpy2DAsync(tlwe0_host, TLWE0_LEN * 2, d_out, SLOT_STRIDE * 2, TLWE0_LEN * 2, n, cudaMemcpyDeviceToHost,
+                         c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_u);
+    cudaFree(d_out);
+    cudaFree(d_jobs);
+    return 0;
+}
+
+int b200fhe_test_read_bk_ntt(b200fhe_ctx* c, uint32_t* out_host, size_t first_i, size_t count_i)
+{
+    if (!c || !out_host) return fail("null argument");
+    if (!c->keys) return fail("keys not loaded");
+    if (first_i + count_i > (size_t)N0) return fail("range");
+    if (set_dev(c)) return 1;
+    const size_t per = (size_t)BK_COLS * ROWS * N1;
+    CK(cudaMemcpy(out_host, c->d_bk_ntt + first_i * per, count_i * per * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,262 @@
+// Per-thread phases of the batched blind-rotation kernel (the hot loop of every gate bootstrap).
+//
+// Computes, for each "rotation job", exactly what the reference computes in
+//   HomGate linear combination          TFHEpp include/gate.hpp:8-18 (and :236-240 for MUX)
+//   BlindRotate<lvl01param>             TFHEpp include/gatebootstrapping.hpp:19-71
+//     CMUXFFTwithPolynomialMulByXaiMinusOne   include/detwfa.hpp:36-49
+//     trgswfftExternalProduct / Decomposition include/trgsw.hpp:62-78,102-131
+//   SampleExtractIndex(.., 0)           TFHEpp include/trlwe.hpp:213-223
+// with the polynomial products evaluated EXACTLY modulo 2^32 (see modarith.h).  The prior-art
+// GPU formulation is cuFHE's __BlindRotatePreAdd__/Accumulate
+// (cuFHE include/gatebootstrapping_gpu.cuh:55-223): one 768-thread block per gate, 64-bit NTT.
+//
+// B200 mapping: a CTA owns G jobs and 2G warps; warp w = 2g + q owns polynomial q (0 = A, 1 = B)
+// of job g: it keeps that accumulator polynomial in registers, produces its three digit
+// polynomials in NTT form (phase F), and after the CTA-wide pointwise stage (phase M, which
+// streams the NTT-domain bootstrapping key once per CTA and reuses it for all G jobs) turns
+// the three limb results back (phase I).  Only two __syncthreads per CMUX step.
+//
+// Every function here is free of intra-phase cross-thread communication: threads talk only
+// through shared memory between phases, so a sequential CPU loop over (phase, thread) is an
+// exact model of the kernel.  tests/sim/br_sim.cpp relies on that.
+#pragma once
+#include "fhe_params.h"
+#include "hd.h"
+#include "modarith.h"
+#include "ntt_warp.h"
+
+namespace b200 {
+
+// One blind rotation: c = s0*in0 + s1*in1 + s2*in2 + off (uint16 torus), then BlindRotate + extract.
+struct BrJob {
+    uint32_t in[3];   // arena slot ids (ignored where the sign is 0)
+    int8_t sgn[3];
+    int8_t pad;
+    uint32_t off;     // added to the b coefficient, modulo 2^16
+};
+
+// Shared-memory carve-up of one CTA (G jobs).
+template <int G>
+struct BrSmem {
+    static constexpr int DBUF_WORDS = G * ROWS * TILE_WORDS;  // digit / limb tiles (in place)
+    static constexpr int ACC_WORDS = G * 2 * N1;              // accumulator copy for rotated reads
+    static constexpr int ABAR_HALFS = G * SLOT_STRIDE;        // mod-switched a_i
+    static constexpr size_t BYTES =
+        (size_t)DBUF_WORDS * 4 + (size_t)ACC_WORDS * 4 + 2 * (size_t)TW2_LEN * sizeof(tw_t) + (size_t)ABAR_HALFS * 2;
+    uint32_t* dbuf;
+    uint32_t* accbuf;
+    tw_t* tw2f;
+    tw_t* tw2i;
+    uint16_t* abar;
+    B200_HD void carve(void* base)
+    {
+        uint8_t* p = reinterpret_cast<uint8_t*>(base);
+        dbuf = reinterpret_cast<uint32_t*>(p);
+        p += (size_t)DBUF_WORDS * 4;
+        accbuf = reinterpret_cast<uint32_t*>(p);
+        p += (size_t)ACC_WORDS * 4;
+        tw2f = reinterpret_cast<tw_t*>(p);
+        p += (size_t)TW2_LEN * sizeof(tw_t);
+        tw2i = reinterpret_cast<tw_t*>(p);
+        p += (size_t)TW2_LEN * sizeof(tw_t);
+        abar = reinterpret_cast<uint16_t*>(p);
+    }
+    B200_HD uint32_t* tile(int g, int row) const { return dbuf + (size_t)(g * ROWS + row) * TILE_WORDS; }
+    B200_HD uint32_t* acc(int g, int q) const { return accbuf + (size_t)(g * 2 + q) * N1; }
+};
+
+// lvl0 linear combination of one coefficient (uint16 wrap-around, gate.hpp:14-16)
+B200_HD uint32_t br_lincomb(const BrJob& job, const uint16_t* arena, int i)
+{
+    int32_t c = 0;
+    B200_UNROLL
+    for (int k = 0; k < 3; k++)
+        if (job.sgn[k] != 0) c += (int32_t)job.sgn[k] * (int32_t)arena[(size_t)job.in[k] * SLOT_STRIDE + i];
+    if (i == N0) c += (int32_t)job.off;
+    return (uint32_t)c & 0xFFFFu;
+}
+
+// ---- prologue: mod switch + accumulator init -------------------------------------------
+// gatebootstrapping.hpp:26-32 (b: no rounding), :58-65 (a_i: rounded, shift 5 for the uint16 torus)
+template <int G>
+B200_HD void br_prologue(const BrSmem<G>& sm, const BrJob& job, const uint16_t* arena, int g, int q, int lane,
+                         uint32_t (&accr)[32])
+{
+    for (int i = q * 32 + lane; i < N0; i += 64) {
+        const uint32_t c = br_lincomb(job, arena, i);
+        sm.abar[g * SLOT_STRIDE + i] = (uint16_t)((c + 16u) >> 5);  // in [0, 2048]
+    }
+    const uint32_t bbar = 2u * N1 - (br_lincomb(job, arena, N0) >> 5);  // in [1, 2048]
+    uint32_t* acc = sm.acc(g, q);
+    B200_UNROLL
+    for (int a = 0; a < 32; a++) {
+        const int n = 32 * a + lane;
+        uint32_t v = 0;
+        if (q == 1) {  // testvector mu * X^bbar (utils.hpp:113-128)
+            const uint32_t m = ((uint32_t)n - bbar) & (2u * N1 - 1);
+            v = (m & N1) ? (0u - MU1) : MU1;
+        }
+        accr[a] = v;
+        acc[n] = v;
+    }
+}
+
+// ---- phase F: (X^abar - 1) * acc, decomposition, forward NTT ----------------------------
+// F0: rotated difference into registers (utils.hpp:130-144)
+template <int G>
+B200_HD void br_rotate_diff(const BrSmem<G>& sm, int i, int g, int q, int lane, const uint32_t (&accr)[32],
+                            uint32_t (&dreg)[32])
+{
+    const uint32_t abar = sm.abar[g * SLOT_STRIDE + i];
+    const uint32_t* acc = sm.acc(g, q);
+    const uint32_t base = ((uint32_t)lane - abar) & (2u * N1 - 1);
+    B200_UNROLL
+    for (int a = 0; a < 32; a++) {
+        const uint32_t m = (base + 32u * a) & (2u * N1 - 1);
+        const uint32_t v = acc[m & (N1 - 1)];
+        const uint32_t neg = 0u - ((m >> NBIT) & 1u);  // all ones when the wrap flips the sign
+        dreg[a] = ((v ^ neg) - neg) - accr[a];
+    }
+}
+
+// Fa(d): digit d of the decomposition (trgsw.hpp:62-78) -> forward pass 1 -> column store
+template <int G>
+B200_HD void br_fwd_a(const BrSmem<G>& sm, int g, int q, int lane, int d, const uint32_t (&dreg)[32])
+{
+    uint32_t x[32];
+    const int sh = 32 - (d + 1) * BGBIT;
+    B200_UNROLL
+    for (int a = 0; a < 32; a++) {
+        const uint32_t v = dreg[a] + (DEC_OFFSET + DEC_ROUND);
+        x[a] = ((v >> sh) & ((1u << BGBIT) - 1)) + (P - (1u << (BGBIT - 1)));  // digit + p, in [p-32, p+31]
+    }
+    fwd_pass1(x);
+    tile_store_col(sm.tile(g, q * GL + d), x, lane);
+}
+// Fb(d): row load -> forward pass 2 -> row store (values < 3p + 8c)
+template <int G>
+B200_HD void br_fwd_b(const BrSmem<G>& sm, int g, int q, int lane, int d)
+{
+    uint32_t x[32];
+    uint32_t* t = sm.tile(g, q * GL + d);
+    tile_load_row(t, x, lane);
+    fwd_pass2(x, sm.tw2f, lane);
+    tile_store_row(t, x, lane);
+}
+
+// ---- phase M: pointwise multiply-accumulate with the NTT-domain key ----------------------
+// bk_i points at bk_ntt[i] : [BK_COLS][ROWS][1024] uint32 in [0,p), pre-scaled by 2^32/N.
+// out[g][c][j] = sum_r D[g][r][j] * BK[c][r][j] * 2^-32  (in place over the digit tiles)
+template <int G>
+B200_HD void br_pointwise(const BrSmem<G>& sm, const uint32_t* bk_i, int tid)
+{
+    constexpr int T = 64 * G;
+    for (int j = tid; j < N1; j += T) {
+        uint32_t bkv[BK_COLS][ROWS];
+        B200_UNROLL
+        for (int c = 0; c < BK_COLS; c++) {
+            B200_UNROLL
+            for (int r = 0; r < ROWS; r++) bkv[c][r] = bk_i[(size_t)(c * ROWS + r) * N1 + j];
+        }
+        const int off = tile_of_j(j);
+        B200_UNROLL
+        for (int g = 0; g < G; g++) {
+            uint32_t d[ROWS], o[BK_COLS];
+            B200_UNROLL
+            for (int r = 0; r < ROWS; r++) d[r] = sm.tile(g, r)[off];
+            B200_UNROLL
+            for (int c = 0; c < BK_COLS; c++) {
+                uint64_t acc = 0;
+                B200_UNROLL
+                for (int r = 0; r < ROWS; r++) acc += (uint64_t)d[r] * bkv[c][r];
+                o[c] = redc64(acc);  // < 4p
+            }
+            B200_UNROLL
+            for (int c = 0; c < BK_COLS; c++) sm.tile(g, c)[off] = o[c];
+        }
+    }
+}
+
+// ---- phase I: inverse NTT of the three limbs, exact recombination, accumulate ------------
+// Ia(l): row load -> inverse pass 1 -> row store
+template <int G>
+B200_HD void br_inv_a(const BrSmem<G>& sm, int g, int q, int lane, int l)
+{
+    uint32_t x[32];
+    uint32_t* t = sm.tile(g, q * LIMBS + l);
+    tile_load_row(t, x, lane);
+    inv_pass1(x, sm.tw2i, lane);
+    tile_store_row(t, x, lane);
+}
+// Ib(l): column load -> inverse pass 2 -> centred lift -> sum += v << (11*l)
+template <int G>
+B200_HD void br_inv_b(const BrSmem<G>& sm, int g, int q, int lane, int l, uint32_t (&sum)[32])
+{
+    uint32_t x[32];
+    tile_load_col(sm.tile(g, q * LIMBS + l), x, lane);
+    inv_pass2(x);
+    B200_UNROLL
+    for (int a = 0; a < 32; a++) {
+        const uint32_t v = (uint32_t)centered_lift(x[a]);
+        sum[a] = (l == 0) ? v : sum[a] + (v << (LIMB_BITS * l));
+    }
+}
+// Ic: acc += external product; refresh the shared copy used by the next rotated read
+template <int G>
+B200_HD void br_acc_update(const BrSmem<G>& sm, int g, int q, int lane, const uint32_t (&sum)[32],
+                           uint32_t (&accr)[32])
+{
+    uint32_t* acc = sm.acc(g, q);
+    B200_UNROLL
+    for (int a = 0; a < 32; a++) {
+        accr[a] += sum[a];
+        acc[32 * a + lane] = accr[a];
+    }
+}
+
+// ---- epilogue: SampleExtractIndex(0) (trlwe.hpp:213-223) into the lvl1 scratch buffer -----
+template <int G>
+B200_HD void br_epilogue(const BrSmem<G>& sm, int g, int q, int lane, uint32_t* u_out)
+{
+    const uint32_t* acc = sm.acc(g, q);
+    if (q == 0) {
+        for (int j = lane; j < N1; j += 32) u_out[j] = (j == 0) ? acc[0] : 0u - acc[N1 - j];
+    } else if (lane == 0) {
+        u_out[N1] = acc[0];
+    }
+}
+
+// ---- bootstrapping-key precomputation (once per key) ------------------------------------
+// Prior art: cuFHE __TRGSW2NTT__ (src/bootstrap_gpu.cu:45-53).  One warp per (i, row, poly, limb):
+// centred 11/11/10-bit limb of the raw uint32 key polynomial -> forward NTT -> * 2^32/N -> [0,p).
+B200_HD int32_t bk_limb(uint32_t raw, int limb)
+{
+    // raw = x0 + 2^11*x1 + 2^22*x2 (mod 2^32), x0,x1 in [-1024,1023], x2 in [-512,512]
+    uint32_t v = raw;
+    const int32_t x0 = (int32_t)((v & 2047u) ^ 1024u) - 1024;
+    v = (uint32_t)((int32_t)(v - (uint32_t)x0) >> LIMB_BITS);
+    const int32_t x1 = (int32_t)((v & 2047u) ^ 1024u) - 1024;
+    v = (uint32_t)((int32_t)(v - (uint32_t)x1) >> LIMB_BITS);
+    return limb == 0 ? x0 : (limb == 1 ? x1 : (int32_t)v);
+}
+B200_HD void bk_prep_a(const uint32_t* raw_poly, int limb, int lane, uint32_t* tile)
+{
+    uint32_t x[32];
+    B200_UNROLL
+    for (int a = 0; a < 32; a++) {
+        const int32_t v = bk_limb(raw_poly[32 * a + lane], limb);
+        x[a] = (uint32_t)(v + (int32_t)P);  // in (0, 2p)
+    }
+    fwd_pass1(x);
+    tile_store_col(tile, x, lane);
+}
+B200_HD void bk_prep_b(const uint32_t* tile, const tw_t* tw2f, tw_t scale, int lane, uint32_t* out_poly)
+{
+    uint32_t x[32];
+    tile_load_row(tile, x, lane);
+    fwd_pass2(x, tw2f, lane);
+    B200_UNROLL
+    for (int b = 0; b < 32; b++) out_poly[32 * lane + b] = reduce_full(shoup_mul(x[b], scale));
+}
+
+}  // namespace b200

@@ -1,0 +1,83 @@
+// Per-thread phases of the batched identity key switch lvl1 -> lvl0 and of the bootstrap-free ops.
+//
+// Reference: IdentityKeySwitch<lvl10param>, TFHEpp include/keyswitch.hpp:11-52
+//   res[n] = (b + 2^15) >> 16;  for each of the 1024 a_i: abar = a_i + 2^17, seven base-4 digits,
+//   every non-zero digit g subtracts row ksk[i][j][g-1][0..n] (uint16 wrap).
+// plus the MUX tail (gate.hpp:256-260): the two extracted lvl1 samples are added before the key
+// switch and mu_lvl0 is added to b afterwards.
+// Prior art: cuFHE KeySwitch (include/keyswitch_gpu.cuh:12-61), 1 thread per output coefficient.
+//
+// B200 mapping: one CTA per gate, thread k owns the 32-bit word holding output coefficients
+// 2k and 2k+1; rows are 1280-byte aligned so a warp reads 128 contiguous bytes per row.
+// The two uint16 lanes are accumulated in two 32-bit registers (low halves add exactly
+// modulo 2^16 inside a 32-bit add), so a row costs one load and two integer ops per thread.
+#pragma once
+#include "fhe_params.h"
+#include "hd.h"
+
+namespace b200 {
+
+constexpr int KS_THREADS = SLOT_STRIDE / 2;  // 320 threads, one 32-bit word (2 coefficients) each
+constexpr uint32_t KS_NONE = 0xFFFFFFFFu;
+
+struct KsJob {
+    uint32_t u0, u1;   // indices into the lvl1 scratch buffer; u1 = KS_NONE unless MUX
+    uint32_t out;      // arena slot
+    uint32_t post;     // added to b after the switch, modulo 2^16 (mu_lvl0 for MUX)
+};
+
+// phase 1: 14-bit digit code of coefficient i (bits 31..18 of a_i + 2^17)
+B200_HD uint16_t ks_code(const uint32_t* ubuf, const KsJob& job, int i)
+{
+    uint32_t u = ubuf[(size_t)job.u0 * U_STRIDE + i];
+    if (job.u1 != KS_NONE) u += ubuf[(size_t)job.u1 * U_STRIDE + i];
+    return (uint16_t)((u + (1u << (32 - 1 - KS_T * KS_BASEBIT))) >> (32 - KS_T * KS_BASEBIT));
+}
+
+B200_HD uint32_t ks_b_rounded(const uint32_t* ubuf, const KsJob& job)
+{
+    uint32_t b = ubuf[(size_t)job.u0 * U_STRIDE + N1];
+    if (job.u1 != KS_NONE) b += ubuf[(size_t)job.u1 * U_STRIDE + N1];
+    return ((b + (1u << 15)) >> 16) & 0xFFFFu;
+}
+
+// phase 2: thread k accumulates its word of every selected row.
+// ksk_words: [1024][7][3][320] uint32 (row padded to 640 uint16).
+B200_HD uint32_t ks_accumulate(const uint32_t* ksk_words, const uint16_t* codes, uint32_t b_rounded,
+                               uint32_t post, int k)
+{
+    uint32_t lo = 0, hi = 0;
+    for (int i = 0; i < N1; i++) {
+        const uint32_t code = codes[i];
+        B200_UNROLL
+        for (int j = 0; j < KS_T; j++) {
+            const uint32_t g = (code >> (2 * (KS_T - 1 - j))) & 3u;
+            const uint32_t* row = ksk_words + (size_t)((i * KS_T + j) * 3 + (g ? g - 1 : 0)) * KS_THREADS;
+            const uint32_t w = g ? row[k] : 0u;
+            lo += w;
+            hi += w >> 16;
+        }
+    }
+    uint32_t r_lo = 0u - lo, r_hi = 0u - hi;
+    if (k == N0 / 2) r_lo += b_rounded + post;  // coefficient 636 = b lives in the low half of word 318
+    return (r_lo & 0xFFFFu) | (r_hi << 16);
+}
+
+// ---- bootstrap-free ops: NOT / COPY / CONST (gate.hpp:32-57) and the DFF tick (iyokan.hpp:1395-1402)
+struct UnaryJob {
+    uint32_t src, dst;
+    uint32_t op;  // OP_NOT, OP_COPY, OP_CONST0, OP_CONST1
+};
+B200_HD uint32_t unary_word(const UnaryJob& job, const uint32_t* arena_words, int k)
+{
+    const uint32_t w = (job.op == OP_NOT || job.op == OP_COPY) ? arena_words[(size_t)job.src * KS_THREADS + k] : 0u;
+    if (job.op == OP_COPY) return w;
+    if (job.op == OP_NOT) {
+        const uint32_t lo = (0u - w) & 0xFFFFu, hi = (0u - (w >> 16)) & 0xFFFFu;
+        return lo | (hi << 16);
+    }
+    const uint32_t b = (job.op == OP_CONST1) ? MU0 : ((0u - MU0) & 0xFFFFu);
+    return (k == N0 / 2) ? b : 0u;
+}
+
+}  // namespace b200

@@ -1,0 +1,222 @@
+// Warp-level 1024-point negacyclic NTT over Z_p (p = 536856577), 32 points per lane.
+//
+// Replaces, for the gate-bootstrap path, the reference's polynomial multipliers:
+//   CPU : TwistIFFT/TwistFFT -> spqlios double-precision FFT (TFHEpp include/mulfft.hpp:69-134)
+//   GPU : NTT1024/NTTInv1024 over 2^64-2^32+1, 128 threads x 8 points, 4 block-synchronised passes
+//         (cuFHE include/ntt_gpu/ntt_1024_device.cuh:139-204)
+// B200 design: ONE warp owns a whole polynomial.  The merged (twist-free) Cooley-Tukey /
+// Gentleman-Sande negacyclic transform is split 32 x 32: five radix-2 stages run entirely in
+// registers, one transpose goes through a warp-private padded shared-memory tile (only
+// __syncwarp, never __syncthreads), five more stages run in registers.  Butterflies use
+// Shoup/Harvey lazy arithmetic in [0, 8p): 3 integer multiplies + 2 adds, with a range fix
+// (shift + multiply-add) on the sum path only every third (forward) / second (inverse) stage.
+//
+// Index conventions (array position j = 32*a + b, a = j >> 5, b = j & 31):
+//   forward : input natural order, output "bit-reversed" order (positions are only ever
+//             consumed position-wise by the pointwise stage and by the inverse).
+//             stage s (0..9): pairs (j, j + t), t = 512 >> s, twiddle psi_rev[2^s + (j >> (10-s))]
+//             pass 1 = stages 0..4, lane = b, registers indexed by a  (twiddles lane-independent)
+//             pass 2 = stages 5..9, lane = a, registers indexed by b  (twiddles lane-dependent)
+//   inverse : exactly the reverse stage order with inverse twiddles; the 1/N factor is folded
+//             into the bootstrapping-key precomputation.
+// Tile layout in shared memory: element (a, b) at word a*36 + b  (row padding 32 -> 36 words keeps
+// both the column-wise 32-bit accesses and the row-wise 128-bit accesses bank-conflict free).
+#pragma once
+#include "hd.h"
+#include "modarith.h"
+
+namespace b200 {
+
+constexpr int TILE_ROW = 36;                 // padded row pitch in words
+constexpr int TILE_WORDS = 32 * TILE_ROW;    // 1152 words = 4608 B per polynomial tile
+constexpr int TW2_LEN = 31 * 32;             // lane-dependent twiddles per direction
+
+B200_HD int tile_idx(int a, int b) { return a * TILE_ROW + b; }
+B200_HD int tile_of_j(int j) { return (j >> 5) * TILE_ROW + (j & 31); }
+
+// ---- twiddle storage -------------------------------------------------------------------
+// psi_rev index idx < 32  : lane-independent, __constant__ on the device
+// psi_rev index idx >= 32 : lane-dependent, table tw2[((2^(s-5) - 1) + h) * 32 + lane] = psi_rev[2^s + lane*2^(s-5) + h]
+struct NttTables {
+    tw_t fwd[1024];      // psi_rev[idx]      (idx 1..1023)
+    tw_t inv[1024];      // psi_rev[idx]^-1
+    tw_t tw2f[TW2_LEN];  // lane-dependent forward table
+    tw_t tw2i[TW2_LEN];  // lane-dependent inverse table
+    tw_t bk_scale;       // 2^32 * N^-1 mod p: folded into the NTT-domain bootstrapping key
+};
+
+inline tw_t h_twf_u[32];
+inline tw_t h_twi_u[32];
+#if defined(__CUDACC__)
+__constant__ tw_t c_twf_u[32];
+__constant__ tw_t c_twi_u[32];
+#endif
+
+B200_HD tw_t twf_u(int idx)
+{
+#if defined(__CUDA_ARCH__)
+    return c_twf_u[idx];
+#else
+    return h_twf_u[idx];
+#endif
+}
+B200_HD tw_t twi_u(int idx)
+{
+#if defined(__CUDA_ARCH__)
+    return c_twi_u[idx];
+#else
+    return h_twi_u[idx];
+#endif
+}
+
+inline uint32_t bitrev10(uint32_t x)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < 10; i++) r |= ((x >> i) & 1u) << (9 - i);
+    return r;
+}
+
+// Build all tables on the host (also fills h_twf_u / h_twi_u used by the CPU simulator).
+inline void ntt_tables_init(NttTables& t)
+{
+    for (uint32_t idx = 0; idx < 1024; idx++) {
+        const uint32_t w = mod_pow(PSI, bitrev10(idx));
+        t.fwd[idx] = make_tw(w);
+        t.inv[idx] = make_tw(mod_inv(w));
+    }
+    for (int idx = 0; idx < 32; idx++) {
+        h_twf_u[idx] = t.fwd[idx];
+        h_twi_u[idx] = t.inv[idx];
+    }
+    for (int ls = 0; ls < 5; ls++)          // global stage s = 5 + ls
+        for (int h = 0; h < (1 << ls); h++)
+            for (int lane = 0; lane < 32; lane++) {
+                const int idx = (32 << ls) + (lane << ls) + h;
+                const int pos = ((1 << ls) - 1 + h) * 32 + lane;
+                t.tw2f[pos] = t.fwd[idx];
+                t.tw2i[pos] = t.inv[idx];
+            }
+    const uint32_t two32 = (uint32_t)((1ull << 32) % P);
+    t.bk_scale = make_tw(mod_mul(two32, mod_inv(1024)));
+}
+
+// ---- register stages -------------------------------------------------------------------
+// One radix-2 stage over the 32 registers of a lane.  LS = local stage 0..4: pairs (i, i + half),
+// half = 16 >> LS, arranged in 2^LS groups that share a twiddle.  tw(g) returns the group twiddle.
+template <int LS, bool FIX, class TwFn>
+B200_HD void ct_stage(uint32_t (&x)[32], TwFn tw)
+{
+    constexpr int half = 16 >> LS;
+    B200_UNROLL
+    for (int g = 0; g < (1 << LS); g++) {
+        const tw_t w = tw(g);
+        B200_UNROLL
+        for (int k = 0; k < half; k++) {
+            const int i0 = g * 2 * half + k, i1 = i0 + half;
+            uint32_t X = x[i0];
+            if (FIX) X = fix29(X);
+            const uint32_t T = shoup_mul(x[i1], w);
+            x[i0] = X + T;
+            x[i1] = X - T + P2;
+        }
+    }
+}
+
+template <int LS, bool FIX, class TwFn>
+B200_HD void gs_stage(uint32_t (&x)[32], TwFn tw)
+{
+    constexpr int half = 16 >> LS;
+    B200_UNROLL
+    for (int g = 0; g < (1 << LS); g++) {
+        const tw_t w = tw(g);
+        B200_UNROLL
+        for (int k = 0; k < half; k++) {
+            const int i0 = g * 2 * half + k, i1 = i0 + half;
+            const uint32_t U = x[i0], V = x[i1];
+            uint32_t S = U + V;
+            if (FIX) S = fix29(S);
+            x[i0] = S;
+            x[i1] = shoup_mul(U - V + P4, w);
+        }
+    }
+}
+
+// Forward pass 1: global stages 0..4.  Input < p + 64 per element; output < 5p + 8c.
+// (bounds: stage0 <3p, stage1 <5p, stage2 <7p, fix before stage3 -> <3p+8c, stage4 <5p+8c)
+B200_HD void fwd_pass1(uint32_t (&x)[32])
+{
+    ct_stage<0, false>(x, [](int g) { return twf_u(1 + g); });
+    ct_stage<1, false>(x, [](int g) { return twf_u(2 + g); });
+    ct_stage<2, false>(x, [](int g) { return twf_u(4 + g); });
+    ct_stage<3, true>(x, [](int g) { return twf_u(8 + g); });
+    ct_stage<4, false>(x, [](int g) { return twf_u(16 + g); });
+}
+
+// Forward pass 2: global stages 5..9, lane-dependent twiddles read from tw2 (shared memory on
+// the device).  Input < 5p+8c; stage5 <7p+8c, fix before stage6 -> <3p+8c, stage7 <5p+8c,
+// stage8 <7p+8c, fix before stage9 -> output < 3p + 8c.
+B200_HD void fwd_pass2(uint32_t (&x)[32], const tw_t* tw2, int lane)
+{
+    ct_stage<0, false>(x, [=](int g) { return tw2[(0 + g) * 32 + lane]; });
+    ct_stage<1, true>(x, [=](int g) { return tw2[(1 + g) * 32 + lane]; });
+    ct_stage<2, false>(x, [=](int g) { return tw2[(3 + g) * 32 + lane]; });
+    ct_stage<3, false>(x, [=](int g) { return tw2[(7 + g) * 32 + lane]; });
+    ct_stage<4, true>(x, [=](int g) { return tw2[(15 + g) * 32 + lane]; });
+}
+
+// Inverse pass 1: global stages 9..5 (lane-dependent).  Input < 4p.
+// Sum-path bounds: stage9 <8p -> fix -> <p+8c | stage8 in<=2p: <4p | stage7 <8p -> fix |
+// stage6 <4p | stage5 <8p -> fix.  Product path is always < 2p.  Output < 2p.
+B200_HD void inv_pass1(uint32_t (&x)[32], const tw_t* tw2, int lane)
+{
+    gs_stage<4, true>(x, [=](int g) { return tw2[(15 + g) * 32 + lane]; });
+    gs_stage<3, false>(x, [=](int g) { return tw2[(7 + g) * 32 + lane]; });
+    gs_stage<2, true>(x, [=](int g) { return tw2[(3 + g) * 32 + lane]; });
+    gs_stage<1, false>(x, [=](int g) { return tw2[(1 + g) * 32 + lane]; });
+    gs_stage<0, true>(x, [=](int g) { return tw2[(0 + g) * 32 + lane]; });
+}
+
+// Inverse pass 2: global stages 4..0 (lane-independent).  Input < 2p.
+// stage4 <4p | stage3 <8p -> fix | stage2 <4p | stage1 <8p -> fix | stage0 <4p.  Output < 4p.
+B200_HD void inv_pass2(uint32_t (&x)[32])
+{
+    gs_stage<4, false>(x, [](int g) { return twi_u(16 + g); });
+    gs_stage<3, true>(x, [](int g) { return twi_u(8 + g); });
+    gs_stage<2, false>(x, [](int g) { return twi_u(4 + g); });
+    gs_stage<1, true>(x, [](int g) { return twi_u(2 + g); });
+    gs_stage<0, false>(x, [](int g) { return twi_u(1 + g); });
+}
+
+// ---- tile access -----------------------------------------------------------------------
+// column access: register index = a, lane = b  (32-bit, conflict free)
+B200_HD void tile_store_col(uint32_t* tile, const uint32_t (&x)[32], int lane)
+{
+    B200_UNROLL
+    for (int a = 0; a < 32; a++) tile[tile_idx(a, lane)] = x[a];
+}
+B200_HD void tile_load_col(const uint32_t* tile, uint32_t (&x)[32], int lane)
+{
+    B200_UNROLL
+    for (int a = 0; a < 32; a++) x[a] = tile[tile_idx(a, lane)];
+}
+// row access: register index = b, lane = a  (128-bit, conflict free thanks to the 36-word pitch)
+B200_HD void tile_store_row(uint32_t* tile, const uint32_t (&x)[32], int lane)
+{
+    u32x4* row = reinterpret_cast<u32x4*>(tile + lane * TILE_ROW);
+    B200_UNROLL
+    for (int k = 0; k < 8; k++) row[k] = u32x4{x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]};
+}
+B200_HD void tile_load_row(const uint32_t* tile, uint32_t (&x)[32], int lane)
+{
+    const u32x4* row = reinterpret_cast<const u32x4*>(tile + lane * TILE_ROW);
+    B200_UNROLL
+    for (int k = 0; k < 8; k++) {
+        const u32x4 v = row[k];
+        x[4 * k] = v.x;
+        x[4 * k + 1] = v.y;
+        x[4 * k + 2] = v.z;
+        x[4 * k + 3] = v.w;
+    }
+}
+
+}  // namespace b200

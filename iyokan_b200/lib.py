@@ -1,0 +1,249 @@
+"""ctypes binding of the C ABI in ``include/b200fhe.h`` (built from ``csrc/b200fhe.cu``).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``iyokan_b200.build.build()`` as
+``iyokan_b200/csrc/libb200fhe.so``.  There is NO fallback: if the shared library is missing or
+no sm_100a GPU is present, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from pathlib import Path
+
+import numpy as np
+
+CSRC = Path(__file__).resolve().parent / "csrc"
+LIB_PATH = CSRC / "libb200fhe.so"
+
+N0, N1 = 636, 1024
+TLWE0_LEN, TLWE1_LEN = 637, 1025
+BK_SHAPE = (636, 6, 2, 1024)        # raw TRGSW bootstrapping key, uint32
+KSK_SHAPE = (1024, 7, 3, 637)       # identity key-switching key, uint16
+BK_NTT_SHAPE = (636, 6, 6, 1024)    # device form: [i][poly*3+limb][row][position]
+
+OPS = {
+    "AND": 0, "NAND": 1, "ANDNOT": 2, "OR": 3, "NOR": 4, "ORNOT": 5, "XOR": 6, "XNOR": 7,
+    "MUX": 8, "NOT": 9, "COPY": 10, "CONST0": 11, "CONST1": 12, "ANDNY": 13, "ORNY": 14,
+}
+# gate bootstraps (blind rotations) per opcode: SURVEY.md §8(d)
+BOOTSTRAPS = {op: (2 if name == "MUX" else 0 if name in ("NOT", "COPY", "CONST0", "CONST1") else 1)
+              for name, op in OPS.items()}
+
+
+class B200FheError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load libb200fhe.so; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise B200FheError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = ctypes.CDLL(str(LIB_PATH))
+    vp, u64, sz, ci = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_int
+    sig = {
+        "b200fhe_create": (ci, [ctypes.POINTER(vp), ci]),
+        "b200fhe_destroy": (None, [vp]),
+        "b200fhe_last_error": (ctypes.c_char_p, []),
+        "b200fhe_set_jobs_per_cta": (ci, [vp, ci]),
+        "b200fhe_load_keys": (ci, [vp, vp, vp]),
+        "b200fhe_arena_alloc": (ci, [vp, sz]),
+        "b200fhe_arena_attach": (ci, [vp, vp, sz]),
+        "b200fhe_arena_slots": (sz, [vp]),
+        "b200fhe_arena_dev_ptr": (vp, [vp]),
+        "b200fhe_upload": (ci, [vp, vp, vp, sz]),
+        "b200fhe_download": (ci, [vp, vp, vp, sz]),
+        "b200fhe_gate_batch": (ci, [vp, vp, vp, vp, vp, vp, sz]),
+        "b200fhe_dff_tick": (ci, [vp, vp, vp, sz]),
+        "b200fhe_sync": (ci, [vp]),
+        "b200fhe_query": (ci, [vp]),
+        "b200fhe_gates_host": (ci, [vp, vp, vp, vp, vp, vp, sz]),
+        "b200fhe_host_alloc": (ci, [ctypes.POINTER(vp), sz]),
+        "b200fhe_host_free": (ci, [vp]),
+        "b200fhe_launch_count": (u64, [vp]),
+        "b200fhe_last_batch_ms": (ci, [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
+        "b200fhe_stream": (vp, [vp]),
+        "b200fhe_test_bootstrap_lvl1": (ci, [vp, vp, vp, sz]),
+        "b200fhe_test_keyswitch": (ci, [vp, vp, vp, sz]),
+        "b200fhe_test_read_bk_ntt": (ci, [vp, vp, sz, sz]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+EXPORTS = [
+    "b200fhe_create", "b200fhe_destroy", "b200fhe_last_error", "b200fhe_set_jobs_per_cta", "b200fhe_load_keys",
+    "b200fhe_arena_alloc", "b200fhe_arena_attach", "b200fhe_arena_slots", "b200fhe_arena_dev_ptr",
+    "b200fhe_upload", "b200fhe_download", "b200fhe_gate_batch", "b200fhe_dff_tick", "b200fhe_sync",
+    "b200fhe_query", "b200fhe_gates_host", "b200fhe_host_alloc", "b200fhe_host_free", "b200fhe_launch_count",
+    "b200fhe_last_batch_ms", "b200fhe_stream", "b200fhe_test_bootstrap_lvl1", "b200fhe_test_keyswitch",
+    "b200fhe_test_read_bk_ntt",
+]
+
+
+def _ptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _u32(a, n=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    if n is not None and a.size != n:
+        raise ValueError("slot id array has the wrong length")
+    return a
+
+
+class PinnedBuffer:
+    """Page-locked host array (cudaHostAlloc through the C ABI)."""
+
+    def __init__(self, shape, dtype):
+        lib = load()
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = ctypes.c_void_p()
+        if lib.b200fhe_host_alloc(ctypes.byref(p), nbytes):
+            raise B200FheError(lib.b200fhe_last_error().decode())
+        self._p = p
+        buf = (ctypes.c_uint8 * nbytes).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def free(self):
+        if self._p is not None:
+            self.array = None
+            load().b200fhe_host_free(self._p)
+            self._p = None
+
+
+class Context:
+    """One GPU's evaluation context: keys, ciphertext arena, stream."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        h = ctypes.c_void_p()
+        if self._lib.b200fhe_create(ctypes.byref(h), device):
+            raise B200FheError(self._lib.b200fhe_last_error().decode())
+        self._h = h
+        self.device = device
+
+    def _ck(self, rc):
+        if rc:
+            raise B200FheError(self._lib.b200fhe_last_error().decode())
+
+    def close(self):
+        if self._h is not None:
+            self._lib.b200fhe_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_jobs_per_cta(self, g: int):
+        self._ck(self._lib.b200fhe_set_jobs_per_cta(self._h, g))
+
+    def load_keys(self, bk_raw: np.ndarray, ksk: np.ndarray):
+        bk_raw = np.ascontiguousarray(bk_raw, dtype=np.uint32)
+        ksk = np.ascontiguousarray(ksk, dtype=np.uint16)
+        if bk_raw.size != int(np.prod(BK_SHAPE)) or ksk.size != int(np.prod(KSK_SHAPE)):
+            raise ValueError("key arrays have the wrong size for the 128-bit parameter set")
+        self._ck(self._lib.b200fhe_load_keys(self._h, _ptr(bk_raw), _ptr(ksk)))
+
+    def arena_alloc(self, n_slots: int):
+        self._ck(self._lib.b200fhe_arena_alloc(self._h, n_slots))
+
+    def arena_attach(self, dev_ptr: int, n_slots: int):
+        self._ck(self._lib.b200fhe_arena_attach(self._h, ctypes.c_void_p(dev_ptr), n_slots))
+
+    @property
+    def arena_slots(self) -> int:
+        return int(self._lib.b200fhe_arena_slots(self._h))
+
+    @property
+    def arena_dev_ptr(self) -> int:
+        return int(self._lib.b200fhe_arena_dev_ptr(self._h) or 0)
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.b200fhe_stream(self._h) or 0)
+
+    def upload(self, slot_ids, tlwe: np.ndarray):
+        ids = _u32(slot_ids)
+        tlwe = np.ascontiguousarray(tlwe, dtype=np.uint16)
+        if tlwe.size != ids.size * TLWE0_LEN:
+            raise ValueError("tlwe array must be [n][637] uint16")
+        self._ck(self._lib.b200fhe_upload(self._h, _ptr(ids), _ptr(tlwe), ids.size))
+        self.sync()  # the source may be pageable numpy memory
+
+    def download(self, slot_ids, out: np.ndarray | None = None) -> np.ndarray:
+        ids = _u32(slot_ids)
+        if out is None:
+            out = np.empty((ids.size, TLWE0_LEN), np.uint16)
+        self._ck(self._lib.b200fhe_download(self._h, _ptr(ids), _ptr(out), ids.size))
+        return out
+
+    def gate_batch(self, opcode, in0, in1, in2, out):
+        op = np.ascontiguousarray(opcode, dtype=np.uint8)
+        n = op.size
+        self._ck(self._lib.b200fhe_gate_batch(self._h, _ptr(op), _ptr(_u32(in0, n)), _ptr(_u32(in1, n)),
+                                               _ptr(_u32(in2, n)), _ptr(_u32(out, n)), n))
+
+    def dff_tick(self, src, dst):
+        s, d = _u32(src), _u32(dst, None)
+        if s.size != d.size:
+            raise ValueError("src/dst length mismatch")
+        self._ck(self._lib.b200fhe_dff_tick(self._h, _ptr(s), _ptr(d), s.size))
+
+    def sync(self):
+        self._ck(self._lib.b200fhe_sync(self._h))
+
+    def query(self) -> int:
+        return int(self._lib.b200fhe_query(self._h))
+
+    def gates_host(self, opcode, in0, in1, in2, out: np.ndarray | None = None) -> np.ndarray:
+        op = np.ascontiguousarray(opcode, dtype=np.uint8)
+        n = op.size
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.uint16) for a in (in0, in1, in2)]
+        if out is None:
+            out = np.empty((n, TLWE0_LEN), np.uint16)
+        self._ck(self._lib.b200fhe_gates_host(self._h, _ptr(op), _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]),
+                                               _ptr(out), n))
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.b200fhe_launch_count(self._h))
+
+    def last_batch_ms(self):
+        a, b = ctypes.c_float(), ctypes.c_float()
+        self._ck(self._lib.b200fhe_last_batch_ms(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    # ---- stage-level test hooks ----
+    def test_bootstrap_lvl1(self, c: np.ndarray) -> np.ndarray:
+        c = np.ascontiguousarray(c, dtype=np.uint16).reshape(-1, TLWE0_LEN)
+        out = np.empty((c.shape[0], TLWE1_LEN), np.uint32)
+        self._ck(self._lib.b200fhe_test_bootstrap_lvl1(self._h, _ptr(c), _ptr(out), c.shape[0]))
+        return out
+
+    def test_keyswitch(self, u: np.ndarray) -> np.ndarray:
+        u = np.ascontiguousarray(u, dtype=np.uint32).reshape(-1, TLWE1_LEN)
+        out = np.empty((u.shape[0], TLWE0_LEN), np.uint16)
+        self._ck(self._lib.b200fhe_test_keyswitch(self._h, _ptr(u), _ptr(out), u.shape[0]))
+        return out
+
+    def test_read_bk_ntt(self, first_i: int, count_i: int) -> np.ndarray:
+        out = np.empty((count_i,) + BK_NTT_SHAPE[1:], np.uint32)
+        self._ck(self._lib.b200fhe_test_read_bk_ntt(self._h, _ptr(out), first_i, count_i))
+        return out

@@ -41,6 +41,14 @@ def plain_gate(op: int, a, b, c):
     return table[int(op)].astype(np.uint8)
 
 
+def plain_gate_vec(ops, a, b, c) -> np.ndarray:
+    ops = np.asarray(ops, dtype=np.uint8)
+    out = np.empty(ops.size, np.uint8)
+    for i, op in enumerate(ops):
+        out[i] = plain_gate(op, a[i], b[i], c[i])
+    return out
+
+
 def build(force: bool = False) -> None:
     """Compile the C restatement (and the reference driver when the reference tree exists)."""
     if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < (HERE / "tfhe_oracle.c").stat().st_mtime:

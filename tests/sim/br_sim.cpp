@@ -1,0 +1,205 @@
+// Lock-step CPU simulator of the CUDA kernels (test infrastructure for the "not gpu" suite).
+//
+// It includes the very same per-thread phase functions the sm_100a kernels are built from
+// (iyokan_b200/csrc/{ntt_warp,br_phases,ks_phases}.h) and runs them thread by thread, phase by
+// phase, with a plain byte array standing in for shared memory.  Because no phase function
+// communicates across threads except through that array between phases, this reproduces the
+// kernel's arithmetic, index math and data layout exactly; what it cannot catch are missing
+// barriers, which the GPU parity tests cover.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../iyokan_b200/csrc/br_phases.h"
+#include "../../iyokan_b200/csrc/ks_phases.h"
+
+using namespace b200;
+
+static NttTables g_tab;
+static bool g_init = false;
+
+extern "C" void sim_init()
+{
+    if (!g_init) {
+        ntt_tables_init(g_tab);
+        g_init = true;
+    }
+}
+
+// forward NTT of 1024 residues (natural order in, tile order out: position j = 32a+b at out[j])
+static void warp_forward(const uint32_t* in, uint32_t* out)
+{
+    std::vector<uint32_t> tile(TILE_WORDS);
+    for (int lane = 0; lane < 32; lane++) {
+        uint32_t x[32];
+        for (int a = 0; a < 32; a++) x[a] = in[32 * a + lane];
+        fwd_pass1(x);
+        tile_store_col(tile.data(), x, lane);
+    }
+    for (int lane = 0; lane < 32; lane++) {
+        uint32_t x[32];
+        tile_load_row(tile.data(), x, lane);
+        fwd_pass2(x, g_tab.tw2f, lane);
+        for (int b = 0; b < 32; b++) out[32 * lane + b] = x[b];
+    }
+}
+static void warp_inverse(const uint32_t* in, uint32_t* out)
+{
+    std::vector<uint32_t> tile(TILE_WORDS);
+    for (int lane = 0; lane < 32; lane++) {
+        uint32_t x[32];
+        for (int b = 0; b < 32; b++) x[b] = in[32 * lane + b];
+        inv_pass1(x, g_tab.tw2i, lane);
+        tile_store_row(tile.data(), x, lane);
+    }
+    for (int lane = 0; lane < 32; lane++) {
+        uint32_t x[32];
+        tile_load_col(tile.data(), x, lane);
+        inv_pass2(x);
+        for (int a = 0; a < 32; a++) out[32 * a + lane] = x[a];
+    }
+}
+
+// c = a (*) b in Z_p[X]/(X^1024+1) through the warp NTT; inputs in [0,p), output in [0,p)
+extern "C" void sim_negacyclic_mul_modp(const uint32_t* a, const uint32_t* b, uint32_t* c)
+{
+    sim_init();
+    std::vector<uint32_t> fa(N1), fb(N1), fc(N1);
+    warp_forward(a, fa.data());
+    warp_forward(b, fb.data());
+    const uint32_t ninv = mod_inv(1024);
+    for (int j = 0; j < N1; j++)
+        fc[j] = mod_mul(mod_mul(reduce_full(fa[j]), reduce_full(fb[j])), ninv);
+    warp_inverse(fc.data(), c);
+    for (int j = 0; j < N1; j++) c[j] = reduce_full(c[j]);
+}
+
+// max value seen at the output of forward / inverse transforms for worst-case-ish inputs
+extern "C" void sim_ntt_ranges(const uint32_t* in, uint32_t* fwd_max, uint32_t* inv_max)
+{
+    sim_init();
+    std::vector<uint32_t> f(N1), g(N1);
+    warp_forward(in, f.data());
+    uint32_t m = 0;
+    for (auto v : f) m = v > m ? v : m;
+    *fwd_max = m;
+    warp_inverse(in, g.data());
+    m = 0;
+    for (auto v : g) m = v > m ? v : m;
+    *inv_max = m;
+}
+
+// bk_raw [n_i][6][2][1024] -> bk_ntt [n_i][BK_COLS][ROWS][1024]
+extern "C" void sim_bk_prepare(const uint32_t* bk_raw, uint32_t* bk_ntt, int n_i)
+{
+    sim_init();
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < n_i; i++) {
+        std::vector<uint32_t> tile(TILE_WORDS);
+        for (int r = 0; r < ROWS; r++)
+            for (int q = 0; q < 2; q++)
+                for (int l = 0; l < LIMBS; l++) {
+                    const uint32_t* raw = bk_raw + ((size_t)(i * ROWS + r) * 2 + q) * N1;
+                    uint32_t* out = bk_ntt + ((size_t)(i * BK_COLS + q * LIMBS + l) * ROWS + r) * N1;
+                    for (int lane = 0; lane < 32; lane++) bk_prep_a(raw, l, lane, tile.data());
+                    for (int lane = 0; lane < 32; lane++) bk_prep_b(tile.data(), g_tab.tw2f, g_tab.bk_scale, lane, out);
+                }
+    }
+}
+
+template <int G>
+static void sim_br_cta(const BrJob* jobs, int njobs, int cta, const uint16_t* arena, const uint32_t* bk_ntt,
+                       uint32_t* ubuf, int n_iter)
+{
+    constexpr int T = 64 * G, W = 2 * G;
+    std::vector<uint8_t> smem(BrSmem<G>::BYTES + 16);
+    BrSmem<G> sm;
+    sm.carve(smem.data());
+    std::memcpy(sm.tw2f, g_tab.tw2f, sizeof(g_tab.tw2f));
+    std::memcpy(sm.tw2i, g_tab.tw2i, sizeof(g_tab.tw2i));
+    struct Regs {
+        uint32_t accr[32], dreg[32], sum[32];
+    };
+    std::vector<Regs> regs(T);
+    auto jobof = [&](int g) {
+        int j = cta * G + g;
+        return j < njobs ? j : njobs - 1;
+    };
+    for (int w = 0; w < W; w++)
+        for (int lane = 0; lane < 32; lane++)
+            br_prologue<G>(sm, jobs[jobof(w >> 1)], arena, w >> 1, w & 1, lane, regs[w * 32 + lane].accr);
+    for (int i = 0; i < n_iter; i++) {
+        for (int w = 0; w < W; w++) {
+            const int g = w >> 1, q = w & 1;
+            for (int lane = 0; lane < 32; lane++)
+                br_rotate_diff<G>(sm, i, g, q, lane, regs[w * 32 + lane].accr, regs[w * 32 + lane].dreg);
+            for (int d = 0; d < GL; d++) {
+                for (int lane = 0; lane < 32; lane++) br_fwd_a<G>(sm, g, q, lane, d, regs[w * 32 + lane].dreg);
+                for (int lane = 0; lane < 32; lane++) br_fwd_b<G>(sm, g, q, lane, d);
+            }
+        }
+        const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
+        for (int tid = 0; tid < T; tid++) br_pointwise<G>(sm, bk_i, tid);
+        for (int w = 0; w < W; w++) {
+            const int g = w >> 1, q = w & 1;
+            for (int l = 0; l < LIMBS; l++) {
+                for (int lane = 0; lane < 32; lane++) br_inv_a<G>(sm, g, q, lane, l);
+                for (int lane = 0; lane < 32; lane++) br_inv_b<G>(sm, g, q, lane, l, regs[w * 32 + lane].sum);
+            }
+            for (int lane = 0; lane < 32; lane++)
+                br_acc_update<G>(sm, g, q, lane, regs[w * 32 + lane].sum, regs[w * 32 + lane].accr);
+        }
+    }
+    for (int w = 0; w < W; w++) {
+        const int g = w >> 1, q = w & 1;
+        if (cta * G + g >= njobs) continue;
+        for (int lane = 0; lane < 32; lane++)
+            br_epilogue<G>(sm, g, q, lane, ubuf + (size_t)(cta * G + g) * U_STRIDE);
+    }
+}
+
+// jobs: packed BrJob array (16 bytes each); arena: uint16 [slots][640]; ubuf: uint32 [njobs][1028]
+extern "C" void sim_blind_rotate(int G, const void* jobs_raw, int njobs, const uint16_t* arena,
+                                 const uint32_t* bk_ntt, uint32_t* ubuf, int n_iter)
+{
+    sim_init();
+    const BrJob* jobs = reinterpret_cast<const BrJob*>(jobs_raw);
+    const int ncta = (njobs + G - 1) / G;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int cta = 0; cta < ncta; cta++) {
+        if (G == 1) sim_br_cta<1>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
+        else if (G == 2) sim_br_cta<2>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
+        else if (G == 4) sim_br_cta<4>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
+        else std::abort();
+    }
+}
+
+// ksk_dev: uint16 [1024][7][3][640]; jobs: packed KsJob (16 bytes each)
+extern "C" void sim_keyswitch(const void* jobs_raw, int njobs, const uint32_t* ubuf, const uint16_t* ksk_dev,
+                              uint16_t* arena)
+{
+    const KsJob* jobs = reinterpret_cast<const KsJob*>(jobs_raw);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int n = 0; n < njobs; n++) {
+        uint16_t codes[N1];
+        for (int i = 0; i < N1; i++) codes[i] = ks_code(ubuf, jobs[n], i);
+        const uint32_t b = ks_b_rounded(ubuf, jobs[n]);
+        uint32_t* out = reinterpret_cast<uint32_t*>(arena + (size_t)jobs[n].out * SLOT_STRIDE);
+        for (int k = 0; k < KS_THREADS; k++)
+            out[k] = ks_accumulate(reinterpret_cast<const uint32_t*>(ksk_dev), codes, b, jobs[n].post, k);
+    }
+}
+
+extern "C" void sim_unary(const void* jobs_raw, int njobs, uint16_t* arena)
+{
+    const UnaryJob* jobs = reinterpret_cast<const UnaryJob*>(jobs_raw);
+    for (int n = 0; n < njobs; n++) {
+        uint32_t tmp[KS_THREADS];
+        for (int k = 0; k < KS_THREADS; k++) tmp[k] = unary_word(jobs[n], reinterpret_cast<const uint32_t*>(arena), k);
+        std::memcpy(arena + (size_t)jobs[n].dst * SLOT_STRIDE, tmp, sizeof(tmp));
+    }
+}
+
+extern "C" int sim_sizeof_brjob() { return (int)sizeof(BrJob); }
+extern "C" int sim_sizeof_ksjob() { return (int)sizeof(KsJob); }
+extern "C" uint32_t sim_prime() { return P; }

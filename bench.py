@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — TFHE gate bootstraps / second on the batched HomNAND workload (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (TFHEpp)
+
+One "step" = one pass of the hot path over one batch of 8192 independent HomNAND gates
+(fresh lvl0 encryptions of seeded random bits, 128-bit parameters).  With N > 1 every rank
+evaluates its own batch (the path shards per gate with no data-path collective; keys replicated),
+so scaling is weak and `value` = N * 8192 * K / max-over-ranks time.
+
+`value`  : ciphertexts resident in HBM when the timed region starts, device-timed (CUDA events on
+           the library's stream), max over ranks.
+`e2e`    : the same metric through the C ABI call with HOST buffers (b200fhe_gates_host): per step
+           the two input arrays go host->device from pinned memory and the outputs come back.
+`roofline`: blind-rotation kernel only (the dominant kernel), algorithmic bytes per SURVEY.md §8(d).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+BATCH = 8192
+BK_BYTES_PER_ROTATION = 636 * 2 * 3 * 2 * 1024 * 8      # 62,521,344
+KS_BYTES_PER_SWITCH = 1024 * 7 * 3 * 637 * 2 * 3 // 4    # 6,849,024 expected rows touched
+BYTES_PER_BOOTSTRAP = BK_BYTES_PER_ROTATION + KS_BYTES_PER_SWITCH + 3 * 1274   # 69,374,190
+BR_KERNEL_BYTES_PER_JOB = BK_BYTES_PER_ROTATION + 2 * 1274 + 4100               # key stream + TLWE in + lvl1 out
+KEY_SEED = 20261017
+
+
+def measured_peak_hbm():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        exe = shutil.which("nvidia-smi")
+        if not exe:
+            return
+        self.proc = subprocess.Popen([exe, f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        # the load samples are the upper half of what we saw (idle samples bracket the region)
+        load = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(keys, rank: int, n: int):
+    import oracle as O
+
+    rng = np.random.default_rng(1000 + rank)
+    pa, pb = rng.integers(0, 2, n, dtype=np.uint8), rng.integers(0, 2, n, dtype=np.uint8)
+    return pa, pb, O.encrypt_bits(50 + 2 * rank, keys, pa), O.encrypt_bits(51 + 2 * rank, keys, pb)
+
+
+def cpu_reference_run(keys, n_gates: int, threads: int, repeat: int = 1):
+    """Time the UNMODIFIED reference (TFHEpp HomNAND, oracle/_ref/ref_driver) on the host cores."""
+    import oracle as O
+
+    if not O.have_ref():
+        return None
+    d = Path(tempfile.mkdtemp(prefix="b200fhe_ref_"))
+    try:
+        keys.save(d)
+        pa, pb, ca, cb = make_inputs(keys, 0, n_gates)
+        ca.tofile(d / "a.bin")
+        cb.tofile(d / "b.bin")
+        np.full(n_gates, O.OPS["NAND"], np.uint8).tofile(d / "ops.bin")
+        out = O.ref("gates", d, d / "ops.bin", d / "a.bin", d / "b.bin", "-", d / "o.bin", threads, repeat)
+        info = json.loads(out.strip().splitlines()[-1])
+        got = O.decrypt_bits(keys, np.fromfile(d / "o.bin", dtype=np.uint16).reshape(n_gates, 637))
+        info["bits_ok"] = bool(np.array_equal(got, 1 - (pa & pb)))
+        return info
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def cpu_port_run(keys, n_gates: int, threads: int):
+    """Fallback CPU baseline: the exact-integer oracle port (only when oracle/_ref is absent)."""
+    import oracle as O
+
+    pa, pb, ca, cb = make_inputs(keys, 0, n_gates)
+    ops = np.full(n_gates, O.OPS["NAND"], np.uint8)
+    t = time.time()
+    out = O.gate_batch(keys, ops, ca, cb, nthreads=threads)
+    sec = time.time() - t
+    ok = bool(np.array_equal(O.decrypt_bits(keys, out), 1 - (pa & pb)))
+    return {"gates": n_gates, "bootstraps": n_gates, "seconds": sec, "bootstraps_per_s": n_gates / sec,
+            "threads": threads, "bits_ok": ok}
+
+
+def run_reference(args, rank: int, world: int):
+    """--impl reference: rank 0 alone times the reference CPU path on a bounded sample per step."""
+    if rank != 0:
+        return
+    import oracle as O
+
+    keys = O.cached_keys(KEY_SEED)
+    cores = os.cpu_count() or 1
+    sample = max(cores * 8, 128)
+    if O.have_ref():
+        kind = "reference"
+        cpu_reference_run(keys, cores, cores)  # warm-up (page in keys, FFT tables)
+        t = time.time()
+        info = cpu_reference_run(keys, sample, cores, repeat=args.steps)
+        total_s = info["seconds"]
+        ok = info["bits_ok"]
+        del t
+    else:
+        kind = "port"
+        t = time.time()
+        ok = True
+        for _ in range(args.steps):
+            ok &= cpu_port_run(keys, sample, cores)["bits_ok"]
+        total_s = time.time() - t
+    value = sample * args.steps / total_s
+    line = {
+        "impl": "reference", "metric": "tfhe_gate_bootstraps_per_s", "value": value, "unit": "bootstraps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if kind == "reference" else "u32",
+        "data": "synthetic", "config": {"workload": "batched HomNAND, 128-bit params (n=636, N=1024)",
+                                         "batch": BATCH, "sample_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "bootstraps/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample} HomNAND gates per step x {args.steps} steps, {cores} host threads"},
+        "e2e": {"value": value, "unit": "bootstraps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "outputs_ok": bool(ok),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--jobs-per-cta", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import oracle as O  # checker + cpu_baseline leg only
+    from iyokan_b200 import Context, OPS, PinnedBuffer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.batch
+    keys = O.cached_keys(KEY_SEED)
+    pa, pb, ca, cb = make_inputs(keys, rank, n)
+
+    ctx = Context(local_rank)
+    if args.jobs_per_cta:
+        ctx.set_jobs_per_cta(args.jobs_per_cta)
+    ctx.load_keys(keys.bk, keys.ksk)
+    ctx.arena_alloc(4 * n)
+    ids = np.arange(4 * n, dtype=np.uint32)
+    ctx.upload(ids[:n], ca)
+    ctx.upload(ids[n:2 * n], cb)
+    ops = np.full(n, OPS["NAND"], np.uint8)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        ctx.gate_batch(ops, ids[:n], ids[n:2 * n], None, ids[3 * n:])
+
+    # host (pinned) buffers for the end-to-end arm
+    h_a, h_b, h_o = (PinnedBuffer((n, 637), np.uint16) for _ in range(3))
+    h_a.array[:] = ca
+    h_b.array[:] = cb
+
+    def step_e2e():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        ctx.gates_host(ops, h_a.array, h_b.array, None, out=h_o.array)
+
+    def timed(step_fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        br_ms = []
+        barrier()
+        ev0.record(stream)
+        for _ in range(steps):
+            step_fn()
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, br_ms
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    l0 = ctx.launch_count
+    ms_total, _ = timed(step_resident, args.steps)
+    launches = ctx.launch_count - l0
+    # per-launch duration of the dominant kernel, CUDA events on the launching stream
+    br_list, ks_list = [], []
+    for _ in range(min(args.steps, 5)):
+        step_resident()
+        ctx.sync()
+        a, b = ctx.last_batch_ms()
+        br_list.append(a)
+        ks_list.append(b)
+    clocks = sampler.stop() if rank == 0 else None
+
+    out_res = ctx.download(ids[3 * n:])
+    bits_ok = bool(np.array_equal(O.decrypt_bits(keys, out_res), 1 - (pa & pb)))
+    k = 4
+    exact_ok = bool(np.array_equal(out_res[:k], O.gate_batch(keys, ops[:k], ca[:k], cb[:k])))
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    e2e_ok = bool(np.array_equal(h_o.array, out_res))
+
+    if world > 1:
+        flags = torch.tensor([int(bits_ok and exact_ok and e2e_ok)], device="cuda")
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        all_ok = bool(flags.item())
+    else:
+        all_ok = bits_ok and exact_ok and e2e_ok
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        value = world * n * args.steps / (ms_total / 1e3)
+        br_ms = float(np.mean(br_list))
+        achieved = n * BR_KERNEL_BYTES_PER_JOB / (br_ms / 1e3) / 1e9
+        traffic = None
+        tp = ROOT / "profiles" / "br_kernel_traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "tfhe_gate_bootstraps_per_s", "value": value, "unit": "bootstraps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "batched HomNAND microbench: 8192 independent gate bootstraps per GPU, "
+                                   "128-bit params (n=636, N=1024, l=3, Bgbit=6, t=7) [BASELINE.json configs[1]]",
+                       "batch_per_gpu": n, "parallelism": f"replicated keys, {world} independent batch shard(s)",
+                       "l2": "256 MiB device memset between steps inside the timed region (L2 flush); "
+                             "working set keys+ciphertexts ~176 MB > 126 MB L2"},
+            "e2e": {"value": world * n * args.steps / (ms_e2e / 1e3), "unit": "bootstraps/s",
+                    "h2d_bytes_per_step": 2 * n * 1274, "d2h_bytes_per_step": n * 1274},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "br_kernel (blind rotation)", "peak_source": peak_src,
+                         "kernel_ms_per_launch": br_ms, "ks_kernel_ms_per_launch": float(np.mean(ks_list)),
+                         "algorithmic_bytes_per_launch": n * BR_KERNEL_BYTES_PER_JOB,
+                         "gate_model_frac": (value / world) * BYTES_PER_BOOTSTRAP / (peak * 1e9)},
+            "outputs_ok": all_ok,
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            sample = max(cores * 16, 256)
+            info = cpu_reference_run(keys, sample, cores)
+            kind = "reference"
+            if info is None:
+                info, kind = cpu_port_run(keys, max(cores * 2, 32), cores), "port"
+            line["cpu_baseline"] = {"value": info["bootstraps_per_s"], "unit": "bootstraps/s", "cores": cores,
+                                    "kind": kind, "bits_ok": info["bits_ok"],
+                                    "sample": f"{info['gates']} HomNAND gates of the same workload, {cores} host threads, "
+                                              f"{info['seconds']:.2f} s"}
+        print(json.dumps(line), flush=True)
+
+    for hb in (h_a, h_b, h_o):
+        hb.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -15,6 +15,7 @@
 
 #include "../../include/b200fhe.h"
 #include "br_phases.h"
+#include "gate_jobs.h"
 #include "ks_phases.h"
 
 using namespace b200;
@@ -394,24 +395,6 @@ int b200fhe_download(b200fhe_ctx* c, const uint32_t* ids, uint16_t* host, size_t
     return 0;
 }
 
-// (sa, sb, off/mu0) of HomGate, TFHEpp include/gate.hpp:59-230
-static bool gate_coef(uint8_t op, int& sa, int& sb, int& off)
-{
-    switch (op) {
-    case OP_NAND:   sa = -1; sb = -1; off = +1; return true;
-    case OP_NOR:    sa = -1; sb = -1; off = -1; return true;
-    case OP_XNOR:   sa = -2; sb = -2; off = -2; return true;
-    case OP_AND:    sa = +1; sb = +1; off = -1; return true;
-    case OP_OR:     sa = +1; sb = +1; off = +1; return true;
-    case OP_XOR:    sa = +2; sb = +2; off = +2; return true;
-    case OP_ANDNY:  sa = -1; sb = +1; off = -1; return true;
-    case OP_ANDNOT: sa = +1; sb = -1; off = -1; return true;
-    case OP_ORNY:   sa = -1; sb = +1; off = +1; return true;
-    case OP_ORNOT:  sa = +1; sb = -1; off = +1; return true;
-    default: return false;
-    }
-}
-
 int b200fhe_gate_batch(b200fhe_ctx* c, const uint8_t* opcode, const uint32_t* in0, const uint32_t* in1,
                        const uint32_t* in2, const uint32_t* out, size_t n)
 {
@@ -425,48 +408,10 @@ int b200fhe_gate_batch(b200fhe_ctx* c, const uint8_t* opcode, const uint32_t* in
         CK(cudaEventSynchronize(c->ev_staged));
         c->staged_pending = false;
     }
-    size_t nbr = 0, nks = 0, nun = 0;
-    auto slot = [&](const uint32_t* arr, size_t i, uint32_t& dst) -> bool {
-        if (!arr || arr[i] >= c->n_slots) return false;
-        dst = arr[i];
-        return true;
-    };
-    for (size_t i = 0; i < n; i++) {
-        const uint8_t op = opcode[i];
-        uint32_t o, a = 0, b = 0, s = 0;
-        if (!slot(out, i, o)) return fail("output slot out of range");
-        int sa, sb, off;
-        if (gate_coef(op, sa, sb, off)) {
-            if (!slot(in0, i, a) || !slot(in1, i, b)) return fail("input slot missing or out of range");
-            BrJob& j = c->h_br[nbr];
-            j.in[0] = a; j.in[1] = b; j.in[2] = 0;
-            j.sgn[0] = (int8_t)sa; j.sgn[1] = (int8_t)sb; j.sgn[2] = 0; j.pad = 0;
-            j.off = (uint32_t)(off * (int)MU0) & 0xFFFFu;
-            c->h_ks[nks++] = KsJob{(uint32_t)nbr, KS_NONE, o, 0u};
-            nbr++;
-        } else if (op == OP_MUX) {
-            // HomMUX(res, cs=in2, c1=in1, c0=in0), gate.hpp:236-240: (cs + c1 - mu), (-cs + c0 - mu)
-            if (!slot(in0, i, a) || !slot(in1, i, b) || !slot(in2, i, s))
-                return fail("input slot missing or out of range");
-            BrJob& j1 = c->h_br[nbr];
-            j1.in[0] = a; j1.in[1] = b; j1.in[2] = s;
-            j1.sgn[0] = 0; j1.sgn[1] = 1; j1.sgn[2] = 1; j1.pad = 0;
-            j1.off = (0u - MU0) & 0xFFFFu;
-            BrJob& j0 = c->h_br[nbr + 1];
-            j0.in[0] = a; j0.in[1] = b; j0.in[2] = s;
-            j0.sgn[0] = 1; j0.sgn[1] = 0; j0.sgn[2] = -1; j0.pad = 0;
-            j0.off = (0u - MU0) & 0xFFFFu;
-            c->h_ks[nks++] = KsJob{(uint32_t)nbr, (uint32_t)nbr + 1, o, MU0};
-            nbr += 2;
-        } else if (op == OP_NOT || op == OP_COPY) {
-            if (!slot(in0, i, a)) return fail("input slot missing or out of range");
-            c->h_un[nun++] = UnaryJob{a, o, op};
-        } else if (op == OP_CONST0 || op == OP_CONST1) {
-            c->h_un[nun++] = UnaryJob{0u, o, op};
-        } else {
-            return fail("unknown opcode");
-        }
-    }
+    BatchCounts cnt;
+    if (const char* err = build_gate_jobs(opcode, in0, in1, in2, out, n, c->n_slots, c->h_br, c->h_ks, c->h_un, cnt))
+        return fail(err);
+    const size_t nbr = cnt.nbr, nks = cnt.nks, nun = cnt.nun;
     if (nbr) CK(cudaMemcpyAsync(c->d_br, c->h_br, nbr * sizeof(BrJob), cudaMemcpyHostToDevice, c->stream));
     if (nks) CK(cudaMemcpyAsync(c->d_ks, c->h_ks, nks * sizeof(KsJob), cudaMemcpyHostToDevice, c->stream));
     if (nun) CK(cudaMemcpyAsync(c->d_un, c->h_un, nun * sizeof(UnaryJob), cudaMemcpyHostToDevice, c->stream));

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../iyokan_b200/csrc/br_phases.h"
+#include "../../iyokan_b200/csrc/gate_jobs.h"
 #include "../../iyokan_b200/csrc/ks_phases.h"
 
 using namespace b200;
@@ -198,6 +199,37 @@ extern "C" void sim_unary(const void* jobs_raw, int njobs, uint16_t* arena)
         for (int k = 0; k < KS_THREADS; k++) tmp[k] = unary_word(jobs[n], reinterpret_cast<const uint32_t*>(arena), k);
         std::memcpy(arena + (size_t)jobs[n].dst * SLOT_STRIDE, tmp, sizeof(tmp));
     }
+}
+
+// Whole gate frontier exactly as b200fhe_gate_batch runs it: job building, unary gather/scatter,
+// blind rotations, key switches.  Returns 0, or -1 with *err set.
+extern "C" int sim_gate_batch(int G, const uint8_t* opcode, const uint32_t* in0, const uint32_t* in1,
+                              const uint32_t* in2, const uint32_t* out, size_t n, uint16_t* arena, size_t n_slots,
+                              const uint32_t* bk_ntt, const uint16_t* ksk_dev, const char** err)
+{
+    sim_init();
+    std::vector<BrJob> br(2 * n + 1);
+    std::vector<KsJob> ks(n + 1);
+    std::vector<UnaryJob> un(n + 1);
+    BatchCounts cnt;
+    if (const char* e = build_gate_jobs(opcode, in0, in1, in2, out, n, n_slots, br.data(), ks.data(), un.data(), cnt)) {
+        if (err) *err = e;
+        return -1;
+    }
+    if (cnt.nun) {  // gather then scatter, like the two unary kernels
+        std::vector<uint32_t> stage(cnt.nun * KS_THREADS);
+        for (size_t j = 0; j < cnt.nun; j++)
+            for (int k = 0; k < KS_THREADS; k++)
+                stage[j * KS_THREADS + k] = unary_word(un[j], reinterpret_cast<const uint32_t*>(arena), k);
+        for (size_t j = 0; j < cnt.nun; j++)
+            std::memcpy(arena + (size_t)un[j].dst * SLOT_STRIDE, &stage[j * KS_THREADS], KS_THREADS * 4);
+    }
+    if (cnt.nbr) {
+        std::vector<uint32_t> ubuf(cnt.nbr * (size_t)U_STRIDE);
+        sim_blind_rotate(G, br.data(), (int)cnt.nbr, arena, bk_ntt, ubuf.data(), N0);
+        sim_keyswitch(ks.data(), (int)cnt.nks, ubuf.data(), ksk_dev, arena);
+    }
+    return 0;
 }
 
 extern "C" int sim_sizeof_brjob() { return (int)sizeof(BrJob); }

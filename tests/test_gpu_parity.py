@@ -1,0 +1,162 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the exact-integer oracle
+(bit-exact) and the reference's golden vectors.  Run with `pytest -m gpu` on a B200."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def fresh(keys, n, seed):
+    rng = np.random.default_rng(seed)
+    bits = [rng.integers(0, 2, n, dtype=np.uint8) for _ in range(3)]
+    cts = [O.encrypt_bits(seed * 10 + k, keys, b) for k, b in enumerate(bits)]
+    return bits, cts
+
+
+def test_native_library_is_loaded(gpu_ctx):
+    # the driver records which .so files the process loaded: make sure ours is the one in-tree
+    maps = open("/proc/self/maps").read()
+    assert "iyokan_b200/csrc/libb200fhe.so" in maps
+
+
+def test_bk_ntt_matches_cpu_simulator(gpu_ctx, bk_ntt_sim):
+    for first in (0, 317, 632):
+        assert np.array_equal(gpu_ctx.test_read_bk_ntt(first, 4), bk_ntt_sim[first:first + 4])
+
+
+@pytest.mark.parametrize("G", [1, 2, 4])
+def test_blind_rotate_bit_exact(gpu_ctx, keys, golden, G):
+    gpu_ctx.set_jobs_per_cta(G)
+    c = golden["br_in"][:3]  # 3 jobs: ragged for G = 2 and 4
+    assert np.array_equal(gpu_ctx.test_bootstrap_lvl1(c), O.bootstrap_to_lvl1(keys, c))
+    gpu_ctx.set_jobs_per_cta(0)
+
+
+def test_blind_rotate_edge_inputs(gpu_ctx, keys):
+    c = np.zeros((3, 637), np.uint16)
+    c[0, :8] = [0xFFFF, 0xFFF0, 0, 15, 0x8000, 0x7FF0, 0x8010, 0x0010]   # a-bar = 2N, 0, N, ...
+    c[0, 636] = 0x001F                                                   # b-bar = 2N
+    c[1, 600:636] = 0x8000
+    c[1, 636] = 0xFFFF                                                   # b-bar = 1
+    c[2, 636] = 1 << 13                                                  # trivial ciphertext: all a-bar = 0
+    assert np.array_equal(gpu_ctx.test_bootstrap_lvl1(c), O.bootstrap_to_lvl1(keys, c))
+
+
+def test_keyswitch_equals_reference_golden(gpu_ctx, golden):
+    # IdentityKeySwitch is integer-only in TFHEpp: the GPU must reproduce the reference bit for bit
+    assert np.array_equal(gpu_ctx.test_keyswitch(golden["ks_in"]), golden["ks_out_tfhepp"])
+
+
+def test_every_opcode_bit_exact_vs_oracle(gpu_ctx, keys):
+    names = list(O.OPS)
+    ops = np.repeat(np.array([O.OPS[n] for n in names], np.uint8), 2)
+    n = ops.size
+    (pa, pb, pc), (ca, cb, cc) = fresh(keys, n, 3)
+    gpu_ctx.arena_alloc(4 * n)
+    got = gpu_ctx.gates_host(ops, ca, cb, cc)
+    assert np.array_equal(got, O.gate_batch(keys, ops, ca, cb, cc))
+    assert np.array_equal(O.decrypt_bits(keys, got), O.plain_gate_vec(ops, pa, pb, pc))
+
+
+def test_reference_golden_gates_decrypt_identically(gpu_ctx, keys, golden):
+    # same keys, same encrypted inputs as the TFHEpp run stored in the fixture
+    ops, pa, pb, pc = (golden[k] for k in ("gate_ops", "gate_pa", "gate_pb", "gate_pc"))
+    ca, cb, cc = (O.encrypt_bits(int(s), keys, p) for s, p in zip(golden["gate_enc_seeds"], (pa, pb, pc)))
+    gpu_ctx.arena_alloc(4 * ops.size)
+    got = gpu_ctx.gates_host(ops, ca, cb, cc)
+    assert np.array_equal(O.decrypt_bits(keys, got), O.decrypt_bits(keys, golden["gate_out_tfhepp"]))
+    free = np.isin(ops, [O.OPS[n] for n in ("NOT", "COPY", "CONST0", "CONST1")])
+    assert np.array_equal(got[free], golden["gate_out_tfhepp"][free])
+
+
+def test_empty_and_single_and_ragged_batches(gpu_ctx, keys):
+    gpu_ctx.arena_alloc(64)
+    gpu_ctx.gate_batch(np.zeros(0, np.uint8), np.zeros(0, np.uint32), None, None, np.zeros(0, np.uint32))
+    gpu_ctx.sync()
+    for n in (1, 5, 7):
+        (pa, pb, _), (ca, cb, _) = fresh(keys, n, 40 + n)
+        ops = np.full(n, O.OPS["NOR"], np.uint8)
+        got = gpu_ctx.gates_host(ops, ca, cb, None)
+        assert np.array_equal(got, O.gate_batch(keys, ops, ca, cb))
+
+
+def test_resident_slots_and_dff_tick(gpu_ctx, keys):
+    # a 3-stage shift register: Q2 <- Q1 <- Q0 <- D, all ticking at once (iyokan.hpp:1395-1402)
+    (bits, _, _), (c, _, _) = fresh(keys, 4, 9)
+    gpu_ctx.arena_alloc(16)
+    ids = np.arange(4, dtype=np.uint32)
+    gpu_ctx.upload(ids, c)
+    gpu_ctx.dff_tick(ids[:3], ids[1:])
+    gpu_ctx.sync()
+    got = gpu_ctx.download(ids)
+    assert np.array_equal(got[0], c[0]) and np.array_equal(got[1:], c[:3])
+    # in-place chain of gates across batches keeps ciphertexts device resident
+    ops = np.array([O.OPS["XOR"]], np.uint8)
+    gpu_ctx.gate_batch(ops, [0], [3], None, [5])
+    gpu_ctx.gate_batch(np.array([O.OPS["NOT"]], np.uint8), [5], None, None, [6])
+    gpu_ctx.sync()
+    out = gpu_ctx.download([5, 6])
+    x = O.gate_batch(keys, ops, got[0:1], got[3:4])
+    assert np.array_equal(out[0], x[0]) and np.array_equal(out[1], (-x[0].astype(np.int32)).astype(np.uint16))
+
+
+def test_error_behaviour(gpu_ctx):
+    from iyokan_b200 import B200FheError, Context
+
+    gpu_ctx.arena_alloc(8)
+    with pytest.raises(B200FheError, match="slot"):
+        gpu_ctx.gate_batch(np.array([1], np.uint8), [0], [1], None, [99])
+    with pytest.raises(B200FheError, match="opcode"):
+        gpu_ctx.gate_batch(np.array([77], np.uint8), [0], [1], None, [2])
+    with pytest.raises(B200FheError, match="input slot"):
+        gpu_ctx.gate_batch(np.array([1], np.uint8), [0], None, None, [2])
+    with Context(0) as c2:
+        c2.arena_alloc(4)
+        with pytest.raises(B200FheError, match="keys"):
+            c2.gate_batch(np.array([1], np.uint8), [0], [1], None, [2])
+    gpu_ctx.sync()  # the context stays usable after rejected calls
+
+
+def test_full_size_batch_properties(gpu_ctx, keys):
+    # BASELINE.json configs[1]: 8192 independent HomNAND; size-independent checks
+    n = 8192
+    (pa, pb, _), (ca, cb, _) = fresh(keys, n, 77)
+    gpu_ctx.arena_alloc(4 * n)
+    ids = np.arange(4 * n, dtype=np.uint32)
+    gpu_ctx.upload(ids[:n], ca)
+    gpu_ctx.upload(ids[n:2 * n], cb)
+    ops = np.full(n, O.OPS["NAND"], np.uint8)
+    gpu_ctx.gate_batch(ops, ids[:n], ids[n:2 * n], None, ids[2 * n:3 * n])
+    gpu_ctx.sync()
+    out = gpu_ctx.download(ids[2 * n:3 * n])
+    assert np.array_equal(O.decrypt_bits(keys, out), 1 - (pa & pb))            # truth table
+    ph = O.phase(keys, out).astype(np.int32)
+    assert np.all(np.abs(np.abs(ph) - O.MU0) < O.MU0 // 2)                     # noise margin
+    sample = np.array([0, 1, 4095, 8190, 8191])
+    assert np.array_equal(out[sample], O.gate_batch(keys, ops[sample], ca[sample], cb[sample]))  # bit-exact sample
+    # determinism / position independence: the same gate anywhere in the batch gives the same bits
+    gpu_ctx.gate_batch(ops, ids[:n][::-1].copy(), ids[n:2 * n][::-1].copy(), None, ids[3 * n:])
+    gpu_ctx.sync()
+    assert np.array_equal(gpu_ctx.download(ids[3 * n:]), out[::-1])
+    # NOT(NAND(a,b)) == AND(a,b) on decrypted bits; double NOT is the identity on ciphertexts
+    gpu_ctx.gate_batch(np.full(n, O.OPS["NOT"], np.uint8), ids[2 * n:3 * n], None, None, ids[3 * n:])
+    gpu_ctx.sync()
+    assert np.array_equal(O.decrypt_bits(keys, gpu_ctx.download(ids[3 * n:])), pa & pb)
+
+
+def test_mux_heavy_batch(gpu_ctx, keys):
+    n = 33
+    (pa, pb, pc), (ca, cb, cc) = fresh(keys, n, 12)
+    ops = np.full(n, O.OPS["MUX"], np.uint8)
+    gpu_ctx.arena_alloc(4 * n)
+    got = gpu_ctx.gates_host(ops, ca, cb, cc)
+    assert np.array_equal(O.decrypt_bits(keys, got), np.where(pc == 1, pb, pa))
+    assert np.array_equal(got[:6], O.gate_batch(keys, ops[:6], ca[:6], cb[:6], cc[:6]))
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+
+    g.smoke()

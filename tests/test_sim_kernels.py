@@ -1,0 +1,158 @@
+"""CPU lock-step simulation of the CUDA kernels (same source as the device code) vs the oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+BRJOB = np.dtype([("in", "<u4", 3), ("sgn", "i1", 3), ("pad", "i1"), ("off", "<u4")])
+KSJOB = np.dtype([("u0", "<u4"), ("u1", "<u4"), ("out", "<u4"), ("post", "<u4")])
+
+
+def p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_struct_layouts(sim):
+    assert sim.sim_sizeof_brjob() == BRJOB.itemsize == 20
+    assert sim.sim_sizeof_ksjob() == KSJOB.itemsize == 16
+
+
+def test_warp_ntt_negacyclic_product(sim):
+    P = sim.sim_prime()
+    rng = np.random.default_rng(1)
+    for trial in range(2):
+        a = rng.integers(0, P, 1024, dtype=np.uint32)
+        b = rng.integers(0, P, 1024, dtype=np.uint32)
+        if trial == 1:  # extreme residues
+            a[:] = P - 1
+            b[:] = P - 1
+        c = np.zeros(1024, np.uint32)
+        sim.sim_negacyclic_mul_modp(p(a), p(b), p(c))
+        A = a.astype(object)
+        B = b.astype(object)
+        full = np.convolve(A, B)
+        ref = full[:1024].copy()
+        ref[:1023] -= full[1024:]
+        assert np.array_equal(np.array([int(v) % P for v in ref], dtype=np.uint64), c.astype(np.uint64))
+
+
+def test_lazy_ranges_never_overflow(sim):
+    # worst-case lazy inputs: forward takes digits+p (< p+64), inverse takes < 4p
+    P = sim.sim_prime()
+    fwd_in = np.full(1024, P + 31, np.uint32)
+    inv_in = np.full(1024, 4 * P - 1, np.uint32)
+    fmax, imax = ctypes.c_uint32(), ctypes.c_uint32()
+    sim.sim_ntt_ranges(p(fwd_in), ctypes.byref(fmax), ctypes.byref(ctypes.c_uint32()))
+    sim.sim_ntt_ranges(p(inv_in), ctypes.byref(ctypes.c_uint32()), ctypes.byref(imax))
+    assert fmax.value < 3 * P + 8 * 14335 + 1
+    assert imax.value < 4 * P
+
+
+def test_bk_limbs_recombine(sim, keys, bk_ntt_sim):
+    P = sim.sim_prime()
+    assert bk_ntt_sim.max() < P
+    # recombination identity on raw values: x0 + 2^11 x1 + 2^22 x2 == raw (mod 2^32)
+    raw = keys.bk[3].astype(np.int64).ravel()
+    v = raw.astype(np.uint32).view(np.int32).astype(np.int64)
+    x0 = ((v & 2047) ^ 1024) - 1024
+    v1 = (v - x0) >> 11
+    x1 = ((v1 & 2047) ^ 1024) - 1024
+    x2 = (v1 - x1) >> 11
+    assert np.abs(x0).max() <= 1024 and np.abs(x1).max() <= 1024 and np.abs(x2).max() <= 512
+    assert np.array_equal((x0 + (x1 << 11) + (x2 << 22)) % 2**32, raw % 2**32)
+
+
+@pytest.mark.parametrize("G", [1, 2, 4])
+def test_blind_rotate_bit_exact(sim, keys, bk_ntt_sim, G):
+    rng = np.random.default_rng(10 + G)
+    n = 3  # not a multiple of G for G = 2, 4: exercises the ragged last CTA
+    pa, pb = rng.integers(0, 2, n, dtype=np.uint8), rng.integers(0, 2, n, dtype=np.uint8)
+    ca, cb = O.encrypt_bits(1, keys, pa), O.encrypt_bits(2, keys, pb)
+    arena = np.zeros((2 * n, 640), np.uint16)
+    arena[:n, :637], arena[n:, :637] = ca, cb
+    jobs = np.zeros(n, BRJOB)
+    for g in range(n):
+        jobs[g]["in"] = (g, n + g, 0)
+        jobs[g]["sgn"] = (2, 2, 0)          # XOR: 2a + 2b + 2mu
+        jobs[g]["off"] = 2 << 13
+    ubuf = np.zeros((n, 1028), np.uint32)
+    sim.sim_blind_rotate(G, p(jobs), n, p(arena), p(bk_ntt_sim), p(ubuf), 636)
+    c = (2 * ca.astype(np.int32) + 2 * cb.astype(np.int32)).astype(np.uint16)
+    c[:, 636] += np.uint16(2 << 13)
+    assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
+
+
+def test_blind_rotate_abar_edges(sim, keys, bk_ntt_sim):
+    # a-bar = 2N (c_i = 0xFFFF), a-bar = 0, a-bar = N and b-bar = 2N / 1
+    c = np.zeros((2, 637), np.uint16)
+    c[0, :8] = [0xFFFF, 0xFFF0, 0, 15, 0x8000, 0x7FF0, 0x8010, 0x0010]
+    c[0, 636] = 0x001F
+    c[1, 600:636] = 0x8000
+    c[1, 636] = 0xFFFF
+    arena = np.zeros((2, 640), np.uint16)
+    arena[:, :637] = c
+    jobs = np.zeros(2, BRJOB)
+    for g in range(2):
+        jobs[g]["in"] = (g, 0, 0)
+        jobs[g]["sgn"] = (1, 0, 0)
+    ubuf = np.zeros((2, 1028), np.uint32)
+    sim.sim_blind_rotate(2, p(jobs), 2, p(arena), p(bk_ntt_sim), p(ubuf), 636)
+    assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
+
+
+def test_keyswitch_bit_exact(sim, keys, ksk_dev, golden):
+    u = golden["ks_in"]
+    n = u.shape[0]
+    ubuf = np.zeros((n, 1028), np.uint32)
+    ubuf[:, :1025] = u
+    jobs = np.zeros(n, KSJOB)
+    jobs["u0"], jobs["u1"], jobs["out"] = np.arange(n), 0xFFFFFFFF, np.arange(n)
+    arena = np.full((n, 640), 0xABCD, np.uint16)
+    sim.sim_keyswitch(p(jobs), n, p(ubuf), p(ksk_dev), p(arena))
+    assert np.array_equal(arena[:, :637], golden["ks_out_tfhepp"])  # == the reference, bit for bit
+    assert np.all(arena[:, 637:] == 0)
+
+
+def run_batch(sim, G, ops, arena, in0, in1, in2, out, bk_ntt_sim, ksk_dev):
+    err = ctypes.c_char_p()
+    ops = np.ascontiguousarray(ops, np.uint8)
+    arrs = [None if a is None else np.ascontiguousarray(a, np.uint32) for a in (in0, in1, in2, out)]
+    rc = sim.sim_gate_batch(G, p(ops), p(arrs[0]), p(arrs[1]), p(arrs[2]), p(arrs[3]), ctypes.c_size_t(ops.size),
+                            p(arena), ctypes.c_size_t(arena.shape[0]), p(bk_ntt_sim), p(ksk_dev), ctypes.byref(err))
+    return rc, err.value
+
+
+def test_full_frontier_all_opcodes(sim, keys, bk_ntt_sim, ksk_dev):
+    names = list(O.OPS)
+    ops = np.array([O.OPS[n] for n in names], np.uint8)
+    n = ops.size
+    rng = np.random.default_rng(5)
+    pa, pb, pc = (rng.integers(0, 2, n, dtype=np.uint8) for _ in range(3))
+    ca, cb, cc = (O.encrypt_bits(s, keys, b) for s, b in ((21, pa), (22, pb), (23, pc)))
+    arena = np.zeros((4 * n, 640), np.uint16)
+    arena[:n, :637], arena[n:2 * n, :637], arena[2 * n:3 * n, :637] = ca, cb, cc
+    ids = np.arange(4 * n, dtype=np.uint32)
+    rc, err = run_batch(sim, 2, ops, arena, ids[:n], ids[n:2 * n], ids[2 * n:3 * n], ids[3 * n:], bk_ntt_sim, ksk_dev)
+    assert rc == 0, err
+    got = arena[3 * n:, :637]
+    assert np.array_equal(got, O.gate_batch(keys, ops, ca, cb, cc))
+    assert np.array_equal(O.decrypt_bits(keys, got.copy()), O.plain_gate_vec(ops, pa, pb, pc))
+    assert np.all(arena[:, 637:] == 0)
+
+
+def test_frontier_errors_and_dff_overlap(sim, keys, bk_ntt_sim, ksk_dev):
+    arena = np.zeros((4, 640), np.uint16)
+    ids = np.arange(4, dtype=np.uint32)
+    rc, err = run_batch(sim, 2, [O.OPS["NAND"]], arena, ids[:1], None, None, ids[3:], bk_ntt_sim, ksk_dev)
+    assert rc == -1 and b"input slot" in err
+    rc, err = run_batch(sim, 2, [99], arena, ids[:1], ids[:1], None, ids[3:], bk_ntt_sim, ksk_dev)
+    assert rc == -1 and b"opcode" in err
+    rc, err = run_batch(sim, 2, [O.OPS["NOT"]], arena, ids[:1], None, None, np.array([7], np.uint32), bk_ntt_sim, ksk_dev)
+    assert rc == -1 and b"output slot" in err
+    # COPY chain with overlapping src/dst behaves like a simultaneous DFF tick
+    arena[:, 0] = [10, 20, 30, 40]
+    rc, err = run_batch(sim, 2, [O.OPS["COPY"]] * 3, arena, ids[:3], None, None, ids[1:], bk_ntt_sim, ksk_dev)
+    assert rc == 0
+    assert list(arena[:, 0]) == [10, 10, 20, 30]

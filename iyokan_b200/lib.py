@@ -196,8 +196,9 @@ class Context:
     def gate_batch(self, opcode, in0, in1, in2, out):
         op = np.ascontiguousarray(opcode, dtype=np.uint8)
         n = op.size
-        self._ck(self._lib.b200fhe_gate_batch(self._h, _ptr(op), _ptr(_u32(in0, n)), _ptr(_u32(in1, n)),
-                                               _ptr(_u32(in2, n)), _ptr(_u32(out, n)), n))
+        # keep the converted id arrays alive across the call (ctypes only sees raw addresses)
+        a, b, c, o = _u32(in0, n), _u32(in1, n), _u32(in2, n), _u32(out, n)
+        self._ck(self._lib.b200fhe_gate_batch(self._h, _ptr(op), _ptr(a), _ptr(b), _ptr(c), _ptr(o), n))
 
     def dff_tick(self, src, dst):
         s, d = _u32(src), _u32(dst, None)

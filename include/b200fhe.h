@@ -62,7 +62,7 @@ typedef struct b200fhe_ctx b200fhe_ctx;
 int b200fhe_create(b200fhe_ctx **out, int device);
 void b200fhe_destroy(b200fhe_ctx *ctx);
 const char *b200fhe_last_error(void);
-/* tuning knob: rotation jobs per CTA (1, 2 or 4); 0 = default */
+/* tuning knob: rotation jobs per CTA (1, 2, 3, 4 or 6); 0 = default */
 int b200fhe_set_jobs_per_cta(b200fhe_ctx *ctx, int g);
 
 /* keys: raw bootstrapping key + key-switching key in the reference's memory layout.

@@ -24,8 +24,11 @@ using namespace b200;
 // kernels
 // =====================================================================================
 
+// resident CTAs per SM the register allocator is asked to allow (shared memory permitting)
+constexpr int br_min_blocks(int G) { return G == 1 ? 4 : G == 2 ? 3 : G == 3 ? 2 : 1; }
+
 template <int G>
-__global__ void __launch_bounds__(64 * G, (G <= 2 ? 2 : 1))
+__global__ void __launch_bounds__(64 * G, br_min_blocks(G))
 br_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ arena,
           const uint32_t* __restrict__ bk_ntt, const tw_t* __restrict__ tw2f_g, const tw_t* __restrict__ tw2i_g,
           uint32_t* __restrict__ ubuf, int n_iter)
@@ -44,28 +47,41 @@ br_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict_
     if (!valid) job = njobs - 1;  // duplicate work, keeps every barrier uniform
     const BrJob jb = jobs[job];
 
-    uint32_t accr[32], dreg[32], sum[32];
+    uint32_t accr[32];
     br_prologue<G>(sm, jb, arena, g, q, lane, accr);
     __syncthreads();
 
     for (int i = 0; i < n_iter; i++) {
-        br_rotate_diff<G>(sm, i, g, q, lane, accr, dreg);
+        const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
+        uint32_t bk0[BK_COLS][ROWS];
+        {
+            uint32_t dreg[32];
+            br_rotate_diff<G>(sm, i, g, q, lane, accr, dreg);
+            __syncwarp();  // the accumulator copy shares the first tile with digit 0
 #pragma unroll 1
-        for (int d = 0; d < GL; d++) {
-            br_fwd_a<G>(sm, g, q, lane, d, dreg);
+            for (int d = 0; d < GL - 1; d++) {
+                br_fwd_a<G>(sm, g, q, lane, d, dreg);
+                __syncwarp();
+                br_fwd_b<G>(sm, g, q, lane, d);
+            }
+            br_fwd_a<G>(sm, g, q, lane, GL - 1, dreg);
             __syncwarp();
-            br_fwd_b<G>(sm, g, q, lane, d);
+            pw_load(bk_i, tid, bk0);  // key words of phase M stay in flight during the last pass
+            br_fwd_b<G>(sm, g, q, lane, GL - 1);
         }
         __syncthreads();
-        br_pointwise<G>(sm, bk_ntt + (size_t)i * BK_COLS * ROWS * N1, tid);
+        br_pointwise<G>(sm, bk_i, tid, bk0);
         __syncthreads();
+        {
+            uint32_t sum[32];
 #pragma unroll 1
-        for (int l = 0; l < LIMBS; l++) {
-            br_inv_a<G>(sm, g, q, lane, l);
-            __syncwarp();
-            br_inv_b<G>(sm, g, q, lane, l, sum);
+            for (int l = 0; l < LIMBS; l++) {
+                br_inv_a<G>(sm, g, q, lane, l);
+                __syncwarp();
+                br_inv_b<G>(sm, g, q, lane, l, sum);
+            }
+            br_acc_update<G>(sm, g, q, lane, sum, accr);
         }
-        br_acc_update<G>(sm, g, q, lane, sum, accr);
         __syncwarp();
     }
     if (valid) br_epilogue<G>(sm, g, q, lane, ubuf + (size_t)job * U_STRIDE);
@@ -150,7 +166,7 @@ static int fail(const std::string& msg)
 struct b200fhe_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    int G = 2;
+    int G = 4;
     NttTables* tab = nullptr;
     tw_t* d_tw2f = nullptr;
     tw_t* d_tw2i = nullptr;
@@ -198,8 +214,10 @@ static int br_dispatch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_
     switch (c->G) {
     case 1: return br_launch<1>(c, njobs, arena, ubuf, d_jobs);
     case 2: return br_launch<2>(c, njobs, arena, ubuf, d_jobs);
+    case 3: return br_launch<3>(c, njobs, arena, ubuf, d_jobs);
     case 4: return br_launch<4>(c, njobs, arena, ubuf, d_jobs);
-    default: return fail("jobs per CTA must be 1, 2 or 4");
+    case 6: return br_launch<6>(c, njobs, arena, ubuf, d_jobs);
+    default: return fail("jobs per CTA must be 1, 2, 3, 4 or 6");
     }
 }
 
@@ -292,8 +310,8 @@ void b200fhe_destroy(b200fhe_ctx* c)
 int b200fhe_set_jobs_per_cta(b200fhe_ctx* c, int g)
 {
     if (!c) return fail("null context");
-    if (g == 0) g = 2;
-    if (g != 1 && g != 2 && g != 4) return fail("jobs per CTA must be 1, 2 or 4");
+    if (g == 0) g = 4;
+    if (g != 1 && g != 2 && g != 3 && g != 4 && g != 6) return fail("jobs per CTA must be 1, 2, 3, 4 or 6");
     c->G = g;
     return 0;
 }

@@ -16,6 +16,14 @@
 // streams the NTT-domain bootstrapping key once per CTA and reuses it for all G jobs) turns
 // the three limb results back (phase I).  Only two __syncthreads per CMUX step.
 //
+// Step sequence executed by the kernel (and, identically, by the CPU simulator):
+//   pw_load(first position)            key words for phase M requested a whole phase early
+//   br_rotate_diff  ; syncwarp         rotated read of the accumulator copy in the warp's first tile
+//   3 x { br_fwd_a ; syncwarp ; br_fwd_b }
+//   syncthreads ; br_pointwise ; syncthreads
+//   3 x { br_inv_a ; syncwarp ; br_inv_b }
+//   br_acc_update ; syncwarp
+//
 // Every function here is free of intra-phase cross-thread communication: threads talk only
 // through shared memory between phases, so a sequential CPU loop over (phase, thread) is an
 // exact model of the kernel.  tests/sim/br_sim.cpp relies on that.
@@ -39,12 +47,10 @@ struct BrJob {
 template <int G>
 struct BrSmem {
     static constexpr int DBUF_WORDS = G * ROWS * TILE_WORDS;  // digit / limb tiles (in place)
-    static constexpr int ACC_WORDS = G * 2 * N1;              // accumulator copy for rotated reads
     static constexpr int ABAR_HALFS = G * SLOT_STRIDE;        // mod-switched a_i
     static constexpr size_t BYTES =
-        (size_t)DBUF_WORDS * 4 + (size_t)ACC_WORDS * 4 + 2 * (size_t)TW2_LEN * sizeof(tw_t) + (size_t)ABAR_HALFS * 2;
+        (size_t)DBUF_WORDS * 4 + 2 * (size_t)TW2_LEN * sizeof(tw_t) + (size_t)ABAR_HALFS * 2;
     uint32_t* dbuf;
-    uint32_t* accbuf;
     tw_t* tw2f;
     tw_t* tw2i;
     uint16_t* abar;
@@ -53,8 +59,6 @@ struct BrSmem {
         uint8_t* p = reinterpret_cast<uint8_t*>(base);
         dbuf = reinterpret_cast<uint32_t*>(p);
         p += (size_t)DBUF_WORDS * 4;
-        accbuf = reinterpret_cast<uint32_t*>(p);
-        p += (size_t)ACC_WORDS * 4;
         tw2f = reinterpret_cast<tw_t*>(p);
         p += (size_t)TW2_LEN * sizeof(tw_t);
         tw2i = reinterpret_cast<tw_t*>(p);
@@ -62,7 +66,10 @@ struct BrSmem {
         abar = reinterpret_cast<uint16_t*>(p);
     }
     B200_HD uint32_t* tile(int g, int row) const { return dbuf + (size_t)(g * ROWS + row) * TILE_WORDS; }
-    B200_HD uint32_t* acc(int g, int q) const { return accbuf + (size_t)(g * 2 + q) * N1; }
+    // Natural-order copy of accumulator polynomial q, used only for the rotated read at the start
+    // of a CMUX step and by the epilogue.  It lives in the first 1024 words of the warp's own first
+    // tile, which is free between phase I of one step and phase F of the next.
+    B200_HD uint32_t* acc(int g, int q) const { return tile(g, q * GL); }
 };
 
 // lvl0 linear combination of one coefficient (uint16 wrap-around, gate.hpp:14-16)
@@ -133,7 +140,7 @@ B200_HD void br_fwd_a(const BrSmem<G>& sm, int g, int q, int lane, int d, const 
     fwd_pass1(x);
     tile_store_col(sm.tile(g, q * GL + d), x, lane);
 }
-// Fb(d): row load -> forward pass 2 -> row store (values < 3p + 8c)
+// Fb(d): row load -> forward pass 2 -> row store (values < 4p)
 template <int G>
 B200_HD void br_fwd_b(const BrSmem<G>& sm, int g, int q, int lane, int d)
 {
@@ -146,33 +153,51 @@ B200_HD void br_fwd_b(const BrSmem<G>& sm, int g, int q, int lane, int d)
 
 // ---- phase M: pointwise multiply-accumulate with the NTT-domain key ----------------------
 // bk_i points at bk_ntt[i] : [BK_COLS][ROWS][1024] uint32 in [0,p), pre-scaled by 2^32/N.
-// out[g][c][j] = sum_r D[g][r][j] * BK[c][r][j] * 2^-32  (in place over the digit tiles)
-template <int G>
-B200_HD void br_pointwise(const BrSmem<G>& sm, const uint32_t* bk_i, int tid)
+// out[g][c][j] = sum_r D[g][r][j] * BK[c][r][j] * 2^-32  (in place over the digit tiles).
+// The 36 key words of position j are loaded once per CTA and reused for all G jobs; the load
+// is split from the compute so the kernel can issue it a whole phase ahead (L2 latency).
+B200_HD void pw_load(const uint32_t* bk_i, int j, uint32_t (&bkv)[BK_COLS][ROWS])
 {
-    constexpr int T = 64 * G;
-    for (int j = tid; j < N1; j += T) {
-        uint32_t bkv[BK_COLS][ROWS];
+    B200_UNROLL
+    for (int c = 0; c < BK_COLS; c++) {
+        B200_UNROLL
+        for (int r = 0; r < ROWS; r++) bkv[c][r] = bk_i[(size_t)(c * ROWS + r) * N1 + j];
+    }
+}
+template <int G>
+B200_HD void pw_compute(const BrSmem<G>& sm, int j, const uint32_t (&bkv)[BK_COLS][ROWS])
+{
+    const int off = tile_of_j(j);
+    B200_UNROLL
+    for (int g = 0; g < G; g++) {
+        uint32_t d[ROWS], o[BK_COLS];
+        B200_UNROLL
+        for (int r = 0; r < ROWS; r++) d[r] = sm.tile(g, r)[off];
         B200_UNROLL
         for (int c = 0; c < BK_COLS; c++) {
+            uint64_t acc = 0;
             B200_UNROLL
-            for (int r = 0; r < ROWS; r++) bkv[c][r] = bk_i[(size_t)(c * ROWS + r) * N1 + j];
+            for (int r = 0; r < ROWS; r++) acc += (uint64_t)d[r] * bkv[c][r];
+            o[c] = redc64(acc);  // < 4p
         }
-        const int off = tile_of_j(j);
         B200_UNROLL
-        for (int g = 0; g < G; g++) {
-            uint32_t d[ROWS], o[BK_COLS];
-            B200_UNROLL
-            for (int r = 0; r < ROWS; r++) d[r] = sm.tile(g, r)[off];
-            B200_UNROLL
-            for (int c = 0; c < BK_COLS; c++) {
-                uint64_t acc = 0;
-                B200_UNROLL
-                for (int r = 0; r < ROWS; r++) acc += (uint64_t)d[r] * bkv[c][r];
-                o[c] = redc64(acc);  // < 4p
-            }
-            B200_UNROLL
-            for (int c = 0; c < BK_COLS; c++) sm.tile(g, c)[off] = o[c];
+        for (int c = 0; c < BK_COLS; c++) sm.tile(g, c)[off] = o[c];
+    }
+}
+// whole phase for thread tid with a two-deep register pipeline; bk0 holds position j = tid
+// (already loaded by the caller, normally before the barrier that opens the phase)
+template <int G>
+B200_HD void br_pointwise(const BrSmem<G>& sm, const uint32_t* bk_i, int tid, uint32_t (&bk0)[BK_COLS][ROWS])
+{
+    constexpr int T = 64 * G;
+    uint32_t bk1[BK_COLS][ROWS];
+    for (int j = tid; j < N1; j += 2 * T) {
+        const int j1 = j + T, j2 = j + 2 * T;
+        if (j1 < N1) pw_load(bk_i, j1, bk1);
+        pw_compute<G>(sm, j, bk0);
+        if (j1 < N1) {
+            if (j2 < N1) pw_load(bk_i, j2, bk0);
+            pw_compute<G>(sm, j1, bk1);
         }
     }
 }

@@ -26,6 +26,9 @@ struct alignas(16) u32x4 {
     uint32_t x, y, z, w;
 };
 
+// High word of a 32x32 product.  Measured on B200 (scripts/microbench/pipes.cu): IMAD.HI.U32 and
+// IMAD.WIDE.U32 both issue at half the rate of IMAD (0.97 vs 1.9 warp-inst/clk/SM), so asking for
+// the full 64-bit product instead buys nothing and costs a register pair.
 B200_HD uint32_t mulhi32(uint32_t a, uint32_t b)
 {
 #if defined(__CUDA_ARCH__)

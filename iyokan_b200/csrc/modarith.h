@@ -35,11 +35,25 @@ B200_HD uint32_t shoup_mul(uint32_t y, tw_t t)
 
 B200_HD uint32_t fix29(uint32_t x) { return x - (x >> 29) * P; }  // < p + 8c
 
+// ALU-only conditional subtractions (unsigned-min trick: x - k wraps above x when x < k).
+// The integer-multiply pipe is the kernel's bottleneck, so range fixes run on the ALU pipe.
+B200_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+B200_HD uint32_t fix_lt8p_to_lt4p(uint32_t x) { return umin32(x, x - P4); }
+B200_HD uint32_t fix_lt4p_to_lt2p(uint32_t x) { return umin32(x, x - P2); }
+B200_HD uint32_t fix_lt8p_to_lt2p(uint32_t x) { return fix_lt4p_to_lt2p(fix_lt8p_to_lt4p(x)); }
+
 // full reduction of any 32-bit value to [0, p)
 B200_HD uint32_t reduce_full(uint32_t x)
 {
     x = fix29(x);
     return x >= P ? x - P : x;
+}
+// exact signed integer v with v = x (mod p), valid when |v| <= CONV_BOUND and x < 4p; ALU only
+B200_HD int32_t centered_lift_alu(uint32_t x)
+{
+    x = fix_lt4p_to_lt2p(x);
+    x = umin32(x, x - P);                      // [0, p)
+    return (int32_t)(x > P / 2 ? x - P : x);  // centred
 }
 
 // Montgomery reduction of a 64-bit accumulator: returns acc * 2^-32 mod p, lazily, < acc/2^32 + p.

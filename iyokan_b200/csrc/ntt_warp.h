@@ -8,8 +8,8 @@
 // Gentleman-Sande negacyclic transform is split 32 x 32: five radix-2 stages run entirely in
 // registers, one transpose goes through a warp-private padded shared-memory tile (only
 // __syncwarp, never __syncthreads), five more stages run in registers.  Butterflies use
-// Shoup/Harvey lazy arithmetic in [0, 8p): 3 integer multiplies + 2 adds, with a range fix
-// (shift + multiply-add) on the sum path only every third (forward) / second (inverse) stage.
+// Shoup/Harvey lazy arithmetic in [0, 8p): 3 integer multiplies + 2 adds; the range fixes on the
+// sum path are ALU-only (add + unsigned min) because the integer-multiply pipe is the bottleneck.
 //
 // Index conventions (array position j = 32*a + b, a = j >> 5, b = j & 31):
 //   forward : input natural order, output "bit-reversed" order (positions are only ever
@@ -103,7 +103,16 @@ inline void ntt_tables_init(NttTables& t)
 // ---- register stages -------------------------------------------------------------------
 // One radix-2 stage over the 32 registers of a lane.  LS = local stage 0..4: pairs (i, i + half),
 // half = 16 >> LS, arranged in 2^LS groups that share a twiddle.  tw(g) returns the group twiddle.
-template <int LS, bool FIX, class TwFn>
+// FIX: 0 = none, 1 = sum-path operand < 8p -> < 4p, 2 = < 8p -> < 2p (both ALU-only)
+template <int FIX>
+B200_HD uint32_t apply_fix(uint32_t x)
+{
+    if (FIX == 1) return fix_lt8p_to_lt4p(x);
+    if (FIX == 2) return fix_lt8p_to_lt2p(x);
+    return x;
+}
+
+template <int LS, int FIX, class TwFn>
 B200_HD void ct_stage(uint32_t (&x)[32], TwFn tw)
 {
     constexpr int half = 16 >> LS;
@@ -113,8 +122,7 @@ B200_HD void ct_stage(uint32_t (&x)[32], TwFn tw)
         B200_UNROLL
         for (int k = 0; k < half; k++) {
             const int i0 = g * 2 * half + k, i1 = i0 + half;
-            uint32_t X = x[i0];
-            if (FIX) X = fix29(X);
+            const uint32_t X = apply_fix<FIX>(x[i0]);
             const uint32_t T = shoup_mul(x[i1], w);
             x[i0] = X + T;
             x[i1] = X - T + P2;
@@ -122,7 +130,7 @@ B200_HD void ct_stage(uint32_t (&x)[32], TwFn tw)
     }
 }
 
-template <int LS, bool FIX, class TwFn>
+template <int LS, int FIX, class TwFn>
 B200_HD void gs_stage(uint32_t (&x)[32], TwFn tw)
 {
     constexpr int half = 16 >> LS;
@@ -133,58 +141,55 @@ B200_HD void gs_stage(uint32_t (&x)[32], TwFn tw)
         for (int k = 0; k < half; k++) {
             const int i0 = g * 2 * half + k, i1 = i0 + half;
             const uint32_t U = x[i0], V = x[i1];
-            uint32_t S = U + V;
-            if (FIX) S = fix29(S);
-            x[i0] = S;
+            x[i0] = apply_fix<FIX>(U + V);
             x[i1] = shoup_mul(U - V + P4, w);
         }
     }
 }
 
-// Forward pass 1: global stages 0..4.  Input < p + 64 per element; output < 5p + 8c.
-// (bounds: stage0 <3p, stage1 <5p, stage2 <7p, fix before stage3 -> <3p+8c, stage4 <5p+8c)
+// Lazy-range schedule (all values < 8p < 2^32; Shoup products are always < 2p):
+//   forward, input < p + 1024:  s0 <3p | s1 <5p | s2 <7p | fix1 s3 <6p | s4 <8p | fix1 s5 <6p | s6 <8p |
+//                               fix1 s7 <6p | s8 <8p | fix2 s9 <4p                       => output < 4p
+//   inverse, input < 4p: every stage forms S = U + V < 8p and folds it back below 4p (fix1);
+//                        the product operand U - V + 4p stays in (0, 8p)                  => output < 4p
+// Forward pass 1: global stages 0..4 (lane-independent twiddles from constant memory).
 B200_HD void fwd_pass1(uint32_t (&x)[32])
 {
-    ct_stage<0, false>(x, [](int g) { return twf_u(1 + g); });
-    ct_stage<1, false>(x, [](int g) { return twf_u(2 + g); });
-    ct_stage<2, false>(x, [](int g) { return twf_u(4 + g); });
-    ct_stage<3, true>(x, [](int g) { return twf_u(8 + g); });
-    ct_stage<4, false>(x, [](int g) { return twf_u(16 + g); });
+    ct_stage<0, 0>(x, [](int g) { return twf_u(1 + g); });
+    ct_stage<1, 0>(x, [](int g) { return twf_u(2 + g); });
+    ct_stage<2, 0>(x, [](int g) { return twf_u(4 + g); });
+    ct_stage<3, 1>(x, [](int g) { return twf_u(8 + g); });
+    ct_stage<4, 0>(x, [](int g) { return twf_u(16 + g); });
 }
 
-// Forward pass 2: global stages 5..9, lane-dependent twiddles read from tw2 (shared memory on
-// the device).  Input < 5p+8c; stage5 <7p+8c, fix before stage6 -> <3p+8c, stage7 <5p+8c,
-// stage8 <7p+8c, fix before stage9 -> output < 3p + 8c.
+// Forward pass 2: global stages 5..9, lane-dependent twiddles read from tw2 (shared memory).
 B200_HD void fwd_pass2(uint32_t (&x)[32], const tw_t* tw2, int lane)
 {
-    ct_stage<0, false>(x, [=](int g) { return tw2[(0 + g) * 32 + lane]; });
-    ct_stage<1, true>(x, [=](int g) { return tw2[(1 + g) * 32 + lane]; });
-    ct_stage<2, false>(x, [=](int g) { return tw2[(3 + g) * 32 + lane]; });
-    ct_stage<3, false>(x, [=](int g) { return tw2[(7 + g) * 32 + lane]; });
-    ct_stage<4, true>(x, [=](int g) { return tw2[(15 + g) * 32 + lane]; });
+    ct_stage<0, 1>(x, [=](int g) { return tw2[(0 + g) * 32 + lane]; });
+    ct_stage<1, 0>(x, [=](int g) { return tw2[(1 + g) * 32 + lane]; });
+    ct_stage<2, 1>(x, [=](int g) { return tw2[(3 + g) * 32 + lane]; });
+    ct_stage<3, 0>(x, [=](int g) { return tw2[(7 + g) * 32 + lane]; });
+    ct_stage<4, 2>(x, [=](int g) { return tw2[(15 + g) * 32 + lane]; });
 }
 
-// Inverse pass 1: global stages 9..5 (lane-dependent).  Input < 4p.
-// Sum-path bounds: stage9 <8p -> fix -> <p+8c | stage8 in<=2p: <4p | stage7 <8p -> fix |
-// stage6 <4p | stage5 <8p -> fix.  Product path is always < 2p.  Output < 2p.
+// Inverse pass 1: global stages 9..5 (lane-dependent).  Input < 4p, output < 4p.
 B200_HD void inv_pass1(uint32_t (&x)[32], const tw_t* tw2, int lane)
 {
-    gs_stage<4, true>(x, [=](int g) { return tw2[(15 + g) * 32 + lane]; });
-    gs_stage<3, false>(x, [=](int g) { return tw2[(7 + g) * 32 + lane]; });
-    gs_stage<2, true>(x, [=](int g) { return tw2[(3 + g) * 32 + lane]; });
-    gs_stage<1, false>(x, [=](int g) { return tw2[(1 + g) * 32 + lane]; });
-    gs_stage<0, true>(x, [=](int g) { return tw2[(0 + g) * 32 + lane]; });
+    gs_stage<4, 1>(x, [=](int g) { return tw2[(15 + g) * 32 + lane]; });
+    gs_stage<3, 1>(x, [=](int g) { return tw2[(7 + g) * 32 + lane]; });
+    gs_stage<2, 1>(x, [=](int g) { return tw2[(3 + g) * 32 + lane]; });
+    gs_stage<1, 1>(x, [=](int g) { return tw2[(1 + g) * 32 + lane]; });
+    gs_stage<0, 1>(x, [=](int g) { return tw2[(0 + g) * 32 + lane]; });
 }
 
-// Inverse pass 2: global stages 4..0 (lane-independent).  Input < 2p.
-// stage4 <4p | stage3 <8p -> fix | stage2 <4p | stage1 <8p -> fix | stage0 <4p.  Output < 4p.
+// Inverse pass 2: global stages 4..0 (lane-independent).  Input < 4p, output < 4p.
 B200_HD void inv_pass2(uint32_t (&x)[32])
 {
-    gs_stage<4, false>(x, [](int g) { return twi_u(16 + g); });
-    gs_stage<3, true>(x, [](int g) { return twi_u(8 + g); });
-    gs_stage<2, false>(x, [](int g) { return twi_u(4 + g); });
-    gs_stage<1, true>(x, [](int g) { return twi_u(2 + g); });
-    gs_stage<0, false>(x, [](int g) { return twi_u(1 + g); });
+    gs_stage<4, 1>(x, [](int g) { return twi_u(16 + g); });
+    gs_stage<3, 1>(x, [](int g) { return twi_u(8 + g); });
+    gs_stage<2, 1>(x, [](int g) { return twi_u(4 + g); });
+    gs_stage<1, 1>(x, [](int g) { return twi_u(2 + g); });
+    gs_stage<0, 1>(x, [](int g) { return twi_u(1 + g); });
 }
 
 // ---- tile access -----------------------------------------------------------------------

@@ -35,7 +35,7 @@ ca, cb = O.encrypt_bits(1, keys, pa), O.encrypt_bits(2, keys, pb)
 c = (-ca.astype(np.int32) - cb.astype(np.int32)).astype(np.uint16)
 c[:, 636] += np.uint16(1 << 13)
 u_ref = O.bootstrap_to_lvl1(keys, c)
-for g in (1, 2, 4):
+for g in (1, 2, 3, 4, 6):
     ctx.set_jobs_per_cta(g)
     u = ctx.test_bootstrap_lvl1(c)
     out[f"br_exact_G{g}"] = bool(np.array_equal(u, u_ref))
@@ -53,7 +53,7 @@ ids = np.arange(3 * N, dtype=np.uint32)
 ctx.upload(ids[:N], A)
 ctx.upload(ids[N:2 * N], Bc)
 ops = np.full(N, OPS["NAND"], np.uint8)
-for g in (2, 4, 1):
+for g in (2, 3, 4, 6):
     ctx.set_jobs_per_cta(g)
     for rep in range(2):
         t = time.time()

@@ -140,7 +140,11 @@ static void sim_br_cta(const BrJob* jobs, int njobs, int cta, const uint16_t* ar
             }
         }
         const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
-        for (int tid = 0; tid < T; tid++) br_pointwise<G>(sm, bk_i, tid);
+        for (int tid = 0; tid < T; tid++) {
+            uint32_t bk0[BK_COLS][ROWS];
+            pw_load(bk_i, tid, bk0);
+            br_pointwise<G>(sm, bk_i, tid, bk0);
+        }
         for (int w = 0; w < W; w++) {
             const int g = w >> 1, q = w & 1;
             for (int l = 0; l < LIMBS; l++) {
@@ -170,6 +174,8 @@ extern "C" void sim_blind_rotate(int G, const void* jobs_raw, int njobs, const u
     for (int cta = 0; cta < ncta; cta++) {
         if (G == 1) sim_br_cta<1>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
         else if (G == 2) sim_br_cta<2>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
+        else if (G == 3) sim_br_cta<3>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
+        else if (G == 6) sim_br_cta<6>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
         else if (G == 4) sim_br_cta<4>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
         else std::abort();
     }

@@ -26,7 +26,7 @@ def test_bk_ntt_matches_cpu_simulator(gpu_ctx, bk_ntt_sim):
         assert np.array_equal(gpu_ctx.test_read_bk_ntt(first, 4), bk_ntt_sim[first:first + 4])
 
 
-@pytest.mark.parametrize("G", [1, 2, 4])
+@pytest.mark.parametrize("G", [1, 2, 3, 4, 6])
 def test_blind_rotate_bit_exact(gpu_ctx, keys, golden, G):
     gpu_ctx.set_jobs_per_cta(G)
     c = golden["br_in"][:3]  # 3 jobs: ragged for G = 2 and 4

@@ -56,3 +56,19 @@ def build_sim(force: bool = False) -> Path:
     if r.returncode != 0:
         raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
     return out
+
+
+def build_host(force: bool = False) -> Path:
+    """Host netlist engine (C++, g++), linked against the CUDA library next to it."""
+    host = ROOT / "iyokan_b200" / "host"
+    out = host / "libb200net.so"
+    srcs = [host / "b200net.cpp", ROOT / "include" / "b200net.h", ROOT / "include" / "b200fhe.h"]
+    if not force and _newer(out, srcs) and out.stat().st_mtime >= (CSRC / "libb200fhe.so").stat().st_mtime:
+        return out
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-o", str(out), str(host / "b200net.cpp"),
+           f"-L{CSRC}", "-lb200fhe", "-Wl,-rpath,$ORIGIN/../csrc"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return out

@@ -1,0 +1,301 @@
+// b200net: levelised netlist engine above the b200fhe C ABI (see include/b200net.h).
+#include "../../include/b200net.h"
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string& m)
+{
+    g_err = m;
+    return 1;
+}
+
+int arity(uint8_t kind)
+{
+    if (kind <= B200FHE_XNOR || kind == B200FHE_ANDNY || kind == B200FHE_ORNY) return 2;
+    if (kind == B200FHE_MUX) return 3;
+    if (kind == B200FHE_NOT || kind == B200FHE_COPY || kind == B200NET_DFF || kind == B200NET_OUTPUT) return 1;
+    if (kind == B200FHE_CONST0 || kind == B200FHE_CONST1 || kind == B200NET_INPUT) return 0;
+    return -1;
+}
+bool is_gate(uint8_t kind) { return kind < B200FHE_NUM_OPS; }
+int bootstraps(uint8_t kind)
+{
+    if (kind == B200FHE_MUX) return 2;
+    return (is_gate(kind) && arity(kind) == 2) ? 1 : 0;
+}
+
+// plaintext truth tables, same opcode meaning as gate_jobs.h / TFHEpp gate.hpp
+uint8_t plain_gate(uint8_t op, uint8_t a, uint8_t b, uint8_t s)
+{
+    switch (op) {
+    case B200FHE_AND: return a & b;
+    case B200FHE_NAND: return !(a & b);
+    case B200FHE_ANDNOT: return a & !b;
+    case B200FHE_OR: return a | b;
+    case B200FHE_NOR: return !(a | b);
+    case B200FHE_ORNOT: return a | !b;
+    case B200FHE_XOR: return a ^ b;
+    case B200FHE_XNOR: return !(a ^ b);
+    case B200FHE_MUX: return s ? b : a;
+    case B200FHE_NOT: return !a;
+    case B200FHE_COPY: return a;
+    case B200FHE_CONST0: return 0;
+    case B200FHE_CONST1: return 1;
+    case B200FHE_ANDNY: return (!a) & b;
+    case B200FHE_ORNY: return (!a) | b;
+    default: return 0;
+    }
+}
+
+}  // namespace
+
+struct b200net {
+    size_t n = 0;
+    std::vector<uint8_t> kind;
+    std::vector<int32_t> in[3];
+    std::vector<int32_t> level;                  // 0 = INPUT/DFF, k>=1 gates, OUTPUT = level of driver
+    std::vector<std::vector<uint32_t>> levels;   // levels[k-1] = gate nodes of level k
+    std::vector<uint32_t> dffs, outputs, inputs;
+    std::vector<uint32_t> slot;                  // node -> arena slot
+    std::vector<uint32_t> level_base;            // first slot of each gate level
+    size_t n_slots = 0, scratch_base = 0;
+    size_t n_boot = 0;
+    int world = 1;
+    b200fhe_ctx* ctx = nullptr;
+    // per-level batch arrays, prepared once at bind time (the "replay" part)
+    struct Batch {
+        std::vector<uint8_t> op;
+        std::vector<uint32_t> a, b, c, o;
+    };
+    std::vector<Batch> batches;
+    std::vector<uint32_t> tick_src, tick_dst;
+
+    uint32_t resolve(uint32_t node) const
+    {
+        while (kind[node] == B200NET_OUTPUT) node = (uint32_t)in[0][node];
+        return node;
+    }
+};
+
+extern "C" {
+
+const char* b200net_last_error(void) { return g_err.c_str(); }
+
+int b200net_create(b200net** out, size_t n, const uint8_t* kind, const int32_t* in0, const int32_t* in1,
+                   const int32_t* in2)
+{
+    if (!out || !kind || !in0 || !in1 || !in2) return fail("null argument");
+    *out = nullptr;
+    auto net = new b200net();
+    net->n = n;
+    net->kind.assign(kind, kind + n);
+    net->in[0].assign(in0, in0 + n);
+    net->in[1].assign(in1, in1 + n);
+    net->in[2].assign(in2, in2 + n);
+    auto bail = [&](const std::string& m) {
+        delete net;
+        return fail(m);
+    };
+    // validation (reference: TaskNetwork::checkValid, src/iyokan.hpp:1002-1015)
+    for (size_t i = 0; i < n; i++) {
+        const int ar = arity(kind[i]);
+        if (ar < 0) return bail("node " + std::to_string(i) + ": unknown kind " + std::to_string(kind[i]));
+        for (int k = 0; k < 3; k++) {
+            const int32_t v = net->in[k][i];
+            if (k < ar) {
+                if (v < 0 || (size_t)v >= n) return bail("node " + std::to_string(i) + ": input out of range");
+                if (net->kind[v] == B200NET_OUTPUT && false) return bail("unreachable");
+            } else if (v != -1) {
+                return bail("node " + std::to_string(i) + ": too many inputs for its kind");
+            }
+        }
+        if (kind[i] == B200NET_INPUT) net->inputs.push_back((uint32_t)i);
+        if (kind[i] == B200NET_DFF) net->dffs.push_back((uint32_t)i);
+        if (kind[i] == B200NET_OUTPUT) net->outputs.push_back((uint32_t)i);
+        net->n_boot += bootstraps(kind[i]);
+    }
+    // levelise with Kahn's algorithm over the combinational edges (DFF outputs are sources, DFF
+    // D-inputs are sinks), detecting combinational loops
+    std::vector<int32_t> pending(n, 0);
+    std::vector<std::vector<uint32_t>> users(n);
+    for (size_t i = 0; i < n; i++) {
+        if (kind[i] == B200NET_DFF || kind[i] == B200NET_INPUT) continue;
+        const int ar = arity(kind[i]);
+        pending[i] = ar;
+        for (int k = 0; k < ar; k++) users[net->in[k][i]].push_back((uint32_t)i);
+    }
+    net->level.assign(n, -1);
+    std::vector<uint32_t> ready;
+    for (size_t i = 0; i < n; i++)
+        if (pending[i] == 0) {
+            net->level[i] = (kind[i] == B200NET_DFF || kind[i] == B200NET_INPUT) ? 0 : 1;  // CONST gates: level 1
+            ready.push_back((uint32_t)i);
+        }
+    size_t done = 0;
+    while (!ready.empty()) {
+        const uint32_t u = ready.back();
+        ready.pop_back();
+        done++;
+        for (uint32_t v : users[u]) {
+            const int32_t lu = net->level[u] + (net->kind[v] == B200NET_OUTPUT ? 0 : 1);
+            net->level[v] = std::max(net->level[v], lu);
+            if (--pending[v] == 0) ready.push_back(v);
+        }
+    }
+    if (done != n) return bail("combinational loop in the netlist");
+    int32_t depth = 0;
+    for (size_t i = 0; i < n; i++)
+        if (is_gate(kind[i])) depth = std::max(depth, net->level[i]);
+    net->levels.resize(depth);
+    for (size_t i = 0; i < n; i++)
+        if (is_gate(kind[i])) net->levels[net->level[i] - 1].push_back((uint32_t)i);
+    *out = net;
+    return 0;
+}
+
+void b200net_destroy(b200net* net) { delete net; }
+size_t b200net_num_nodes(const b200net* net) { return net->n; }
+size_t b200net_num_levels(const b200net* net) { return net->levels.size(); }
+size_t b200net_level_width(const b200net* net, size_t l) { return l < net->levels.size() ? net->levels[l].size() : 0; }
+size_t b200net_bootstraps_per_cycle(const b200net* net) { return net->n_boot; }
+size_t b200net_num_dff(const b200net* net) { return net->dffs.size(); }
+int32_t b200net_node_level(const b200net* net, size_t node) { return node < net->n ? net->level[node] : -1; }
+uint32_t b200net_slot_of(const b200net* net, size_t node)
+{
+    return (node < net->n && !net->slot.empty()) ? net->slot[net->resolve((uint32_t)node)] : 0xFFFFFFFFu;
+}
+size_t b200net_num_slots(const b200net* net) { return net->n_slots; }
+uint32_t b200net_level_slot_base(const b200net* net, size_t l)
+{
+    return l < net->level_base.size() ? net->level_base[l] : 0xFFFFFFFFu;
+}
+
+int b200net_plain_eval(const b200net* net, uint8_t* v)
+{
+    if (!net || !v) return fail("null argument");
+    for (const auto& lv : net->levels)
+        for (uint32_t g : lv) {
+            const uint8_t a = net->in[0][g] >= 0 ? v[net->resolve(net->in[0][g])] : 0;
+            const uint8_t b = net->in[1][g] >= 0 ? v[net->resolve(net->in[1][g])] : 0;
+            const uint8_t s = net->in[2][g] >= 0 ? v[net->resolve(net->in[2][g])] : 0;
+            v[g] = plain_gate(net->kind[g], a & 1, b & 1, s & 1) & 1;
+        }
+    for (uint32_t o : net->outputs) v[o] = v[net->resolve(o)];
+    return 0;
+}
+
+int b200net_plain_tick(const b200net* net, uint8_t* v)
+{
+    if (!net || !v) return fail("null argument");
+    std::vector<uint8_t> d(net->dffs.size());
+    for (size_t i = 0; i < d.size(); i++) d[i] = v[net->resolve(net->in[0][net->dffs[i]])];
+    for (size_t i = 0; i < d.size(); i++) v[net->dffs[i]] = d[i];
+    return 0;
+}
+
+// Slot layout: [sources (INPUT, DFF)] [level 1, padded to world] [level 2, padded] ...
+int b200net_bind(b200net* net, b200fhe_ctx* ctx, int world)
+{
+    if (!net || !ctx) return fail("null argument");
+    if (world < 1) return fail("world_size must be >= 1");
+    net->ctx = ctx;
+    net->world = world;
+    net->slot.assign(net->n, 0xFFFFFFFFu);
+    uint32_t next = 0;
+    for (uint32_t i : net->inputs) net->slot[i] = next++;
+    for (uint32_t i : net->dffs) net->slot[i] = next++;
+    net->level_base.clear();
+    for (const auto& lv : net->levels) {
+        net->level_base.push_back(next);
+        for (size_t k = 0; k < lv.size(); k++) net->slot[lv[k]] = next + (uint32_t)k;
+        const size_t chunk = (lv.size() + world - 1) / world;
+        next += (uint32_t)(chunk * world);
+    }
+    net->n_slots = next;
+    net->batches.clear();
+    for (const auto& lv : net->levels) {
+        b200net::Batch bt;
+        for (uint32_t g : lv) {
+            bt.op.push_back(net->kind[g]);
+            auto s = [&](int k) { return net->in[k][g] >= 0 ? net->slot[net->resolve(net->in[k][g])] : 0u; };
+            bt.a.push_back(s(0));
+            bt.b.push_back(s(1));
+            bt.c.push_back(s(2));
+            bt.o.push_back(net->slot[g]);
+        }
+        net->batches.push_back(std::move(bt));
+    }
+    net->tick_src.clear();
+    net->tick_dst.clear();
+    for (uint32_t d : net->dffs) {
+        net->tick_src.push_back(net->slot[net->resolve(net->in[0][d])]);
+        net->tick_dst.push_back(net->slot[d]);
+    }
+    if (b200fhe_arena_alloc(ctx, std::max<size_t>(net->n_slots, 1))) return fail(b200fhe_last_error());
+    return 0;
+}
+
+int b200net_set(b200net* net, const uint32_t* nodes, const uint16_t* tlwe, size_t n)
+{
+    if (!net || !net->ctx) return fail("netlist is not bound to a context");
+    std::vector<uint32_t> s(n);
+    for (size_t i = 0; i < n; i++) {
+        if (nodes[i] >= net->n) return fail("node out of range");
+        const uint8_t k = net->kind[nodes[i]];
+        if (k != B200NET_INPUT && k != B200NET_DFF) return fail("only INPUT and DFF nodes can be set");
+        s[i] = net->slot[nodes[i]];
+    }
+    if (b200fhe_upload(net->ctx, s.data(), tlwe, n) || b200fhe_sync(net->ctx)) return fail(b200fhe_last_error());
+    return 0;
+}
+
+int b200net_get(b200net* net, const uint32_t* nodes, uint16_t* tlwe, size_t n)
+{
+    if (!net || !net->ctx) return fail("netlist is not bound to a context");
+    std::vector<uint32_t> s(n);
+    for (size_t i = 0; i < n; i++) {
+        if (nodes[i] >= net->n) return fail("node out of range");
+        s[i] = net->slot[net->resolve(nodes[i])];
+    }
+    if (b200fhe_download(net->ctx, s.data(), tlwe, n)) return fail(b200fhe_last_error());
+    return 0;
+}
+
+int b200net_tick(b200net* net)
+{
+    if (!net || !net->ctx) return fail("netlist is not bound to a context");
+    if (b200fhe_dff_tick(net->ctx, net->tick_src.data(), net->tick_dst.data(), net->tick_src.size()))
+        return fail(b200fhe_last_error());
+    return 0;
+}
+
+int b200net_run_level_shard(b200net* net, size_t level, int rank, int world)
+{
+    if (!net || !net->ctx) return fail("netlist is not bound to a context");
+    if (level >= net->batches.size()) return fail("level out of range");
+    if (world != net->world || rank < 0 || rank >= world) return fail("rank/world mismatch with bind");
+    const auto& bt = net->batches[level];
+    const size_t w = bt.op.size(), chunk = (w + world - 1) / world;
+    const size_t lo = std::min(w, (size_t)rank * chunk), hi = std::min(w, lo + chunk);
+    if (hi == lo) return 0;
+    if (b200fhe_gate_batch(net->ctx, bt.op.data() + lo, bt.a.data() + lo, bt.b.data() + lo, bt.c.data() + lo,
+                           bt.o.data() + lo, hi - lo))
+        return fail(b200fhe_last_error());
+    return 0;
+}
+
+int b200net_run(b200net* net)
+{
+    if (!net || !net->ctx) return fail("netlist is not bound to a context");
+    if (net->world != 1) return fail("b200net_run needs world_size 1; use b200net_run_level_shard");
+    for (size_t l = 0; l < net->batches.size(); l++)
+        if (b200net_run_level_shard(net, l, 0, 1)) return 1;
+    return 0;
+}
+
+}  // extern "C"

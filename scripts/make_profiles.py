@@ -1,0 +1,64 @@
+"""Copy the evidence of the latest GPU calls from gpurun_out/ (scratch) into profiles/ (tracked)."""
+import csv
+import io
+import json
+import subprocess
+import sys
+from collections import defaultdict
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+OUT = ROOT / "gpurun_out"
+PROF = ROOT / "profiles"
+ROUND = sys.argv[1] if len(sys.argv) > 1 else "r01"
+
+
+def raw_metrics(rep):
+    out = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    return dict(zip(rows[0], rows[2])), dict(zip(rows[0], rows[1]))
+
+
+def main():
+    PROF.mkdir(exist_ok=True)
+    # 1. full captures -> markdown summaries + traffic json
+    for rep in sorted(OUT.glob("prof_br_G*.ncu-rep")):
+        tag = rep.stem.replace("prof_br_", "")
+        txt = subprocess.run([sys.executable, str(ROOT / "scripts" / "ncu_summary.py"), str(rep)],
+                             capture_output=True, text=True).stdout
+        (PROF / f"{ROUND}_br_kernel_{tag}.md").write_text(
+            f"# ncu --set full --clock-control none, br_kernel ({tag}), {ROUND}\n\n"
+            f"Source: `{rep.name}` captured by scripts/gpu_ncu.sh; summarised by scripts/ncu_summary.py\n\n```\n{txt}```\n")
+        m, _ = raw_metrics(rep)
+        if tag == "G4":
+            rd = float(m["dram__bytes_read.sum"]) * 1e6
+            wr = float(m["dram__bytes_write.sum"]) * 1e6
+            jobs = int(float(m["launch__grid_size"])) * 4
+            json.dump({"kernel": "br_kernel<4>", "jobs_in_captured_launch": jobs, "dram_bytes_per_launch": rd + wr,
+                       "dram_bytes_per_job": (rd + wr) / jobs, "source": rep.name, "round": ROUND},
+                      open(PROF / "br_kernel_traffic.json", "w"), indent=1)
+    # 2. launch list
+    lc = OUT / "launches.csv"
+    if lc.exists():
+        rows = [r for r in csv.reader(l for l in open(lc) if not l.startswith("==")) if r]
+        hdr = rows[0]
+        ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+        d = defaultdict(list)
+        for r in rows[1:]:
+            if len(r) > vi:
+                d[r[ki].split("(")[0]].append(float(r[vi].replace(",", "")))
+        tot = sum(sum(v) for v in d.values())
+        lines = [f"# ncu launch list (gpu__time_duration.sum, --clock-control none), {ROUND}", "",
+                 "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv python bench.py --steps 1 --warmup 3`", "",
+                 "| kernel | launches | total ms | share |", "|---|---|---|---|"]
+        for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
+            lines.append(f"| `{k}` | {len(v)} | {sum(v) / 1e6:.3f} | {sum(v) / tot:.3f} |")
+        (PROF / f"{ROUND}_launch_list.md").write_text("\n".join(lines) + "\n")
+        (PROF / f"{ROUND}_launches.csv").write_text(open(lc).read())
+    for name in ("bench.log", "bench_ref.log", "pytest_gpu.log"):
+        if (OUT / name).exists():
+            (PROF / f"{ROUND}_{name}").write_text(open(OUT / name).read())
+
+
+if __name__ == "__main__":
+    main()

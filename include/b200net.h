@@ -53,7 +53,9 @@ uint32_t b200net_level_slot_base(const b200net *net, size_t level);
 int b200net_plain_eval(const b200net *net, uint8_t *values);
 int b200net_plain_tick(const b200net *net, uint8_t *values);
 
-/* encrypted back-end on one GPU context (keys already loaded).  Allocates the arena. */
+/* assigns arena slots for a given number of ranks (no GPU needed); implied by b200net_bind */
+int b200net_layout(b200net *net, int world_size);
+/* encrypted back-end on one GPU context (keys already loaded).  Lays out and allocates the arena. */
 int b200net_bind(b200net *net, b200fhe_ctx *ctx, int world_size);
 /* tlwe is [n][637] uint16; nodes must be INPUT or DFF nodes for set, any node for get */
 int b200net_set(b200net *net, const uint32_t *nodes, const uint16_t *tlwe, size_t n);

@@ -199,11 +199,10 @@ int b200net_plain_tick(const b200net* net, uint8_t* v)
 }
 
 // Slot layout: [sources (INPUT, DFF)] [level 1, padded to world] [level 2, padded] ...
-int b200net_bind(b200net* net, b200fhe_ctx* ctx, int world)
+int b200net_layout(b200net* net, int world)
 {
-    if (!net || !ctx) return fail("null argument");
+    if (!net) return fail("null argument");
     if (world < 1) return fail("world_size must be >= 1");
-    net->ctx = ctx;
     net->world = world;
     net->slot.assign(net->n, 0xFFFFFFFFu);
     uint32_t next = 0;
@@ -236,6 +235,14 @@ int b200net_bind(b200net* net, b200fhe_ctx* ctx, int world)
         net->tick_src.push_back(net->slot[net->resolve(net->in[0][d])]);
         net->tick_dst.push_back(net->slot[d]);
     }
+    return 0;
+}
+
+int b200net_bind(b200net* net, b200fhe_ctx* ctx, int world)
+{
+    if (!net || !ctx) return fail("null argument");
+    if (b200net_layout(net, world)) return 1;
+    net->ctx = ctx;
     if (b200fhe_arena_alloc(ctx, std::max<size_t>(net->n_slots, 1))) return fail(b200fhe_last_error());
     return 0;
 }

@@ -199,7 +199,7 @@ def load_net():
             "b200net_slot_of": (ctypes.c_uint32, [vp, sz]), "b200net_num_slots": (sz, [vp]),
             "b200net_level_slot_base": (ctypes.c_uint32, [vp, sz]),
             "b200net_plain_eval": (ci, [vp, vp]), "b200net_plain_tick": (ci, [vp, vp]),
-            "b200net_bind": (ci, [vp, vp, ci]), "b200net_set": (ci, [vp, vp, vp, sz]),
+            "b200net_layout": (ci, [vp, ci]), "b200net_bind": (ci, [vp, vp, ci]), "b200net_set": (ci, [vp, vp, vp, sz]),
             "b200net_get": (ci, [vp, vp, vp, sz]), "b200net_tick": (ci, [vp]), "b200net_run": (ci, [vp]),
             "b200net_run_level_shard": (ci, [vp, sz, ci, ci]),
         }
@@ -214,7 +214,7 @@ NET_EXPORTS = [
     "b200net_create", "b200net_destroy", "b200net_last_error", "b200net_num_nodes", "b200net_num_levels",
     "b200net_level_width", "b200net_bootstraps_per_cycle", "b200net_num_dff", "b200net_node_level",
     "b200net_slot_of", "b200net_num_slots", "b200net_level_slot_base", "b200net_plain_eval", "b200net_plain_tick",
-    "b200net_bind", "b200net_set", "b200net_get", "b200net_tick", "b200net_run", "b200net_run_level_shard",
+    "b200net_layout", "b200net_bind", "b200net_set", "b200net_get", "b200net_tick", "b200net_run", "b200net_run_level_shard",
 ]
 
 
@@ -279,6 +279,10 @@ class NetEngine:
 
     def plain_tick(self, values: np.ndarray):
         self._ck(self.lib.b200net_plain_tick(self._h, _p(values)))
+
+    def layout(self, world_size: int = 1):
+        self.world = world_size
+        self._ck(self.lib.b200net_layout(self._h, world_size))
 
     # encrypted back-end
     def bind(self, ctx: Context, world_size: int = 1):

@@ -285,7 +285,8 @@ int b200net_run_level_shard(b200net* net, size_t level, int rank, int world)
 {
     if (!net || !net->ctx) return fail("netlist is not bound to a context");
     if (level >= net->batches.size()) return fail("level out of range");
-    if (world != net->world || rank < 0 || rank >= world) return fail("rank/world mismatch with bind");
+    // world may be 1 (whole level, used for levels too narrow to shard) or the bound world size
+    if ((world != net->world && world != 1) || rank < 0 || rank >= world) return fail("rank/world mismatch with bind");
     const auto& bt = net->batches[level];
     const size_t w = bt.op.size(), chunk = (w + world - 1) / world;
     const size_t lo = std::min(w, (size_t)rank * chunk), hi = std::min(w, lo + chunk);
@@ -299,7 +300,6 @@ int b200net_run_level_shard(b200net* net, size_t level, int rank, int world)
 int b200net_run(b200net* net)
 {
     if (!net || !net->ctx) return fail("netlist is not bound to a context");
-    if (net->world != 1) return fail("b200net_run needs world_size 1; use b200net_run_level_shard");
     for (size_t l = 0; l < net->batches.size(); l++)
         if (b200net_run_level_shard(net, l, 0, 1)) return 1;
     return 0;

@@ -79,19 +79,19 @@ class PlainBackend:
 
 
 class GpuBackend:
-    """Ciphertexts on one GPU: the engine's arena wrapped as a torch tensor for the NCCL all-gather."""
+    """Ciphertexts on one GPU: the engine's arena wrapped as a torch int16 tensor (NCCL has no uint16) for the all-gather."""
 
-    elem = SLOT
+    elem = SLOT * 2  # bytes: the arena is exposed as uint8 (ProcessGroupNCCL rejects uint16 / int16)
 
     def __init__(self, nl: Netlist, eng: NetEngine, ctx, world: int):
         import torch
 
         self.nl, self.eng, self.ctx = nl, eng, ctx
         eng.bind(ctx, world)
-        n = eng.num_slots * SLOT
+        n = eng.num_slots * SLOT * 2
 
         class _Arena:
-            __cuda_array_interface__ = {"shape": (n,), "typestr": "<u2", "data": (ctx.arena_dev_ptr, False), "version": 2}
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ctx.arena_dev_ptr, False), "version": 2}
 
         self.arena = torch.as_tensor(_Arena(), device=torch.device("cuda", ctx.device))
         self._stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", ctx.device))
@@ -143,9 +143,8 @@ class ShardedRunner:
                 _, lo, hi = self._share(level)
                 self.be.run_level_shard(level, lo, hi)
         else:
-            if everyone:  # every rank computes the whole level: world==1 style call on rank 0's share of 1
-                for r in range(self.world):
-                    self.eng.run_level_shard(level, r, self.world)
+            if everyone:  # every rank computes the whole level in one batch
+                self.eng.run_level_shard(level, 0, 1)
             else:
                 self.eng.run_level_shard(level, self.rank, self.world)
 

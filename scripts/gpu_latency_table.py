@@ -1,0 +1,26 @@
+"""Blind-rotation kernel time vs batch size for each jobs-per-CTA setting (feeds the host heuristic)."""
+import json, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oracle as O
+from iyokan_b200 import Context, OPS
+keys = O.cached_keys(20261017)
+ctx = Context(0); ctx.load_keys(keys.bk, keys.ksk)
+N = 2368
+rng = np.random.default_rng(1)
+a = O.encrypt_bits(1, keys, rng.integers(0, 2, N, dtype=np.uint8)); b = O.encrypt_bits(2, keys, rng.integers(0, 2, N, dtype=np.uint8))
+ctx.arena_alloc(3 * N); ids = np.arange(3 * N, dtype=np.uint32)
+ctx.upload(ids[:N], a); ctx.upload(ids[N:2 * N], b)
+ops = np.full(N, OPS["NAND"], np.uint8)
+table = {}
+for g in (1, 2, 3, 4, 6):
+    ctx.set_jobs_per_cta(g)
+    row = {}
+    for nb in (1, 37, 74, 148, 222, 296, 444, 592, 888, 1184, 1776, 2368):
+        for rep in range(2):
+            ctx.gate_batch(ops[:nb], ids[:nb], ids[N:N + nb], None, ids[2 * N:2 * N + nb]); ctx.sync()
+        row[nb] = round(ctx.last_batch_ms()[0], 3)
+    table[g] = row
+    print(g, row, flush=True)
+json.dump(table, open(os.path.join(ROOT, "gpurun_out", "latency_table.json"), "w"), indent=1)

@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--jobs-per-cta", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -222,6 +223,8 @@ def main():
     pa, pb, ca, cb = make_inputs(keys, rank, n)
 
     ctx = Context(local_rank)
+    if args.variant:
+        ctx.set_kernel_variant(args.variant)
     if args.jobs_per_cta:
         ctx.set_jobs_per_cta(args.jobs_per_cta)
     ctx.load_keys(keys.bk, keys.ksk)

@@ -62,8 +62,12 @@ typedef struct b200fhe_ctx b200fhe_ctx;
 int b200fhe_create(b200fhe_ctx **out, int device);
 void b200fhe_destroy(b200fhe_ctx *ctx);
 const char *b200fhe_last_error(void);
-/* tuning knob: rotation jobs per CTA (1, 2, 3, 4 or 6); 0 = default */
+/* tuning knob: rotation jobs per CTA (1, 2, 3, 4 or 6); 0 = default: chosen per batch size (and kernel
+ * variant with it).  Pinning either knob switches the heuristic off. */
 int b200fhe_set_jobs_per_cta(b200fhe_ctx *ctx, int g);
+/* tuning knob: blind-rotation kernel variant. 1 = one warp per accumulator polynomial (2 warps per
+ * job), 2 = one warp per transform (6 warps per job: lower latency per dependency level) */
+int b200fhe_set_kernel_variant(b200fhe_ctx *ctx, int variant);
 
 /* keys: raw bootstrapping key + key-switching key in the reference's memory layout.
  * Copies to the device, converts the bootstrapping key to NTT form there. */

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/b200fhe.h"
+#include "br2_phases.h"
 #include "br_phases.h"
 #include "gate_jobs.h"
 #include "ks_phases.h"
@@ -87,19 +88,120 @@ br_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict_
     if (valid) br_epilogue<G>(sm, g, q, lane, ubuf + (size_t)job * U_STRIDE);
 }
 
-__global__ void __launch_bounds__(KS_THREADS)
+// "one warp per transform" variant: 6 warps per job (br2_phases.h)
+constexpr int br2_min_blocks(int G) { return G == 1 ? 4 : G == 2 ? 2 : 1; }
+
+__device__ __forceinline__ void named_barrier_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int G>
+__device__ __forceinline__ void pw2_process(const Br2Smem<G>& sm, int item, const uint32_t (&bkv)[PW2_COLS][ROWS])
+{
+    int j, half;
+    pw2_item(item, j, half);
+    const int off = tile_of_j(j);
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        uint32_t o[PW2_COLS];
+        pw2_compute<G>(sm, g, off, bkv, o);
+        __syncwarp();  // the partner lane (same position, other column half) has read its operands
+        pw2_store<G>(sm, g, half, off, o);
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(192 * G, br2_min_blocks(G))
+br2_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ arena,
+           const uint32_t* __restrict__ bk_ntt, const tw_t* __restrict__ tw2f_g, const tw_t* __restrict__ tw2i_g,
+           uint32_t* __restrict__ ubuf, int n_iter)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    constexpr int T = 192 * G;
+    Br2Smem<G> sm;
+    sm.carve(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = warp / BR2_WARPS_PER_JOB, r = warp % BR2_WARPS_PER_JOB, q = r / GL, d = r % GL;
+    const int barid = 1 + g * 2 + q;  // named barrier of the three warps that share polynomial q of job g
+
+    for (int k = tid; k < TW2_LEN; k += T) {
+        sm.tw2f[k] = tw2f_g[k];
+        sm.tw2i[k] = tw2i_g[k];
+    }
+    int job = blockIdx.x * G + g;
+    const bool valid = job < njobs;
+    if (!valid) job = njobs - 1;
+    const BrJob jb = jobs[job];
+    br2_prologue<G>(sm, jb, arena, g, q, d, lane);
+    __syncthreads();
+
+    for (int i = 0; i < n_iter; i++) {
+        const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
+        uint32_t bk0[PW2_COLS][ROWS], bk1[PW2_COLS][ROWS];
+        br2_fwd_a<G>(sm, i, g, q, d, lane);
+        __syncwarp();
+        {
+            int j, half;
+            pw2_item(tid, j, half);
+            pw2_load(bk_i, j, half, bk0);  // key words of phase M in flight during pass 2
+        }
+        br2_fwd_b<G>(sm, g, q, d, lane);
+        __syncthreads();
+        for (int item = tid; item < PW2_ITEMS; item += 2 * T) {
+            const int item1 = item + T, item2 = item + 2 * T;
+            int j, half;
+            if (item1 < PW2_ITEMS) {
+                pw2_item(item1, j, half);
+                pw2_load(bk_i, j, half, bk1);
+            }
+            pw2_process<G>(sm, item, bk0);
+            if (item1 < PW2_ITEMS) {
+                if (item2 < PW2_ITEMS) {
+                    pw2_item(item2, j, half);
+                    pw2_load(bk_i, j, half, bk0);
+                }
+                pw2_process<G>(sm, item1, bk1);
+            }
+        }
+        __syncthreads();
+        br2_inv_a<G>(sm, g, q, d, lane);
+        __syncwarp();
+        br2_inv_b<G>(sm, g, q, d, lane);
+        named_barrier_sync(barid, 96);
+        br2_combine<G>(sm, g, q, d, lane);
+        named_barrier_sync(barid, 96);
+    }
+    if (valid) br2_epilogue<G>(sm, g, q, d, lane, ubuf + (size_t)job * U_STRIDE);
+}
+
+__global__ void __launch_bounds__(KS_THREADS * KS_GROUPS)
 ks_kernel(const KsJob* __restrict__ jobs, const uint32_t* __restrict__ ubuf,
           const uint32_t* __restrict__ ksk_words, uint16_t* __restrict__ arena)
 {
     __shared__ uint16_t codes[N1];
     __shared__ uint32_t b_sh;
+    __shared__ uint32_t part[KS_GROUPS - 1][2][KS_THREADS];
     const KsJob job = jobs[blockIdx.x];
-    const int tid = threadIdx.x;
-    for (int i = tid; i < N1; i += KS_THREADS) codes[i] = ks_code(ubuf, job, i);
+    const int k = threadIdx.x, y = threadIdx.y, tid = y * KS_THREADS + k;
+    for (int i = tid; i < N1; i += KS_THREADS * KS_GROUPS) codes[i] = ks_code(ubuf, job, i);
     if (tid == 0) b_sh = ks_b_rounded(ubuf, job);
     __syncthreads();
-    const uint32_t w = ks_accumulate(ksk_words, codes, b_sh, job.post, tid);
-    reinterpret_cast<uint32_t*>(arena + (size_t)job.out * SLOT_STRIDE)[tid] = w;
+    uint32_t lo, hi;
+    ks_accumulate_group(ksk_words, codes, k, y, KS_GROUPS, lo, hi);
+    if (y > 0) {
+        part[y - 1][0][k] = lo;
+        part[y - 1][1][k] = hi;
+    }
+    __syncthreads();
+    if (y == 0) {
+#pragma unroll
+        for (int g = 0; g < KS_GROUPS - 1; g++) {
+            lo += part[g][0][k];
+            hi += part[g][1][k];
+        }
+        reinterpret_cast<uint32_t*>(arena + (size_t)job.out * SLOT_STRIDE)[k] = ks_finish(lo, hi, b_sh, job.post, k);
+    }
 }
 
 // Reads every source before any destination is written (two launches: gather, scatter) so that
@@ -167,6 +269,8 @@ struct b200fhe_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     int G = 4;
+    int variant = 1;  // 1: warp per accumulator polynomial (br_kernel), 2: warp per transform (br2_kernel)
+    bool autotune = true;  // pick (variant, G) per batch size unless the caller pinned them
     NttTables* tab = nullptr;
     tw_t* d_tw2f = nullptr;
     tw_t* d_tw2i = nullptr;
@@ -209,9 +313,49 @@ static int br_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t*
     c->launches++;
     return 0;
 }
+template <int G>
+static int br2_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+{
+    static bool attr_set[64] = {};
+    if (!attr_set[c->device]) {
+        CK(cudaFuncSetAttribute(br2_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br2Smem<G>::BYTES));
+        attr_set[c->device] = true;
+    }
+    const int grid = (njobs + G - 1) / G;
+    br2_kernel<G><<<grid, 192 * G, Br2Smem<G>::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_tw2f,
+                                                                    c->d_tw2i, ubuf, N0);
+    CK(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+// Batch-size heuristic from the measured latency table (profiles/r01_latency_table.json, B200):
+// a frontier that cannot fill the GPU is latency bound, so it gets the 6-warps-per-job kernel with
+// few jobs per CTA (6.1-7.5 ms per level); anything larger gets the throughput configuration.
+static void pick_config(const b200fhe_ctx* c, int njobs, int& variant, int& G)
+{
+    variant = c->variant;
+    G = c->G;
+    if (!c->autotune) return;
+    if (njobs <= 148) { variant = 2; G = 1; }
+    else if (njobs <= 296) { variant = 2; G = 2; }
+    else { variant = 1; G = 4; }
+}
+
 static int br_dispatch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
 {
-    switch (c->G) {
+    int variant, G;
+    pick_config(c, njobs, variant, G);
+    if (variant == 2) {
+        switch (G) {
+        case 1: return br2_launch<1>(c, njobs, arena, ubuf, d_jobs);
+        case 2: return br2_launch<2>(c, njobs, arena, ubuf, d_jobs);
+        case 3: return br2_launch<3>(c, njobs, arena, ubuf, d_jobs);
+        case 4: return br2_launch<4>(c, njobs, arena, ubuf, d_jobs);
+        default: return fail("variant 2 supports 1, 2, 3 or 4 jobs per CTA");
+        }
+    }
+    switch (G) {
     case 1: return br_launch<1>(c, njobs, arena, ubuf, d_jobs);
     case 2: return br_launch<2>(c, njobs, arena, ubuf, d_jobs);
     case 3: return br_launch<3>(c, njobs, arena, ubuf, d_jobs);
@@ -310,9 +454,24 @@ void b200fhe_destroy(b200fhe_ctx* c)
 int b200fhe_set_jobs_per_cta(b200fhe_ctx* c, int g)
 {
     if (!c) return fail("null context");
-    if (g == 0) g = 4;
+    if (g == 0) {  // back to the batch-size heuristic
+        c->autotune = true;
+        c->G = 4;
+        c->variant = 1;
+        return 0;
+    }
     if (g != 1 && g != 2 && g != 3 && g != 4 && g != 6) return fail("jobs per CTA must be 1, 2, 3, 4 or 6");
     c->G = g;
+    c->autotune = false;
+    return 0;
+}
+
+int b200fhe_set_kernel_variant(b200fhe_ctx* c, int variant)
+{
+    if (!c) return fail("null context");
+    if (variant != 1 && variant != 2) return fail("kernel variant must be 1 or 2");
+    c->variant = variant;
+    c->autotune = false;
     return 0;
 }
 
@@ -450,7 +609,7 @@ int b200fhe_gate_batch(b200fhe_ctx* c, const uint8_t* opcode, const uint32_t* in
         CK(cudaEventRecord(c->ev_t[0], c->stream));
         if (br_dispatch(c, (int)nbr, c->d_arena, c->d_ubuf, c->d_br)) return 1;
         CK(cudaEventRecord(c->ev_t[1], c->stream));
-        ks_kernel<<<(unsigned)nks, KS_THREADS, 0, c->stream>>>(c->d_ks, c->d_ubuf,
+        ks_kernel<<<(unsigned)nks, dim3(KS_THREADS, KS_GROUPS), 0, c->stream>>>(c->d_ks, c->d_ubuf,
                                                                reinterpret_cast<const uint32_t*>(c->d_ksk), c->d_arena);
         CK(cudaGetLastError());
         c->launches++;
@@ -595,7 +754,7 @@ int b200fhe_test_keyswitch(b200fhe_ctx* c, const uint32_t* tlwe1_host, uint16_t*
     CK(cudaMemcpy2DAsync(d_u, U_STRIDE * 4, tlwe1_host, TLWE1_LEN * 4, TLWE1_LEN * 4, n, cudaMemcpyHostToDevice,
                          c->stream));
     CK(cudaMemcpyAsync(d_jobs, jobs.data(), n * sizeof(KsJob), cudaMemcpyHostToDevice, c->stream));
-    ks_kernel<<<(unsigned)n, KS_THREADS, 0, c->stream>>>(d_jobs, d_u, reinterpret_cast<const uint32_t*>(c->d_ksk), d_out);
+    ks_kernel<<<(unsigned)n, dim3(KS_THREADS, KS_GROUPS), 0, c->stream>>>(d_jobs, d_u, reinterpret_cast<const uint32_t*>(c->d_ksk), d_out);
     CK(cudaGetLastError());
     c->launches++;
     CK(cudaMemcpy2DAsync(tlwe0_host, TLWE0_LEN * 2, d_out, SLOT_STRIDE * 2, TLWE0_LEN * 2, n, cudaMemcpyDeviceToHost,

@@ -41,8 +41,36 @@ B200_HD uint32_t ks_b_rounded(const uint32_t* ubuf, const KsJob& job)
     return ((b + (1u << 15)) >> 16) & 0xFFFFu;
 }
 
-// phase 2: thread k accumulates its word of every selected row.
-// ksk_words: [1024][7][3][320] uint32 (row padded to 640 uint16).
+constexpr int KS_GROUPS = 3;  // row groups per CTA: group y walks coefficients i = y, y+3, ... (latency / 3)
+
+// phase 2: thread (k, y) accumulates word k of every selected row of its coefficient group.
+// ksk_words: [1024][7][3][320] uint32 (row padded to 640 uint16).  Returns the two partial sums.
+B200_HD void ks_accumulate_group(const uint32_t* ksk_words, const uint16_t* codes, int k, int y, int ngroups,
+                                 uint32_t& lo_out, uint32_t& hi_out)
+{
+    uint32_t lo = 0, hi = 0;
+    for (int i = y; i < N1; i += ngroups) {
+        const uint32_t code = codes[i];
+        B200_UNROLL
+        for (int j = 0; j < KS_T; j++) {
+            const uint32_t g = (code >> (2 * (KS_T - 1 - j))) & 3u;
+            const uint32_t* row = ksk_words + (size_t)((i * KS_T + j) * 3 + (g ? g - 1 : 0)) * KS_THREADS;
+            const uint32_t w = g ? row[k] : 0u;
+            lo += w;
+            hi += w >> 16;
+        }
+    }
+    lo_out = lo;
+    hi_out = hi;
+}
+// final word from the summed partials
+B200_HD uint32_t ks_finish(uint32_t lo, uint32_t hi, uint32_t b_rounded, uint32_t post, int k)
+{
+    uint32_t r_lo = 0u - lo, r_hi = 0u - hi;
+    if (k == N0 / 2) r_lo += b_rounded + post;  // coefficient 636 = b lives in the low half of word 318
+    return (r_lo & 0xFFFFu) | (r_hi << 16);
+}
+
 B200_HD uint32_t ks_accumulate(const uint32_t* ksk_words, const uint16_t* codes, uint32_t b_rounded,
                                uint32_t post, int k)
 {

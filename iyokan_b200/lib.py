@@ -52,6 +52,7 @@ def load() -> ctypes.CDLL:
         "b200fhe_destroy": (None, [vp]),
         "b200fhe_last_error": (ctypes.c_char_p, []),
         "b200fhe_set_jobs_per_cta": (ci, [vp, ci]),
+        "b200fhe_set_kernel_variant": (ci, [vp, ci]),
         "b200fhe_load_keys": (ci, [vp, vp, vp]),
         "b200fhe_arena_alloc": (ci, [vp, sz]),
         "b200fhe_arena_attach": (ci, [vp, vp, sz]),
@@ -81,7 +82,8 @@ def load() -> ctypes.CDLL:
 
 
 EXPORTS = [
-    "b200fhe_create", "b200fhe_destroy", "b200fhe_last_error", "b200fhe_set_jobs_per_cta", "b200fhe_load_keys",
+    "b200fhe_create", "b200fhe_destroy", "b200fhe_last_error", "b200fhe_set_jobs_per_cta", "b200fhe_set_kernel_variant",
+    "b200fhe_load_keys",
     "b200fhe_arena_alloc", "b200fhe_arena_attach", "b200fhe_arena_slots", "b200fhe_arena_dev_ptr",
     "b200fhe_upload", "b200fhe_download", "b200fhe_gate_batch", "b200fhe_dff_tick", "b200fhe_sync",
     "b200fhe_query", "b200fhe_gates_host", "b200fhe_host_alloc", "b200fhe_host_free", "b200fhe_launch_count",
@@ -152,6 +154,9 @@ class Context:
 
     def set_jobs_per_cta(self, g: int):
         self._ck(self._lib.b200fhe_set_jobs_per_cta(self._h, g))
+
+    def set_kernel_variant(self, variant: int):
+        self._ck(self._lib.b200fhe_set_kernel_variant(self._h, variant))
 
     def load_keys(self, bk_raw: np.ndarray, ksk: np.ndarray):
         bk_raw = np.ascontiguousarray(bk_raw, dtype=np.uint32)

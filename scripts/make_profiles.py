@@ -22,7 +22,7 @@ def raw_metrics(rep):
 def main():
     PROF.mkdir(exist_ok=True)
     # 1. full captures -> markdown summaries + traffic json
-    for rep in sorted(OUT.glob("prof_br_G*.ncu-rep")):
+    for rep in sorted(OUT.glob("prof_br_v*_G*.ncu-rep")):
         tag = rep.stem.replace("prof_br_", "")
         txt = subprocess.run([sys.executable, str(ROOT / "scripts" / "ncu_summary.py"), str(rep)],
                              capture_output=True, text=True).stdout
@@ -30,9 +30,11 @@ def main():
             f"# ncu --set full --clock-control none, br_kernel ({tag}), {ROUND}\n\n"
             f"Source: `{rep.name}` captured by scripts/gpu_ncu.sh; summarised by scripts/ncu_summary.py\n\n```\n{txt}```\n")
         m, _ = raw_metrics(rep)
-        if tag == "G4":
-            rd = float(m["dram__bytes_read.sum"]) * 1e6
-            wr = float(m["dram__bytes_write.sum"]) * 1e6
+        if tag == "v1_G4":
+            unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+            _, u = raw_metrics(rep)
+            rd = float(m["dram__bytes_read.sum"]) * unit[u["dram__bytes_read.sum"]]
+            wr = float(m["dram__bytes_write.sum"]) * unit[u["dram__bytes_write.sum"]]
             jobs = int(float(m["launch__grid_size"])) * 4
             json.dump({"kernel": "br_kernel<4>", "jobs_in_captured_launch": jobs, "dram_bytes_per_launch": rd + wr,
                        "dram_bytes_per_job": (rd + wr) / jobs, "source": rep.name, "round": ROUND},
@@ -55,9 +57,12 @@ def main():
             lines.append(f"| `{k}` | {len(v)} | {sum(v) / 1e6:.3f} | {sum(v) / tot:.3f} |")
         (PROF / f"{ROUND}_launch_list.md").write_text("\n".join(lines) + "\n")
         (PROF / f"{ROUND}_launches.csv").write_text(open(lc).read())
-    for name in ("bench.log", "bench_ref.log", "pytest_gpu.log"):
+    for name in ("bench.log", "bench_ref.log", "pytest_gpu.log", "microbench_pipes.txt", "latency_table.json",
+                 "net_mux-ram-8-16-16_n1.log", "net_cahp-pearl-mux_n1.log", "mg_mux-ram-8-16-16.log",
+                 "mg_cahp-pearl-mux.log", "bench_n1.log", "bench_n2.log"):
         if (OUT / name).exists():
-            (PROF / f"{ROUND}_{name}").write_text(open(OUT / name).read())
+            txt = "\n".join(l for l in open(OUT / name).read().splitlines() if "Warning" not in l and "warn" not in l)
+            (PROF / f"{ROUND}_{name}").write_text(txt + "\n")
 
 
 if __name__ == "__main__":

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../iyokan_b200/csrc/br2_phases.h"
 #include "../../iyokan_b200/csrc/br_phases.h"
 #include "../../iyokan_b200/csrc/gate_jobs.h"
 #include "../../iyokan_b200/csrc/ks_phases.h"
@@ -181,6 +182,92 @@ extern "C" void sim_blind_rotate(int G, const void* jobs_raw, int njobs, const u
     }
 }
 
+// ---- variant 2: one warp per transform (br2_kernel) ----
+template <int G>
+static void sim_br2_cta(const BrJob* jobs, int njobs, int cta, const uint16_t* arena, const uint32_t* bk_ntt,
+                        uint32_t* ubuf, int n_iter)
+{
+    constexpr int T = 192 * G, W = 6 * G;
+    std::vector<uint8_t> smem(Br2Smem<G>::BYTES + 16);
+    Br2Smem<G> sm;
+    sm.carve(smem.data());
+    std::memcpy(sm.tw2f, g_tab.tw2f, sizeof(g_tab.tw2f));
+    std::memcpy(sm.tw2i, g_tab.tw2i, sizeof(g_tab.tw2i));
+    auto jobof = [&](int g) {
+        int j = cta * G + g;
+        return j < njobs ? j : njobs - 1;
+    };
+    auto ids = [](int w, int& g, int& q, int& d) {
+        g = w / 6;
+        q = (w % 6) / 3;
+        d = (w % 6) % 3;
+    };
+    int g, q, d;
+    for (int w = 0; w < W; w++) {
+        ids(w, g, q, d);
+        for (int lane = 0; lane < 32; lane++) br2_prologue<G>(sm, jobs[jobof(g)], arena, g, q, d, lane);
+    }
+    for (int i = 0; i < n_iter; i++) {
+        for (int w = 0; w < W; w++) {
+            ids(w, g, q, d);
+            for (int lane = 0; lane < 32; lane++) br2_fwd_a<G>(sm, i, g, q, d, lane);
+        }
+        for (int w = 0; w < W; w++) {  // all rotated reads happen before any tile is overwritten? no:
+            ids(w, g, q, d);           // fwd_a only writes the warp's own tile, acc is read-only here
+            for (int lane = 0; lane < 32; lane++) br2_fwd_b<G>(sm, g, q, d, lane);
+        }
+        const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
+        // pointwise: per warp, per item round, per job: all lanes compute, then all lanes store
+        for (int w = 0; w < W; w++)
+            for (int item0 = w * 32; item0 < PW2_ITEMS; item0 += T)
+                for (int gg = 0; gg < G; gg++) {
+                    uint32_t o[32][PW2_COLS];
+                    for (int lane = 0; lane < 32; lane++) {
+                        int j, half;
+                        pw2_item(item0 + lane, j, half);
+                        uint32_t bkv[PW2_COLS][ROWS];
+                        pw2_load(bk_i, j, half, bkv);
+                        pw2_compute<G>(sm, gg, tile_of_j(j), bkv, o[lane]);
+                    }
+                    for (int lane = 0; lane < 32; lane++) {
+                        int j, half;
+                        pw2_item(item0 + lane, j, half);
+                        pw2_store<G>(sm, gg, half, tile_of_j(j), o[lane]);
+                    }
+                }
+        for (int w = 0; w < W; w++) {
+            ids(w, g, q, d);
+            for (int lane = 0; lane < 32; lane++) br2_inv_a<G>(sm, g, q, d, lane);
+            for (int lane = 0; lane < 32; lane++) br2_inv_b<G>(sm, g, q, d, lane);
+        }
+        for (int w = 0; w < W; w++) {  // after the named barrier
+            ids(w, g, q, d);
+            for (int lane = 0; lane < 32; lane++) br2_combine<G>(sm, g, q, d, lane);
+        }
+    }
+    for (int w = 0; w < W; w++) {
+        ids(w, g, q, d);
+        if (cta * G + g >= njobs) continue;
+        for (int lane = 0; lane < 32; lane++) br2_epilogue<G>(sm, g, q, d, lane, ubuf + (size_t)(cta * G + g) * U_STRIDE);
+    }
+}
+
+extern "C" void sim_blind_rotate2(int G, const void* jobs_raw, int njobs, const uint16_t* arena,
+                                  const uint32_t* bk_ntt, uint32_t* ubuf, int n_iter)
+{
+    sim_init();
+    const BrJob* jobs = reinterpret_cast<const BrJob*>(jobs_raw);
+    const int ncta = (njobs + G - 1) / G;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int cta = 0; cta < ncta; cta++) {
+        if (G == 1) sim_br2_cta<1>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
+        else if (G == 2) sim_br2_cta<2>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
+        else if (G == 3) sim_br2_cta<3>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
+        else if (G == 4) sim_br2_cta<4>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
+        else std::abort();
+    }
+}
+
 // ksk_dev: uint16 [1024][7][3][640]; jobs: packed KsJob (16 bytes each)
 extern "C" void sim_keyswitch(const void* jobs_raw, int njobs, const uint32_t* ubuf, const uint16_t* ksk_dev,
                               uint16_t* arena)
@@ -192,8 +279,16 @@ extern "C" void sim_keyswitch(const void* jobs_raw, int njobs, const uint32_t* u
         for (int i = 0; i < N1; i++) codes[i] = ks_code(ubuf, jobs[n], i);
         const uint32_t b = ks_b_rounded(ubuf, jobs[n]);
         uint32_t* out = reinterpret_cast<uint32_t*>(arena + (size_t)jobs[n].out * SLOT_STRIDE);
-        for (int k = 0; k < KS_THREADS; k++)
-            out[k] = ks_accumulate(reinterpret_cast<const uint32_t*>(ksk_dev), codes, b, jobs[n].post, k);
+        for (int k = 0; k < KS_THREADS; k++) {  // grouped accumulation exactly as ks_kernel does it
+            uint32_t lo = 0, hi = 0;
+            for (int y = 0; y < KS_GROUPS; y++) {
+                uint32_t l, h;
+                ks_accumulate_group(reinterpret_cast<const uint32_t*>(ksk_dev), codes, k, y, KS_GROUPS, l, h);
+                lo += l;
+                hi += h;
+            }
+            out[k] = ks_finish(lo, hi, b, jobs[n].post, k);
+        }
     }
 }
 

@@ -377,10 +377,14 @@ class PlainRunner:
 
 
 class EncryptedRunner:
-    """Same cycle protocol on the GPU back-end.  `encrypt(bits) -> [n][637] uint16` is supplied by the caller
-    (key material stays outside the engine, as in Iyokan where iyokan-packet encrypts)."""
+    """Same cycle protocol on the GPU back-end (TFHEppFrontend::go, src/iyokan_tfhepp.cpp:465-566).
 
-    def __init__(self, nl: Netlist, ctx: Context, encrypt, eng: NetEngine | None = None):
+    Inputs are CIPHERTEXTS: `inputs[port]` is a TLWE stream [size][637] uint16 (what TFHEPacket.bits holds),
+    `rams` / `roms` are [bits][637] arrays (TFHEPacket.ramInTLWE / romInTLWE).  For tests that start from
+    plaintext, pass `encrypt(bits) -> [n][637]` and plain bit arrays instead; key material never enters the
+    engine, as in Iyokan where iyokan-packet encrypts and decrypts."""
+
+    def __init__(self, nl: Netlist, ctx: Context, encrypt=None, eng: NetEngine | None = None):
         self.nl, self.ctx, self.encrypt = nl, ctx, encrypt
         self.eng = eng or NetEngine(nl)
         self.eng.bind(ctx, 1)
@@ -388,37 +392,65 @@ class EncryptedRunner:
         if dffs.size:  # DFF initial value: trivial 0 (iyokan_tfhepp.hpp:23-27)
             self.eng.set(dffs, np.tile(trivial(0), (dffs.size, 1)))
 
-    def _set_nodes(self, nodes, bits, trivial_ct=False):
-        nodes = [n for n in nodes if n >= 0]
-        if not nodes:
-            return
-        bits = np.asarray(bits, np.uint8)[:len(nodes)]
-        ct = np.stack([trivial(b) for b in bits]) if trivial_ct else self.encrypt(bits)
-        self.eng.set(np.array(nodes, np.uint32), ct)
+    def _ct(self, x):
+        x = np.asarray(x)
+        if x.dtype == np.uint16 and x.ndim == 2 and x.shape[1] == TLWE0_LEN:
+            return x
+        if self.encrypt is None:
+            raise ValueError("plaintext bits given but no encrypt callback")
+        return self.encrypt(np.asarray(x, np.uint8))
+
+    def _set_nodes(self, nodes, ct):
+        keep = [i for i, n in enumerate(nodes) if n >= 0 and i < len(ct)]
+        if keep:
+            self.eng.set(np.array([nodes[i] for i in keep], np.uint32), np.ascontiguousarray(ct[keep]))
 
     def run(self, cycles, inputs=None, rams=None, roms=None):
-        inputs = inputs or {}
-        for name, bits in (roms or {}).items():
-            self._set_nodes(self.nl.mem[name], bits)
+        inputs = {p: self._ct(v) for p, v in (inputs or {}).items()}
+        for name, v in (roms or {}).items():
+            self._set_nodes(self.nl.mem[name], self._ct(v))
         has_reset = "reset" in self.nl.in_ports
         if has_reset:
             # reset pass (iyokan_tfhepp.cpp:487-500): reset <- trivial 1, every other input still holds
             # the all-zero TLWE a default-constructed Task has (the arena is zero-initialised)
-            self._set_nodes(self.nl.in_ports["reset"], [1], trivial_ct=True)
+            self._set_nodes(self.nl.in_ports["reset"], trivial(1)[None])
             self.eng.run()
         for c in range(cycles):
             self.eng.tick()
             if c == 0:
                 if has_reset:
-                    self._set_nodes(self.nl.in_ports["reset"], [0], trivial_ct=True)
-                for name, bits in (rams or {}).items():
-                    self._set_nodes(self.nl.mem[name], bits)
-            for port, stream in inputs.items():
+                    self._set_nodes(self.nl.in_ports["reset"], trivial(0)[None])
+                for name, v in (rams or {}).items():
+                    self._set_nodes(self.nl.mem[name], self._ct(v))
+            for port, stream in inputs.items():  # setCircularInputs, iyokan_tfhepp.cpp:274-296
                 w = len(self.nl.in_ports[port])
-                self._set_nodes(self.nl.in_ports[port], [stream[(w * c + b) % len(stream)] for b in range(w)])
+                idx = [(w * c + b) % len(stream) for b in range(w)]
+                self._set_nodes(self.nl.in_ports[port], stream[idx])
             self.eng.run()
         self.ctx.sync()
         return {p: self.eng.get(np.array(nodes, np.uint32)) for p, nodes in self.nl.out_ports.items()}
 
     def get_mem(self, name):
         return self.eng.get(np.array(self.nl.mem[name], np.uint32))
+
+
+def run_packet(nl: Netlist, ctx: Context, req, cycles: int | None = None):
+    """`iyokan tfhe -i req -o res` for an all-gate blueprint: TFHEPacket in, TFHEPacket out
+    (TFHEppFrontend::go + makeResPacket, src/iyokan_tfhepp.cpp:176-227,465-566)."""
+    from .packet import TFHEPacket
+
+    n = cycles if cycles is not None else req.num_cycles
+    if n is None or n < 0:
+        raise ValueError("number of cycles must be given (packet has none)")
+    for name in list(req.bits):
+        if name not in nl.in_ports:
+            raise ValueError(f"request packet drives unknown input port @{name}")
+    runner = EncryptedRunner(nl, ctx)
+    rams = {k: v for k, v in req.ram_in_tlwe.items() if k in nl.mem}
+    roms = {k: v for k, v in req.rom_in_tlwe.items() if k in nl.mem}
+    out = runner.run(n, inputs=req.bits, rams=rams, roms=roms)
+    res = TFHEPacket(bits=out, num_cycles=n)
+    for name, nodes in nl.mem.items():
+        if nl.kind[nodes[0]] == DFF:  # RAM cells are part of the result packet, ROM is not
+            res.ram_in_tlwe[name] = runner.get_mem(name)
+    return res

@@ -19,6 +19,7 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "libtfhe_oracle.so"
 REF_DRIVER = HERE / "_ref" / "ref_driver"
+IYOKAN_PACKET = HERE / "_ref" / "iyokan-packet"   # the reference's own packet tool, built unmodified
 
 N0, N1, L, T = 636, 1024, 3, 7
 TLWE0, TLWE1, ROWS = N0 + 1, N1 + 1, 6
@@ -54,7 +55,8 @@ def build(force: bool = False) -> None:
     if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < (HERE / "tfhe_oracle.c").stat().st_mtime:
         subprocess.run(["make", "-C", str(HERE), "oracle"], check=True, capture_output=True)
     if Path("/root/reference/thirdparty/cuFHE/thirdparties/TFHEpp/include").is_dir():
-        if force or not REF_DRIVER.exists() or REF_DRIVER.stat().st_mtime < (HERE / "ref_driver.cpp").stat().st_mtime:
+        if (force or not REF_DRIVER.exists() or not IYOKAN_PACKET.exists()
+                or REF_DRIVER.stat().st_mtime < (HERE / "ref_driver.cpp").stat().st_mtime):
             subprocess.run(["make", "-C", str(HERE), "-j8", "ref"], check=True, capture_output=True)
 
 
@@ -222,4 +224,14 @@ def have_ref() -> bool:
 def ref(*args, check=True) -> str:
     """Run the unmodified-reference driver (oracle/_ref/ref_driver)."""
     r = subprocess.run([str(REF_DRIVER), *map(str, args)], check=check, capture_output=True, text=True)
+    return r.stdout
+
+
+def have_iyokan_packet() -> bool:
+    return IYOKAN_PACKET.exists() and os.access(IYOKAN_PACKET, os.X_OK)
+
+
+def iyokan_packet(*args) -> str:
+    """Run the reference's iyokan-packet tool (oracle/_ref/iyokan-packet)."""
+    r = subprocess.run([str(IYOKAN_PACKET), *map(str, args)], check=True, capture_output=True, text=True)
     return r.stdout

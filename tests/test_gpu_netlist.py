@@ -99,3 +99,34 @@ def test_cahp_pearl_processor_runs_the_program(gpu_ctx, keys):
     ram = O.decrypt_bits(keys, r.get_mem("ram"))
     e = case["expected"]["ram"]["ram"]
     assert N.bytes_of(ram[:e["size"]]) == e["bytes"]
+
+
+@pytest.mark.skipif(not O.have_iyokan_packet(), reason="oracle/_ref/iyokan-packet not built")
+def test_drop_in_with_the_reference_packet_tools(tmp_path):
+    """Keys and encrypted request from the reference's own `iyokan-packet` (genkey, genevalkey, enc); this
+    back-end evaluates the netlist; the reference's `dec` + plain packets give the result (test.rb:287-315
+    flow with `iyokan tfhe` replaced).  Cases: addr-4bit-04 and counter-4bit-13."""
+    from iyokan_b200 import Context, packet as K
+
+    sk, ek = tmp_path / "sk", tmp_path / "ek"
+    O.iyokan_packet("genkey", "--type", "tfhepp", "--out", sk)
+    O.iyokan_packet("genevalkey", "--in", sk, "--out", ek)            # ~2.2 GB, as the reference writes it
+    bk, ksk = K.read_eval_key(ek, K.secret_key_params_bytes(sk))
+    ek.unlink()
+    with Context(0) as ctx:
+        ctx.load_keys(bk, ksk)
+        for name in ("addr-4bit", "counter-4bit"):
+            case = CASES[name]
+            lines = [f"cycles = {case['cycles']}"]
+            for port, e in case["request"]["bits"].items():
+                lines += ["[[bits]]", f'name = "{port}"', f"size = {e['size']}", f"bytes = {e['bytes']}"]
+            (tmp_path / "req.in").write_text("\n".join(lines) + "\n")
+            O.iyokan_packet("toml2packet", "--in", tmp_path / "req.in", "--out", tmp_path / "req")
+            O.iyokan_packet("enc", "--key", sk, "--in", tmp_path / "req", "--out", tmp_path / "req.enc")
+            res = N.run_packet(N.Netlist.load(NL / f"{name}.npz"), ctx, K.TFHEPacket.load(tmp_path / "req.enc"))
+            res.save(tmp_path / "res.enc")
+            O.iyokan_packet("dec", "--key", sk, "--in", tmp_path / "res.enc", "--out", tmp_path / "res")
+            plain = K.PlainPacket.loads((tmp_path / "res").read_bytes())
+            assert plain.num_cycles == case["cycles"]
+            for port, e in case["expected"]["bits"].items():
+                assert N.bytes_of(plain.bits[port][:e["size"]]) == e["bytes"], (name, port)

@@ -66,7 +66,8 @@ const char *b200fhe_last_error(void);
  * variant with it).  Pinning either knob switches the heuristic off. */
 int b200fhe_set_jobs_per_cta(b200fhe_ctx *ctx, int g);
 /* tuning knob: blind-rotation kernel variant. 1 = one warp per accumulator polynomial (2 warps per
- * job), 2 = one warp per transform (6 warps per job: lower latency per dependency level) */
+ * job), 2 = one warp per transform (6 warps per job: lower latency per dependency level),
+ * 3 = as 1 with the three transforms of a warp interleaved (more ILP per warp) */
 int b200fhe_set_kernel_variant(b200fhe_ctx *ctx, int variant);
 
 /* keys: raw bootstrapping key + key-switching key in the reference's memory layout.

@@ -88,6 +88,54 @@ br_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict_
     if (valid) br_epilogue<G>(sm, g, q, lane, ubuf + (size_t)job * U_STRIDE);
 }
 
+// interleaved variant: same decomposition as br_kernel, but the three transforms a warp owns run in
+// lock step (ct_stage3 / gs_stage3): 3x the ILP per warp and one twiddle fetch for three butterflies
+template <int G>
+__global__ void __launch_bounds__(64 * G, 1)
+br3_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ arena,
+           const uint32_t* __restrict__ bk_ntt, const tw_t* __restrict__ tw2f_g, const tw_t* __restrict__ tw2i_g,
+           uint32_t* __restrict__ ubuf, int n_iter)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    BrSmem<G> sm;
+    sm.carve(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = warp >> 1, q = warp & 1;
+    for (int k = tid; k < TW2_LEN; k += 64 * G) {
+        sm.tw2f[k] = tw2f_g[k];
+        sm.tw2i[k] = tw2i_g[k];
+    }
+    int job = blockIdx.x * G + g;
+    const bool valid = job < njobs;
+    if (!valid) job = njobs - 1;
+    const BrJob jb = jobs[job];
+    uint32_t accr[32];
+    br_prologue<G>(sm, jb, arena, g, q, lane, accr);
+    __syncthreads();
+    for (int i = 0; i < n_iter; i++) {
+        const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
+        uint32_t bk0[BK_COLS][ROWS];
+        {
+            uint32_t x0[32], x1[32], x2[32];
+            br_fwd3_a<G>(sm, i, g, q, lane, accr, x0, x1, x2);
+            __syncwarp();
+            br_fwd3_b<G>(sm, g, q, lane, x0, x1, x2);
+        }
+        __syncwarp();
+        br_fwd3_c<G>(sm, g, q, lane);
+        pw_load(bk_i, tid, bk0);
+        __syncthreads();
+        br_pointwise<G>(sm, bk_i, tid, bk0);
+        __syncthreads();
+        br_inv3_a<G>(sm, g, q, lane);
+        __syncwarp();
+        br_inv3_b<G>(sm, g, q, lane, accr);
+        __syncwarp();
+        br_inv3_c<G>(sm, g, q, lane, accr);
+        __syncwarp();
+    }
+    if (valid) br_epilogue<G>(sm, g, q, lane, ubuf + (size_t)job * U_STRIDE);
+}
+
 // "one warp per transform" variant: 6 warps per job (br2_phases.h)
 constexpr int br2_min_blocks(int G) { return G == 1 ? 4 : G == 2 ? 2 : 1; }
 
@@ -329,23 +377,62 @@ static int br2_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
     return 0;
 }
 
-// Batch-size heuristic from the measured latency table (profiles/r01_latency_table.json, B200):
-// a frontier that cannot fill the GPU is latency bound, so it gets the 6-warps-per-job kernel with
-// few jobs per CTA (6.1-7.5 ms per level); anything larger gets the throughput configuration.
+// Batch-size heuristic from the measured latency tables (profiles/r01_latency_table*.json, B200, ms per
+// launch).  A frontier that cannot fill the GPU is latency bound and gets the 6-warps-per-job kernel with
+// few jobs per CTA; larger ones get the throughput kernels, choosing the CTA size whose wave quantisation
+// wastes least (592 or 888 jobs per wave).
 static void pick_config(const b200fhe_ctx* c, int njobs, int& variant, int& G)
 {
     variant = c->variant;
     G = c->G;
     if (!c->autotune) return;
-    if (njobs <= 148) { variant = 2; G = 1; }
-    else if (njobs <= 296) { variant = 2; G = 2; }
-    else { variant = 1; G = 4; }
+    struct Cand { int variant, G; double ms; };
+    const double inf = 1e30;
+    auto waves = [&](int per_wave) { return (double)((njobs + per_wave - 1) / per_wave); };
+    static const double v2g1[4] = {6.5, 7.8, 10.6, 13.4};  // 1..4 CTAs per SM resident
+    const Cand cands[] = {
+        {2, 1, njobs <= 592 ? v2g1[(njobs - 1) / 148] : inf},
+        {2, 2, njobs <= 296 ? 7.45 : (njobs <= 592 ? 11.65 : inf)},
+        {3, 4, waves(592) * 10.25},
+        {3, 6, waves(888) * 14.68},
+    };
+    double best = inf;
+    for (const Cand& k : cands)
+        if (k.ms < best) {
+            best = k.ms;
+            variant = k.variant;
+            G = k.G;
+        }
+}
+
+template <int G>
+static int br3_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+{
+    static bool attr_set[64] = {};
+    if (!attr_set[c->device]) {
+        CK(cudaFuncSetAttribute(br3_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BrSmem<G>::BYTES));
+        attr_set[c->device] = true;
+    }
+    const int grid = (njobs + G - 1) / G;
+    br3_kernel<G><<<grid, 64 * G, BrSmem<G>::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_tw2f,
+                                                                  c->d_tw2i, ubuf, N0);
+    CK(cudaGetLastError());
+    c->launches++;
+    return 0;
 }
 
 static int br_dispatch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
 {
     int variant, G;
     pick_config(c, njobs, variant, G);
+    if (variant == 3) {
+        switch (G) {
+        case 2: return br3_launch<2>(c, njobs, arena, ubuf, d_jobs);
+        case 4: return br3_launch<4>(c, njobs, arena, ubuf, d_jobs);
+        case 6: return br3_launch<6>(c, njobs, arena, ubuf, d_jobs);
+        default: return fail("variant 3 supports 2, 4 or 6 jobs per CTA");
+        }
+    }
     if (variant == 2) {
         switch (G) {
         case 1: return br2_launch<1>(c, njobs, arena, ubuf, d_jobs);
@@ -469,7 +556,7 @@ int b200fhe_set_jobs_per_cta(b200fhe_ctx* c, int g)
 int b200fhe_set_kernel_variant(b200fhe_ctx* c, int variant)
 {
     if (!c) return fail("null context");
-    if (variant != 1 && variant != 2) return fail("kernel variant must be 1 or 2");
+    if (variant < 1 || variant > 3) return fail("kernel variant must be 1, 2 or 3");
     c->variant = variant;
     c->autotune = false;
     return 0;

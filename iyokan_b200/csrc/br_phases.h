@@ -151,6 +151,94 @@ B200_HD void br_fwd_b(const BrSmem<G>& sm, int g, int q, int lane, int d)
     tile_store_row(t, x, lane);
 }
 
+// ---- interleaved variant (br3_kernel): the three digit / limb transforms of a polynomial run in
+// lock step inside the owning warp (see ct_stage3 in ntt_warp.h).  Same tiles, same barriers.
+// F3a: rotated difference -> three digits -> pass 1 x3; returns the three register sets so the
+// caller can __syncwarp (the accumulator copy shares tile 3q) before F3b stores them.
+template <int G>
+B200_HD void br_fwd3_a(const BrSmem<G>& sm, int i, int g, int q, int lane, const uint32_t (&accr)[32],
+                       uint32_t (&x0)[32], uint32_t (&x1)[32], uint32_t (&x2)[32])
+{
+    const uint32_t abar = sm.abar[g * SLOT_STRIDE + i];
+    const uint32_t* acc = sm.acc(g, q);
+    const uint32_t base = ((uint32_t)lane - abar) & (2u * N1 - 1);
+    B200_UNROLL
+    for (int a = 0; a < 32; a++) {
+        const uint32_t m = (base + 32u * a) & (2u * N1 - 1);
+        const uint32_t v = acc[m & (N1 - 1)];
+        const uint32_t neg = 0u - ((m >> NBIT) & 1u);
+        const uint32_t dv = ((v ^ neg) - neg) - accr[a] + (DEC_OFFSET + DEC_ROUND);
+        constexpr uint32_t mask = (1u << BGBIT) - 1, bias = P - (1u << (BGBIT - 1));
+        x0[a] = ((dv >> (32 - BGBIT)) & mask) + bias;
+        x1[a] = ((dv >> (32 - 2 * BGBIT)) & mask) + bias;
+        x2[a] = ((dv >> (32 - 3 * BGBIT)) & mask) + bias;
+    }
+    fwd_pass1_x3(x0, x1, x2);
+}
+// F3b (after __syncwarp): three column stores
+template <int G>
+B200_HD void br_fwd3_b(const BrSmem<G>& sm, int g, int q, int lane, const uint32_t (&x0)[32],
+                       const uint32_t (&x1)[32], const uint32_t (&x2)[32])
+{
+    tile_store_col(sm.tile(g, q * GL + 0), x0, lane);
+    tile_store_col(sm.tile(g, q * GL + 1), x1, lane);
+    tile_store_col(sm.tile(g, q * GL + 2), x2, lane);
+}
+// F3c (after __syncwarp): three row loads -> pass 2 x3 -> three row stores
+template <int G>
+B200_HD void br_fwd3_c(const BrSmem<G>& sm, int g, int q, int lane)
+{
+    uint32_t x0[32], x1[32], x2[32];
+    uint32_t* t = sm.tile(g, q * GL);
+    tile_load_row(t, x0, lane);
+    tile_load_row(t + TILE_WORDS, x1, lane);
+    tile_load_row(t + 2 * TILE_WORDS, x2, lane);
+    fwd_pass2_x3(x0, x1, x2, sm.tw2f, lane);
+    tile_store_row(t, x0, lane);
+    tile_store_row(t + TILE_WORDS, x1, lane);
+    tile_store_row(t + 2 * TILE_WORDS, x2, lane);
+}
+// I3a: three row loads -> inverse pass 1 x3 -> three row stores
+template <int G>
+B200_HD void br_inv3_a(const BrSmem<G>& sm, int g, int q, int lane)
+{
+    uint32_t x0[32], x1[32], x2[32];
+    uint32_t* t = sm.tile(g, q * LIMBS);
+    tile_load_row(t, x0, lane);
+    tile_load_row(t + TILE_WORDS, x1, lane);
+    tile_load_row(t + 2 * TILE_WORDS, x2, lane);
+    inv_pass1_x3(x0, x1, x2, sm.tw2i, lane);
+    tile_store_row(t, x0, lane);
+    tile_store_row(t + TILE_WORDS, x1, lane);
+    tile_store_row(t + 2 * TILE_WORDS, x2, lane);
+}
+// I3b (after __syncwarp): three column loads -> inverse pass 2 x3 -> lift, recombine, accumulate,
+// refresh the accumulator copy (tile 3q is dead by now: all three limbs are in registers)
+template <int G>
+B200_HD void br_inv3_b(const BrSmem<G>& sm, int g, int q, int lane, uint32_t (&accr)[32])
+{
+    uint32_t x0[32], x1[32], x2[32];
+    uint32_t* t = sm.tile(g, q * LIMBS);
+    tile_load_col(t, x0, lane);
+    tile_load_col(t + TILE_WORDS, x1, lane);
+    tile_load_col(t + 2 * TILE_WORDS, x2, lane);
+    inv_pass2_x3(x0, x1, x2);
+    B200_UNROLL
+    for (int a = 0; a < 32; a++) {
+        const uint32_t v = (uint32_t)centered_lift(x0[a]) + ((uint32_t)centered_lift(x1[a]) << LIMB_BITS) +
+                           ((uint32_t)centered_lift(x2[a]) << (2 * LIMB_BITS));
+        accr[a] += v;
+    }
+}
+// I3c (after __syncwarp: every lane has finished its column loads of tile 3q): refresh the copy
+template <int G>
+B200_HD void br_inv3_c(const BrSmem<G>& sm, int g, int q, int lane, const uint32_t (&accr)[32])
+{
+    uint32_t* acc = sm.acc(g, q);
+    B200_UNROLL
+    for (int a = 0; a < 32; a++) acc[32 * a + lane] = accr[a];
+}
+
 // ---- phase M: pointwise multiply-accumulate with the NTT-domain key ----------------------
 // bk_i points at bk_ntt[i] : [BK_COLS][ROWS][1024] uint32 in [0,p), pre-scaled by 2^32/N.
 // out[g][c][j] = sum_r D[g][r][j] * BK[c][r][j] * 2^-32  (in place over the digit tiles).

@@ -192,6 +192,85 @@ B200_HD void inv_pass2(uint32_t (&x)[32])
     gs_stage<0, 1>(x, [](int g) { return twi_u(1 + g); });
 }
 
+// ---- three transforms interleaved in one lane -------------------------------------------
+// A warp that owns the three digit (or limb) polynomials of one accumulator polynomial can run
+// them in lock step: 48 independent butterflies per stage instead of 16 (more ILP per warp, so
+// fewer warps saturate the multiply pipe) and ONE twiddle fetch per group instead of three.
+template <int LS, int FIX, class TwFn>
+B200_HD void ct_stage3(uint32_t (&x0)[32], uint32_t (&x1)[32], uint32_t (&x2)[32], TwFn tw)
+{
+    constexpr int half = 16 >> LS;
+    B200_UNROLL
+    for (int g = 0; g < (1 << LS); g++) {
+        const tw_t w = tw(g);
+        B200_UNROLL
+        for (int k = 0; k < half; k++) {
+            const int i0 = g * 2 * half + k, i1 = i0 + half;
+            const uint32_t X0 = apply_fix<FIX>(x0[i0]), X1 = apply_fix<FIX>(x1[i0]), X2 = apply_fix<FIX>(x2[i0]);
+            const uint32_t T0 = shoup_mul(x0[i1], w), T1 = shoup_mul(x1[i1], w), T2 = shoup_mul(x2[i1], w);
+            x0[i0] = X0 + T0;
+            x0[i1] = X0 - T0 + P2;
+            x1[i0] = X1 + T1;
+            x1[i1] = X1 - T1 + P2;
+            x2[i0] = X2 + T2;
+            x2[i1] = X2 - T2 + P2;
+        }
+    }
+}
+template <int LS, int FIX, class TwFn>
+B200_HD void gs_stage3(uint32_t (&x0)[32], uint32_t (&x1)[32], uint32_t (&x2)[32], TwFn tw)
+{
+    constexpr int half = 16 >> LS;
+    B200_UNROLL
+    for (int g = 0; g < (1 << LS); g++) {
+        const tw_t w = tw(g);
+        B200_UNROLL
+        for (int k = 0; k < half; k++) {
+            const int i0 = g * 2 * half + k, i1 = i0 + half;
+            const uint32_t U0 = x0[i0], V0 = x0[i1], U1 = x1[i0], V1 = x1[i1], U2 = x2[i0], V2 = x2[i1];
+            x0[i0] = apply_fix<FIX>(U0 + V0);
+            x1[i0] = apply_fix<FIX>(U1 + V1);
+            x2[i0] = apply_fix<FIX>(U2 + V2);
+            x0[i1] = shoup_mul(U0 - V0 + P4, w);
+            x1[i1] = shoup_mul(U1 - V1 + P4, w);
+            x2[i1] = shoup_mul(U2 - V2 + P4, w);
+        }
+    }
+}
+#define B200_X3 uint32_t (&x0)[32], uint32_t (&x1)[32], uint32_t (&x2)[32]
+B200_HD void fwd_pass1_x3(B200_X3)
+{
+    ct_stage3<0, 0>(x0, x1, x2, [](int g) { return twf_u(1 + g); });
+    ct_stage3<1, 0>(x0, x1, x2, [](int g) { return twf_u(2 + g); });
+    ct_stage3<2, 0>(x0, x1, x2, [](int g) { return twf_u(4 + g); });
+    ct_stage3<3, 1>(x0, x1, x2, [](int g) { return twf_u(8 + g); });
+    ct_stage3<4, 0>(x0, x1, x2, [](int g) { return twf_u(16 + g); });
+}
+B200_HD void fwd_pass2_x3(B200_X3, const tw_t* tw2, int lane)
+{
+    ct_stage3<0, 1>(x0, x1, x2, [=](int g) { return tw2[(0 + g) * 32 + lane]; });
+    ct_stage3<1, 0>(x0, x1, x2, [=](int g) { return tw2[(1 + g) * 32 + lane]; });
+    ct_stage3<2, 1>(x0, x1, x2, [=](int g) { return tw2[(3 + g) * 32 + lane]; });
+    ct_stage3<3, 0>(x0, x1, x2, [=](int g) { return tw2[(7 + g) * 32 + lane]; });
+    ct_stage3<4, 2>(x0, x1, x2, [=](int g) { return tw2[(15 + g) * 32 + lane]; });
+}
+B200_HD void inv_pass1_x3(B200_X3, const tw_t* tw2, int lane)
+{
+    gs_stage3<4, 1>(x0, x1, x2, [=](int g) { return tw2[(15 + g) * 32 + lane]; });
+    gs_stage3<3, 1>(x0, x1, x2, [=](int g) { return tw2[(7 + g) * 32 + lane]; });
+    gs_stage3<2, 1>(x0, x1, x2, [=](int g) { return tw2[(3 + g) * 32 + lane]; });
+    gs_stage3<1, 1>(x0, x1, x2, [=](int g) { return tw2[(1 + g) * 32 + lane]; });
+    gs_stage3<0, 1>(x0, x1, x2, [=](int g) { return tw2[(0 + g) * 32 + lane]; });
+}
+B200_HD void inv_pass2_x3(B200_X3)
+{
+    gs_stage3<4, 1>(x0, x1, x2, [](int g) { return twi_u(16 + g); });
+    gs_stage3<3, 1>(x0, x1, x2, [](int g) { return twi_u(8 + g); });
+    gs_stage3<2, 1>(x0, x1, x2, [](int g) { return twi_u(4 + g); });
+    gs_stage3<1, 1>(x0, x1, x2, [](int g) { return twi_u(2 + g); });
+    gs_stage3<0, 1>(x0, x1, x2, [](int g) { return twi_u(1 + g); });
+}
+
 // ---- tile access -----------------------------------------------------------------------
 // column access: register index = a, lane = b  (32-bit, conflict free)
 B200_HD void tile_store_col(uint32_t* tile, const uint32_t (&x)[32], int lane)

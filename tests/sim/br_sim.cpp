@@ -182,6 +182,77 @@ extern "C" void sim_blind_rotate(int G, const void* jobs_raw, int njobs, const u
     }
 }
 
+// ---- variant 3: interleaved transforms (br3_kernel) ----
+template <int G>
+static void sim_br3_cta(const BrJob* jobs, int njobs, int cta, const uint16_t* arena, const uint32_t* bk_ntt,
+                        uint32_t* ubuf, int n_iter)
+{
+    constexpr int T = 64 * G, W = 2 * G;
+    std::vector<uint8_t> smem(BrSmem<G>::BYTES + 16);
+    BrSmem<G> sm;
+    sm.carve(smem.data());
+    std::memcpy(sm.tw2f, g_tab.tw2f, sizeof(g_tab.tw2f));
+    std::memcpy(sm.tw2i, g_tab.tw2i, sizeof(g_tab.tw2i));
+    struct Regs {
+        uint32_t accr[32], x0[32], x1[32], x2[32];
+    };
+    std::vector<Regs> regs(T);
+    auto jobof = [&](int g) {
+        int j = cta * G + g;
+        return j < njobs ? j : njobs - 1;
+    };
+    for (int w = 0; w < W; w++)
+        for (int lane = 0; lane < 32; lane++)
+            br_prologue<G>(sm, jobs[jobof(w >> 1)], arena, w >> 1, w & 1, lane, regs[w * 32 + lane].accr);
+    for (int i = 0; i < n_iter; i++) {
+        for (int w = 0; w < W; w++) {
+            const int g = w >> 1, q = w & 1;
+            for (int lane = 0; lane < 32; lane++) {
+                Regs& r = regs[w * 32 + lane];
+                br_fwd3_a<G>(sm, i, g, q, lane, r.accr, r.x0, r.x1, r.x2);
+            }
+            for (int lane = 0; lane < 32; lane++) {
+                Regs& r = regs[w * 32 + lane];
+                br_fwd3_b<G>(sm, g, q, lane, r.x0, r.x1, r.x2);
+            }
+            for (int lane = 0; lane < 32; lane++) br_fwd3_c<G>(sm, g, q, lane);
+        }
+        const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
+        for (int tid = 0; tid < T; tid++) {
+            uint32_t bk0[BK_COLS][ROWS];
+            pw_load(bk_i, tid, bk0);
+            br_pointwise<G>(sm, bk_i, tid, bk0);
+        }
+        for (int w = 0; w < W; w++) {
+            const int g = w >> 1, q = w & 1;
+            for (int lane = 0; lane < 32; lane++) br_inv3_a<G>(sm, g, q, lane);
+            for (int lane = 0; lane < 32; lane++) br_inv3_b<G>(sm, g, q, lane, regs[w * 32 + lane].accr);
+            for (int lane = 0; lane < 32; lane++) br_inv3_c<G>(sm, g, q, lane, regs[w * 32 + lane].accr);
+        }
+    }
+    for (int w = 0; w < W; w++) {
+        const int g = w >> 1, q = w & 1;
+        if (cta * G + g >= njobs) continue;
+        for (int lane = 0; lane < 32; lane++)
+            br_epilogue<G>(sm, g, q, lane, ubuf + (size_t)(cta * G + g) * U_STRIDE);
+    }
+}
+
+extern "C" void sim_blind_rotate3(int G, const void* jobs_raw, int njobs, const uint16_t* arena,
+                                  const uint32_t* bk_ntt, uint32_t* ubuf, int n_iter)
+{
+    sim_init();
+    const BrJob* jobs = reinterpret_cast<const BrJob*>(jobs_raw);
+    const int ncta = (njobs + G - 1) / G;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int cta = 0; cta < ncta; cta++) {
+        if (G == 2) sim_br3_cta<2>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
+        else if (G == 4) sim_br3_cta<4>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
+        else if (G == 6) sim_br3_cta<6>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
+        else std::abort();
+    }
+}
+
 // ---- variant 2: one warp per transform (br2_kernel) ----
 template <int G>
 static void sim_br2_cta(const BrJob* jobs, int njobs, int cta, const uint16_t* arena, const uint32_t* bk_ntt,

@@ -51,6 +51,18 @@ def test_blind_rotate_variant2_bit_exact(gpu_ctx, keys, golden, G):
         gpu_ctx.set_jobs_per_cta(0)
 
 
+@pytest.mark.parametrize("G", [2, 4, 6])
+def test_blind_rotate_variant3_bit_exact(gpu_ctx, keys, golden, G):
+    gpu_ctx.set_kernel_variant(3)
+    gpu_ctx.set_jobs_per_cta(G)
+    try:
+        c = golden["br_in"][:3]
+        assert np.array_equal(gpu_ctx.test_bootstrap_lvl1(c), O.bootstrap_to_lvl1(keys, c))
+    finally:
+        gpu_ctx.set_kernel_variant(1)
+        gpu_ctx.set_jobs_per_cta(0)
+
+
 def test_blind_rotate_edge_inputs(gpu_ctx, keys):
     c = np.zeros((3, 637), np.uint16)
     c[0, :8] = [0xFFFF, 0xFFF0, 0, 15, 0x8000, 0x7FF0, 0x8010, 0x0010]   # a-bar = 2N, 0, N, ...

@@ -503,12 +503,15 @@ int b200fhe_create(b200fhe_ctx** out, int device)
     for (auto& e : c->ev_t) CK(cudaEventCreate(&e));
     c->tab = new NttTables();
     ntt_tables_init(*c->tab);
-    CK(cudaMemcpyToSymbol(c_twf_u, h_twf_u, sizeof(h_twf_u)));
-    CK(cudaMemcpyToSymbol(c_twi_u, h_twi_u, sizeof(h_twi_u)));
+    // every transfer goes through the context's non-blocking stream: the legacy default stream is not
+    // ordered with it
+    CK(cudaMemcpyToSymbolAsync(c_twf_u, h_twf_u, sizeof(h_twf_u), 0, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyToSymbolAsync(c_twi_u, h_twi_u, sizeof(h_twi_u), 0, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMalloc(&c->d_tw2f, sizeof(c->tab->tw2f)));
     CK(cudaMalloc(&c->d_tw2i, sizeof(c->tab->tw2i)));
-    CK(cudaMemcpy(c->d_tw2f, c->tab->tw2f, sizeof(c->tab->tw2f), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->d_tw2i, c->tab->tw2i, sizeof(c->tab->tw2i), cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(c->d_tw2f, c->tab->tw2f, sizeof(c->tab->tw2f), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_tw2i, c->tab->tw2i, sizeof(c->tab->tw2i), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     *out = c;
     return 0;
 }
@@ -598,7 +601,10 @@ int b200fhe_arena_alloc(b200fhe_ctx* c, size_t n_slots)
     if (c->arena_owned && c->d_arena) CK(cudaFree(c->d_arena));
     c->d_arena = nullptr;
     CK(cudaMalloc(&c->d_arena, n_slots * SLOT_STRIDE * 2));
-    CK(cudaMemset(c->d_arena, 0, n_slots * SLOT_STRIDE * 2));
+    // on the context's own (non-blocking) stream: a legacy-stream memset would not be ordered with the
+    // uploads that follow and could wipe them
+    CK(cudaMemsetAsync(c->d_arena, 0, n_slots * SLOT_STRIDE * 2, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     c->arena_owned = true;
     c->n_slots = n_slots;
     return 0;
@@ -860,7 +866,8 @@ int b200fhe_test_read_bk_ntt(b200fhe_ctx* c, uint32_t* out_host, size_t first_i,
     if (first_i + count_i > (size_t)N0) return fail("range");
     if (set_dev(c)) return 1;
     const size_t per = (size_t)BK_COLS * ROWS * N1;
-    CK(cudaMemcpy(out_host, c->d_bk_ntt + first_i * per, count_i * per * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(out_host, c->d_bk_ntt + first_i * per, count_i * per * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

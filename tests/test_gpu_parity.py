@@ -131,6 +131,19 @@ def test_resident_slots_and_dff_tick(gpu_ctx, keys):
     assert np.array_equal(out[0], x[0]) and np.array_equal(out[1], (-x[0].astype(np.int32)).astype(np.uint16))
 
 
+def test_arena_realloc_is_ordered_with_uploads(gpu_ctx):
+    # regression: the arena's zero-fill must run on the context's stream, before the uploads that follow
+    rng = np.random.default_rng(1)
+    for it in range(20):
+        n = 64 + 37 * it
+        data = rng.integers(0, 2**16, (n, 637), dtype=np.uint16)
+        gpu_ctx.arena_alloc(n + 3)
+        ids = np.arange(n, dtype=np.uint32)
+        gpu_ctx.upload(ids, data)
+        assert np.array_equal(gpu_ctx.download(ids), data), it
+        assert not gpu_ctx.download(np.array([n, n + 2], np.uint32)).any()
+
+
 def test_error_behaviour(gpu_ctx):
     from iyokan_b200 import B200FheError, Context
 

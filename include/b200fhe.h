@@ -67,7 +67,9 @@ const char *b200fhe_last_error(void);
 int b200fhe_set_jobs_per_cta(b200fhe_ctx *ctx, int g);
 /* tuning knob: blind-rotation kernel variant. 1 = one warp per accumulator polynomial (2 warps per
  * job), 2 = one warp per transform (6 warps per job: lower latency per dependency level),
- * 3 = as 1 with the three transforms of a warp interleaved (more ILP per warp) */
+ * 3 = as 1 with the three transforms of a warp interleaved (more ILP per warp),
+ * 4 = one job per CTA, 12 warps (6 teams of 64 threads), key staged into shared memory by bulk-async
+ *     copies: the lowest latency for one dependency level (jobs-per-CTA is ignored) */
 int b200fhe_set_kernel_variant(b200fhe_ctx *ctx, int variant);
 
 /* keys: raw bootstrapping key + key-switching key in the reference's memory layout.

@@ -15,6 +15,7 @@
 
 #include "../../include/b200fhe.h"
 #include "br2_phases.h"
+#include "br4_phases.h"
 #include "br_phases.h"
 #include "gate_jobs.h"
 #include "ks_phases.h"
@@ -223,6 +224,88 @@ br2_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict
     if (valid) br2_epilogue<G>(sm, g, q, d, lane, ubuf + (size_t)job * U_STRIDE);
 }
 
+
+// ---- latency shape: one job per CTA, 6 teams of 64 threads, key staged by bulk-async copies ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// one thread: arm the barrier with the byte count and issue the bulk copies of bk_ntt[i] (6 x 24 KB)
+__device__ __forceinline__ void key_stage_issue(const Br4Smem& sm, const uint32_t* bk_i)
+{
+    constexpr uint32_t CHUNK = ROWS * N1 * 4;  // one output column: 24,576 B
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the buffer precede the async writes
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(sm.mbar)),
+                 "r"((uint32_t)(BK_COLS * CHUNK))
+                 : "memory");
+#pragma unroll
+    for (int c = 0; c < BK_COLS; c++)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(sm.keyb + (size_t)c * ROWS * N1)),
+                     "l"(bk_i + (size_t)c * ROWS * N1), "r"(CHUNK), "r"(smem_u32(sm.mbar))
+                     : "memory");
+}
+
+__global__ void __launch_bounds__(BR4_THREADS, 1)
+br4_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ arena,
+           const uint32_t* __restrict__ bk_ntt, const BlockTw* __restrict__ tw_g, uint32_t* __restrict__ ubuf, int n_iter)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Br4Smem sm;
+    sm.carve(smem_raw);
+    const int tid = threadIdx.x, team = tid >> 6, t = tid & 63, q = team / GL, d = team % GL;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tw_g);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(sm.tw);
+        for (int k = tid; k < (int)(sizeof(BlockTw) / 4); k += BR4_THREADS) dst[k] = src[k];
+    }
+    if (tid == 0) mbar_init(sm.mbar, 1);
+    const int job = blockIdx.x;
+    const BrJob jb = jobs[job];
+    br4_prologue(sm, jb, arena, tid);
+    __syncthreads();
+    if (tid == 0 && n_iter > 0) key_stage_issue(sm, bk_ntt);
+
+    for (int i = 0; i < n_iter; i++) {
+        br4_fwd_p1(sm, i, q, d, t);
+        named_barrier_sync(1 + team, TEAM_THREADS);
+        br4_fwd_p2(sm, q, d, t);
+        named_barrier_sync(1 + team, TEAM_THREADS);
+        br4_fwd_p3(sm, q, d, t);
+        mbar_wait(sm.mbar, (uint32_t)(i & 1));  // key of step i has landed
+        __syncthreads();
+        br4_pointwise_item(sm, tid);
+        br4_pointwise_item(sm, tid + BR4_THREADS);
+        __syncthreads();
+        if (tid == 0 && i + 1 < n_iter) key_stage_issue(sm, bk_ntt + (size_t)(i + 1) * BR4_KEY_WORDS);
+        br4_inv_pA(sm, q, d, t);
+        named_barrier_sync(1 + team, TEAM_THREADS);
+        br4_inv_pB(sm, q, d, t);
+        named_barrier_sync(1 + team, TEAM_THREADS);
+        br4_inv_pC(sm, q, d, t);
+        named_barrier_sync(7 + q, GL * TEAM_THREADS);  // the three limb teams of polynomial q
+    }
+    __syncthreads();
+    br4_epilogue(sm, tid, ubuf + (size_t)job * U_STRIDE);
+}
+
 __global__ void __launch_bounds__(KS_THREADS * KS_GROUPS)
 ks_kernel(const KsJob* __restrict__ jobs, const uint32_t* __restrict__ ubuf,
           const uint32_t* __restrict__ ksk_words, uint16_t* __restrict__ arena)
@@ -322,6 +405,7 @@ struct b200fhe_ctx {
     NttTables* tab = nullptr;
     tw_t* d_tw2f = nullptr;
     tw_t* d_tw2i = nullptr;
+    BlockTw* d_blocktw = nullptr;   // team-NTT twiddles (br4_kernel)
     uint32_t* d_bk_ntt = nullptr;   // [636][6][6][1024]
     uint16_t* d_ksk = nullptr;      // [1024][7][3][640]
     bool keys = false;
@@ -421,10 +505,24 @@ static int br3_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
     return 0;
 }
 
+static int br4_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+{
+    static bool attr_set[64] = {};
+    if (!attr_set[c->device]) {
+        CK(cudaFuncSetAttribute(br4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br4Smem::BYTES));
+        attr_set[c->device] = true;
+    }
+    br4_kernel<<<njobs, BR4_THREADS, Br4Smem::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_blocktw, ubuf, N0);
+    CK(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
 static int br_dispatch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
 {
     int variant, G;
     pick_config(c, njobs, variant, G);
+    if (variant == 4) return br4_launch(c, njobs, arena, ubuf, d_jobs);
     if (variant == 3) {
         switch (G) {
         case 2: return br3_launch<2>(c, njobs, arena, ubuf, d_jobs);
@@ -511,7 +609,12 @@ int b200fhe_create(b200fhe_ctx** out, int device)
     CK(cudaMalloc(&c->d_tw2i, sizeof(c->tab->tw2i)));
     CK(cudaMemcpyAsync(c->d_tw2f, c->tab->tw2f, sizeof(c->tab->tw2f), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_tw2i, c->tab->tw2i, sizeof(c->tab->tw2i), cudaMemcpyHostToDevice, c->stream));
+    BlockTw* btw = new BlockTw();
+    block_tw_init(*c->tab, *btw);
+    CK(cudaMalloc(&c->d_blocktw, sizeof(BlockTw)));
+    CK(cudaMemcpyAsync(c->d_blocktw, btw, sizeof(BlockTw), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    delete btw;
     *out = c;
     return 0;
 }
@@ -523,6 +626,7 @@ void b200fhe_destroy(b200fhe_ctx* c)
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tw2f);
     cudaFree(c->d_tw2i);
+    cudaFree(c->d_blocktw);
     cudaFree(c->d_bk_ntt);
     cudaFree(c->d_ksk);
     if (c->arena_owned) cudaFree(c->d_arena);
@@ -559,7 +663,7 @@ int b200fhe_set_jobs_per_cta(b200fhe_ctx* c, int g)
 int b200fhe_set_kernel_variant(b200fhe_ctx* c, int variant)
 {
     if (!c) return fail("null context");
-    if (variant < 1 || variant > 3) return fail("kernel variant must be 1, 2 or 3");
+    if (variant < 1 || variant > 4) return fail("kernel variant must be 1, 2, 3 or 4");
     c->variant = variant;
     c->autotune = false;
     return 0;

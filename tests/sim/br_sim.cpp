@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../iyokan_b200/csrc/br2_phases.h"
+#include "../../iyokan_b200/csrc/br4_phases.h"
 #include "../../iyokan_b200/csrc/br_phases.h"
 #include "../../iyokan_b200/csrc/gate_jobs.h"
 #include "../../iyokan_b200/csrc/ks_phases.h"
@@ -18,12 +19,14 @@
 using namespace b200;
 
 static NttTables g_tab;
+static BlockTw g_btw;
 static bool g_init = false;
 
 extern "C" void sim_init()
 {
     if (!g_init) {
         ntt_tables_init(g_tab);
+        block_tw_init(g_tab, g_btw);
         g_init = true;
     }
 }
@@ -337,6 +340,87 @@ extern "C" void sim_blind_rotate2(int G, const void* jobs_raw, int njobs, const 
         else if (G == 4) sim_br2_cta<4>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
         else std::abort();
     }
+}
+
+
+// ---- variant 4: one job per CTA, 6 teams of 64 threads (br4_kernel) ----
+// team transform on its own: natural order in, NTT positions out (must equal the warp transform bit for bit)
+extern "C" void sim_block_forward(const uint32_t* in, uint32_t* out)
+{
+    sim_init();
+    std::vector<uint32_t> tile(BT_WORDS);
+    for (int t = 0; t < TEAM_THREADS; t++) {
+        uint32_t x[16];
+        for (int a = 0; a < 16; a++) x[a] = in[64 * a + t];
+        blk_fwd_p1(x);
+        blk_store_p1(tile.data(), x, t);
+    }
+    for (int t = 0; t < TEAM_THREADS; t++) blk_fwd_p2(tile.data(), g_btw.p2f, t);
+    for (int t = 0; t < TEAM_THREADS; t++) blk_fwd_p3(tile.data(), g_btw.p3f, t);
+    for (int j = 0; j < N1; j++) out[j] = tile[bt_pad(j)];
+}
+extern "C" void sim_block_inverse(const uint32_t* in, uint32_t* out)
+{
+    sim_init();
+    std::vector<uint32_t> tile(BT_WORDS);
+    for (int j = 0; j < N1; j++) tile[bt_pad(j)] = in[j];
+    for (int t = 0; t < TEAM_THREADS; t++) blk_inv_pA(tile.data(), g_btw.p3i, t);
+    for (int t = 0; t < TEAM_THREADS; t++) blk_inv_pB(tile.data(), g_btw.p2i, t);
+    for (int t = 0; t < TEAM_THREADS; t++) {
+        uint32_t x[16];
+        blk_load_p1(tile.data(), x, t);
+        blk_inv_pC(x);
+        for (int a = 0; a < 16; a++) out[64 * a + t] = x[a];
+    }
+}
+extern "C" void sim_warp_forward(const uint32_t* in, uint32_t* out)
+{
+    sim_init();
+    warp_forward(in, out);
+}
+extern "C" void sim_warp_inverse(const uint32_t* in, uint32_t* out)
+{
+    sim_init();
+    warp_inverse(in, out);
+}
+
+static void sim_br4_cta(const BrJob* jobs, int job, const uint16_t* arena, const uint32_t* bk_ntt, uint32_t* ubuf,
+                        int n_iter)
+{
+    std::vector<uint8_t> smem(Br4Smem::BYTES + 128);
+    Br4Smem sm;
+    sm.carve(reinterpret_cast<void*>(((uintptr_t)smem.data() + 127) & ~(uintptr_t)127));
+    std::memcpy(sm.tw, &g_btw, sizeof(BlockTw));
+    for (int tid = 0; tid < BR4_THREADS; tid++) br4_prologue(sm, jobs[job], arena, tid);
+    auto each = [&](auto fn) {
+        for (int tid = 0; tid < BR4_THREADS; tid++) {
+            const int team = tid >> 6;
+            fn(team / GL, team % GL, tid & 63);
+        }
+    };
+    for (int i = 0; i < n_iter; i++) {
+        std::memcpy(sm.keyb, bk_ntt + (size_t)i * BR4_KEY_WORDS, (size_t)BR4_KEY_WORDS * 4);  // the bulk-async copy
+        each([&](int q, int d, int t) { br4_fwd_p1(sm, i, q, d, t); });
+        each([&](int q, int d, int t) { br4_fwd_p2(sm, q, d, t); });
+        each([&](int q, int d, int t) { br4_fwd_p3(sm, q, d, t); });
+        for (int tid = 0; tid < BR4_THREADS; tid++) {
+            br4_pointwise_item(sm, tid);
+            br4_pointwise_item(sm, tid + BR4_THREADS);
+        }
+        each([&](int q, int d, int t) { br4_inv_pA(sm, q, d, t); });
+        each([&](int q, int d, int t) { br4_inv_pB(sm, q, d, t); });
+        each([&](int q, int d, int t) { br4_inv_pC(sm, q, d, t); });
+    }
+    for (int tid = 0; tid < BR4_THREADS; tid++) br4_epilogue(sm, tid, ubuf + (size_t)job * U_STRIDE);
+}
+
+extern "C" void sim_blind_rotate4(const void* jobs_raw, int njobs, const uint16_t* arena, const uint32_t* bk_ntt,
+                                  uint32_t* ubuf, int n_iter)
+{
+    sim_init();
+    const BrJob* jobs = reinterpret_cast<const BrJob*>(jobs_raw);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int job = 0; job < njobs; job++) sim_br4_cta(jobs, job, arena, bk_ntt, ubuf, n_iter);
 }
 
 // ksk_dev: uint16 [1024][7][3][640]; jobs: packed KsJob (16 bytes each)

@@ -126,6 +126,42 @@ def test_blind_rotate_variant3_bit_exact(sim, keys, bk_ntt_sim, G):
     assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
 
 
+def test_team_ntt_equals_warp_ntt(sim):
+    # the 64-thread x 16-point transform (ntt_block.h) reproduces the warp transform value for value,
+    # lazy representation included, so the two kernels share one bootstrapping-key layout
+    P = sim.sim_prime()
+    rng = np.random.default_rng(7)
+    for lo, hi in ((0, P + 64), (0, 4 * P)):
+        x = rng.integers(lo, hi, 1024, dtype=np.uint32)
+        a, b = np.zeros(1024, np.uint32), np.zeros(1024, np.uint32)
+        sim.sim_warp_forward(p(x), p(a))
+        sim.sim_block_forward(p(x), p(b))
+        assert np.array_equal(a, b)
+        sim.sim_warp_inverse(p(x), p(a))
+        sim.sim_block_inverse(p(x), p(b))
+        assert np.array_equal(a, b)
+
+
+def test_blind_rotate_variant4_bit_exact(sim, keys, bk_ntt_sim):
+    # latency shape (br4_phases.h): one job per CTA, staged key, shared-memory accumulator
+    rng = np.random.default_rng(44)
+    n = 3
+    pa, pb = rng.integers(0, 2, n, dtype=np.uint8), rng.integers(0, 2, n, dtype=np.uint8)
+    ca, cb = O.encrypt_bits(7, keys, pa), O.encrypt_bits(8, keys, pb)
+    arena = np.zeros((2 * n, 640), np.uint16)
+    arena[:n, :637], arena[n:, :637] = ca, cb
+    jobs = np.zeros(n, BRJOB)
+    for g in range(n):
+        jobs[g]["in"] = (g, n + g, 0)
+        jobs[g]["sgn"] = (-2, -2, 0)         # XNOR: -2a - 2b - 2mu
+        jobs[g]["off"] = (-(2 << 13)) & 0xFFFF
+    ubuf = np.zeros((n, 1028), np.uint32)
+    sim.sim_blind_rotate4(p(jobs), n, p(arena), p(bk_ntt_sim), p(ubuf), 636)
+    c = (-2 * ca.astype(np.int32) - 2 * cb.astype(np.int32)).astype(np.uint16)
+    c[:, 636] -= np.uint16(2 << 13)
+    assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
+
+
 def test_blind_rotate_abar_edges(sim, keys, bk_ntt_sim):
     # a-bar = 2N (c_i = 0xFFFF), a-bar = 0, a-bar = N and b-bar = 2N / 1
     c = np.zeros((2, 637), np.uint16)

@@ -34,6 +34,8 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 BATCH = 8192
+WORKLOAD = ("batched HomNAND microbench: 8192 independent gate bootstraps per GPU, "
+            "128-bit params (n=636, N=1024, l=3, Bgbit=6, t=7) [BASELINE.json configs[1]]")
 BK_BYTES_PER_ROTATION = 636 * 2 * 3 * 2 * 1024 * 8      # 62,521,344
 KS_BYTES_PER_SWITCH = 1024 * 7 * 3 * 637 * 2 * 3 // 4    # 6,849,024 expected rows touched
 BYTES_PER_BOOTSTRAP = BK_BYTES_PER_ROTATION + KS_BYTES_PER_SWITCH + 3 * 1274   # 69,374,190
@@ -153,7 +155,7 @@ def run_reference(args, rank: int, world: int):
 
     keys = O.cached_keys(KEY_SEED)
     cores = os.cpu_count() or 1
-    sample = max(cores * 8, 128)
+    sample = min(BATCH, max(cores * 64, 256))  # ~1 s of work per step on all host cores
     if O.have_ref():
         kind = "reference"
         cpu_reference_run(keys, cores, cores)  # warm-up (page in keys, FFT tables)
@@ -174,8 +176,8 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": "tfhe_gate_bootstraps_per_s", "value": value, "unit": "bootstraps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if kind == "reference" else "u32",
-        "data": "synthetic", "config": {"workload": "batched HomNAND, 128-bit params (n=636, N=1024)",
-                                         "batch": BATCH, "sample_per_step": sample},
+        "data": "synthetic", "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "sample_per_step": sample,
+                                         "parallelism": f"{cores} host threads, one gate per thread at a time"},
         "cpu_baseline": {"value": value, "unit": "bootstraps/s", "cores": cores, "kind": kind,
                          "sample": f"{sample} HomNAND gates per step x {args.steps} steps, {cores} host threads"},
         "e2e": {"value": value, "unit": "bootstraps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -325,8 +327,7 @@ def main():
             "metric": "tfhe_gate_bootstraps_per_s", "value": value, "unit": "bootstraps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "batched HomNAND microbench: 8192 independent gate bootstraps per GPU, "
-                                   "128-bit params (n=636, N=1024, l=3, Bgbit=6, t=7) [BASELINE.json configs[1]]",
+            "config": {"workload": WORKLOAD,
                        "batch_per_gpu": n, "parallelism": f"replicated keys, {world} independent batch shard(s)",
                        "l2": "256 MiB device memset between steps inside the timed region (L2 flush); "
                              "working set keys+ciphertexts ~176 MB > 126 MB L2"},
@@ -343,7 +344,7 @@ def main():
         }
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            sample = max(cores * 16, 256)
+            sample = min(n, max(cores * 512, 256))  # ~10 s of host work: the whole batch on a 16-core box
             info = cpu_reference_run(keys, sample, cores)
             kind = "reference"
             if info is None:

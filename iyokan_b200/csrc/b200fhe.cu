@@ -35,7 +35,7 @@ br_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict_
           const uint32_t* __restrict__ bk_ntt, const tw_t* __restrict__ tw2f_g, const tw_t* __restrict__ tw2i_g,
           uint32_t* __restrict__ ubuf, int n_iter)
 {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     BrSmem<G> sm;
     sm.carve(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = warp >> 1, q = warp & 1;
@@ -97,7 +97,7 @@ br3_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict
            const uint32_t* __restrict__ bk_ntt, const tw_t* __restrict__ tw2f_g, const tw_t* __restrict__ tw2i_g,
            uint32_t* __restrict__ ubuf, int n_iter)
 {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     BrSmem<G> sm;
     sm.carve(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = warp >> 1, q = warp & 1;
@@ -166,7 +166,7 @@ br2_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict
            const uint32_t* __restrict__ bk_ntt, const tw_t* __restrict__ tw2f_g, const tw_t* __restrict__ tw2i_g,
            uint32_t* __restrict__ ubuf, int n_iter)
 {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     constexpr int T = 192 * G;
     Br2Smem<G> sm;
     sm.carve(smem_raw);
@@ -461,32 +461,44 @@ static int br2_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
     return 0;
 }
 
-// Batch-size heuristic from the measured latency tables (profiles/r01_latency_table*.json, B200, ms per
-// launch).  A frontier that cannot fill the GPU is latency bound and gets the 6-warps-per-job kernel with
-// few jobs per CTA; larger ones get the throughput kernels, choosing the CTA size whose wave quantisation
-// wastes least (592 or 888 jobs per wave).
-static void pick_config(const b200fhe_ctx* c, int njobs, int& variant, int& G)
+// Launch plan from the measured latency tables (profiles/r01_latency_table*.json, B200, ms per wave):
+//   variant 4 (one job per SM)          148 jobs per wave,  3.02 ms  -> 49.0 k rotations/s, lowest latency
+//   variant 3, 4 jobs per CTA           592 jobs per wave, 10.25 ms  -> 57.8 k/s
+//   variant 3, 6 jobs per CTA           888 jobs per wave, 14.68 ms  -> 60.5 k/s
+// A frontier is cut into at most three segments (full waves of the throughput shapes, the tail on the
+// latency shape) so that wave quantisation never costs more than one 3 ms wave; narrow dependency levels
+// (< 445 jobs) run entirely on the latency shape.
+struct BrSegment { int variant, G, count; };
+static int plan_rotation(const b200fhe_ctx* c, int njobs, BrSegment (&seg)[3])
 {
-    variant = c->variant;
-    G = c->G;
-    if (!c->autotune) return;
-    struct Cand { int variant, G; double ms; };
-    const double inf = 1e30;
-    auto waves = [&](int per_wave) { return (double)((njobs + per_wave - 1) / per_wave); };
-    static const double v2g1[4] = {6.5, 7.8, 10.6, 13.4};  // 1..4 CTAs per SM resident
-    const Cand cands[] = {
-        {2, 1, njobs <= 592 ? v2g1[(njobs - 1) / 148] : inf},
-        {2, 2, njobs <= 296 ? 7.45 : (njobs <= 592 ? 11.65 : inf)},
-        {3, 4, waves(592) * 10.25},
-        {3, 6, waves(888) * 14.68},
-    };
-    double best = inf;
-    for (const Cand& k : cands)
-        if (k.ms < best) {
-            best = k.ms;
-            variant = k.variant;
-            G = k.G;
+    if (!c->autotune) {
+        seg[0] = BrSegment{c->variant, c->G, njobs};
+        return 1;
+    }
+    constexpr double T4 = 3.02, T34 = 10.25, T36 = 14.68;
+    constexpr int W4 = 148, W34 = 592, W36 = 888;
+    const int K = (njobs + W36 - 1) / W36;
+    double best = 1e30;
+    int b6 = 0, b4 = 0;
+    auto waves = [](int count, int per_wave) { return (count + per_wave - 1) / per_wave; };
+    for (int k6 = K > 2 ? K - 2 : 0; k6 <= K; k6++)
+        for (int k4 = 0; k4 <= 3; k4++) {
+            const int c6 = k6 * W36 < njobs ? k6 * W36 : njobs;
+            const int c4 = k4 * W34 < njobs - c6 ? k4 * W34 : njobs - c6;
+            const int rest = njobs - c6 - c4;
+            const double ms = waves(c6, W36) * T36 + waves(c4, W34) * T34 + waves(rest, W4) * T4 +
+                              0.01 * ((c6 > 0) + (c4 > 0) + (rest > 0));  // launch overhead breaks ties
+            if (ms < best) best = ms, b6 = k6, b4 = k4;
         }
+    int n = 0, left = njobs;
+    auto push = [&](int variant, int G, int count) {
+        if (count > 0) seg[n++] = BrSegment{variant, G, count};
+        left -= count;
+    };
+    push(3, 6, b6 * W36 < left ? b6 * W36 : left);
+    push(3, 4, b4 * W34 < left ? b4 * W34 : left);
+    push(4, 1, left);
+    return n;
 }
 
 template <int G>
@@ -518,10 +530,9 @@ static int br4_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
     return 0;
 }
 
-static int br_dispatch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+static int br_dispatch_one(b200fhe_ctx* c, int variant, int G, int njobs, const uint16_t* arena, uint32_t* ubuf,
+                           const BrJob* d_jobs)
 {
-    int variant, G;
-    pick_config(c, njobs, variant, G);
     if (variant == 4) return br4_launch(c, njobs, arena, ubuf, d_jobs);
     if (variant == 3) {
         switch (G) {
@@ -548,6 +559,21 @@ static int br_dispatch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_
     case 6: return br_launch<6>(c, njobs, arena, ubuf, d_jobs);
     default: return fail("jobs per CTA must be 1, 2, 3, 4 or 6");
     }
+}
+
+// rotation job k writes ubuf[k]: segments are contiguous ranges of the job list
+static int br_dispatch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+{
+    BrSegment seg[3];
+    const int nseg = plan_rotation(c, njobs, seg);
+    int first = 0;
+    for (int k = 0; k < nseg; k++) {
+        if (br_dispatch_one(c, seg[k].variant, seg[k].G, seg[k].count, arena, ubuf + (size_t)first * U_STRIDE,
+                            d_jobs + first))
+            return 1;
+        first += seg[k].count;
+    }
+    return 0;
 }
 
 static int ensure_cap(b200fhe_ctx* c, size_t n)

@@ -104,21 +104,25 @@ B200_HD void br4_fwd_p1(const Br4Smem& sm, int i, int q, int d, int t)
     blk_fwd_p1(x);
     blk_store_p1(sm.in_tile(q * GL + d), x, t);
 }
-B200_HD void br4_fwd_p2(const Br4Smem& sm, int q, int d, int t) { blk_fwd_p2(sm.in_tile(q * GL + d), sm.tw->p2f, t); }
+B200_HD void br4_fwd_p2(const Br4Smem& sm, int q, int d, int t)
+{
+    tw_t w[15];
+    blk_load_tw2(sm.tw->p2f, t, w);
+    blk_fwd_p2(sm.in_tile(q * GL + d), w, t);
+}
 B200_HD void br4_fwd_p3(const Br4Smem& sm, int q, int d, int t) { blk_fwd_p3(sm.in_tile(q * GL + d), sm.tw->p3f, t); }
 
 // ---- phase M: pointwise multiply-accumulate against the staged key ----
 // item = (quad m of NTT positions 4m..4m+3, column pair cp): out[c][j] = REDC(sum_r D[r][j] * BK[c][r][j])
+// (measured on B200: interleaving the key loads with the multiply-accumulate of each column beats
+// hoisting all 18 loads - every warp is in this phase at once, so bursts serialise LSU and FMA)
 B200_HD void br4_pointwise_item(const Br4Smem& sm, int item)
 {
     const int m = item & 255, cp = item >> 8;
     const int toff = 4 * m + 4 * (m >> 4);  // bt_pad(4m)
-    uint32_t dv[ROWS][4];
+    u32x4 dv[ROWS];
     B200_UNROLL
-    for (int r = 0; r < ROWS; r++) {
-        const u32x4 v = *reinterpret_cast<const u32x4*>(sm.in_tile(r) + toff);
-        dv[r][0] = v.x, dv[r][1] = v.y, dv[r][2] = v.z, dv[r][3] = v.w;
-    }
+    for (int r = 0; r < ROWS; r++) dv[r] = *reinterpret_cast<const u32x4*>(sm.in_tile(r) + toff);
     B200_UNROLL
     for (int h = 0; h < 2; h++) {
         const int c = 2 * cp + h;
@@ -126,10 +130,10 @@ B200_HD void br4_pointwise_item(const Br4Smem& sm, int item)
         B200_UNROLL
         for (int r = 0; r < ROWS; r++) {
             const u32x4 k = *reinterpret_cast<const u32x4*>(sm.keyb + (size_t)(c * ROWS + r) * N1 + 4 * m);
-            acc[0] += (uint64_t)dv[r][0] * k.x;
-            acc[1] += (uint64_t)dv[r][1] * k.y;
-            acc[2] += (uint64_t)dv[r][2] * k.z;
-            acc[3] += (uint64_t)dv[r][3] * k.w;
+            acc[0] += (uint64_t)dv[r].x * k.x;
+            acc[1] += (uint64_t)dv[r].y * k.y;
+            acc[2] += (uint64_t)dv[r].z * k.z;
+            acc[3] += (uint64_t)dv[r].w * k.w;
         }
         *reinterpret_cast<u32x4*>(sm.out_tile(c) + toff) = u32x4{redc64(acc[0]), redc64(acc[1]), redc64(acc[2]), redc64(acc[3])};
     }
@@ -137,7 +141,12 @@ B200_HD void br4_pointwise_item(const Br4Smem& sm, int item)
 
 // ---- phase I: inverse NTT of limb l of polynomial q, exact recombination into the accumulator ----
 B200_HD void br4_inv_pA(const Br4Smem& sm, int q, int l, int t) { blk_inv_pA(sm.out_tile(q * LIMBS + l), sm.tw->p3i, t); }
-B200_HD void br4_inv_pB(const Br4Smem& sm, int q, int l, int t) { blk_inv_pB(sm.out_tile(q * LIMBS + l), sm.tw->p2i, t); }
+B200_HD void br4_inv_pB(const Br4Smem& sm, int q, int l, int t)
+{
+    tw_t w[15];
+    blk_load_tw2(sm.tw->p2i, t, w);
+    blk_inv_pB(sm.out_tile(q * LIMBS + l), w, t);
+}
 B200_HD void br4_inv_pC(const Br4Smem& sm, int q, int l, int t)
 {
     uint32_t x[16];

@@ -110,19 +110,24 @@ B200_HD void blk_load_p1(const uint32_t* tile, uint32_t (&x)[16], int t)
     B200_UNROLL
     for (int a = 0; a < 16; a++) x[a] = tile[bt_pad(64 * a + t)];
 }
-// pass 2 in place on the tile: load, stages 4..7, store
-B200_HD void blk_fwd_p2(uint32_t* tile, const tw_t* p2f, int t)
+// pass 2 in place on the tile: load, stages 4..7, store.  The 15 twiddles of a thread depend only on
+// A = t >> 2 and are fetched first (measured: keeping them in registers across steps buys nothing).
+B200_HD void blk_load_tw2(const tw_t* p2, int t, tw_t (&tw)[15])
+{
+    B200_UNROLL
+    for (int k = 0; k < 15; k++) tw[k] = p2[(t >> 2) * 15 + k];
+}
+B200_HD void blk_fwd_p2(uint32_t* tile, const tw_t (&tw)[15], int t)
 {
     const int A = t >> 2, c = t & 3;
     uint32_t* base = tile + 68 * A + c;  // bt_pad(64A + 4b + c) = 68A + 4b + c
-    const tw_t* tw = p2f + A * 15;
     uint32_t x[16];
     B200_UNROLL
     for (int b = 0; b < 16; b++) x[b] = base[4 * b];
-    ct_stage_n<16, 0, 0>(x, [=](int g) { return tw[0 + g]; });
-    ct_stage_n<16, 1, 1>(x, [=](int g) { return tw[1 + g]; });
-    ct_stage_n<16, 2, 0>(x, [=](int g) { return tw[3 + g]; });
-    ct_stage_n<16, 3, 1>(x, [=](int g) { return tw[7 + g]; });
+    ct_stage_n<16, 0, 0>(x, [&](int g) { return tw[0 + g]; });
+    ct_stage_n<16, 1, 1>(x, [&](int g) { return tw[1 + g]; });
+    ct_stage_n<16, 2, 0>(x, [&](int g) { return tw[3 + g]; });
+    ct_stage_n<16, 3, 1>(x, [&](int g) { return tw[7 + g]; });
     B200_UNROLL
     for (int b = 0; b < 16; b++) base[4 * b] = x[b];
 }
@@ -157,18 +162,17 @@ B200_HD void blk_inv_pA(uint32_t* tile, const tw_t* p3i, int t)
         *ptr = u32x4{x[0], x[1], x[2], x[3]};
     }
 }
-B200_HD void blk_inv_pB(uint32_t* tile, const tw_t* p2i, int t)
+B200_HD void blk_inv_pB(uint32_t* tile, const tw_t (&tw)[15], int t)
 {
     const int A = t >> 2, c = t & 3;
     uint32_t* base = tile + 68 * A + c;
-    const tw_t* tw = p2i + A * 15;
     uint32_t x[16];
     B200_UNROLL
     for (int b = 0; b < 16; b++) x[b] = base[4 * b];
-    gs_stage_n<16, 3, 1>(x, [=](int g) { return tw[7 + g]; });
-    gs_stage_n<16, 2, 1>(x, [=](int g) { return tw[3 + g]; });
-    gs_stage_n<16, 1, 1>(x, [=](int g) { return tw[1 + g]; });
-    gs_stage_n<16, 0, 1>(x, [=](int g) { return tw[0 + g]; });
+    gs_stage_n<16, 3, 1>(x, [&](int g) { return tw[7 + g]; });
+    gs_stage_n<16, 2, 1>(x, [&](int g) { return tw[3 + g]; });
+    gs_stage_n<16, 1, 1>(x, [&](int g) { return tw[1 + g]; });
+    gs_stage_n<16, 0, 1>(x, [&](int g) { return tw[0 + g]; });
     B200_UNROLL
     for (int b = 0; b < 16; b++) base[4 * b] = x[b];
 }

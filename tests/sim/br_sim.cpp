@@ -355,7 +355,11 @@ extern "C" void sim_block_forward(const uint32_t* in, uint32_t* out)
         blk_fwd_p1(x);
         blk_store_p1(tile.data(), x, t);
     }
-    for (int t = 0; t < TEAM_THREADS; t++) blk_fwd_p2(tile.data(), g_btw.p2f, t);
+    for (int t = 0; t < TEAM_THREADS; t++) {
+        tw_t w[15];
+        blk_load_tw2(g_btw.p2f, t, w);
+        blk_fwd_p2(tile.data(), w, t);
+    }
     for (int t = 0; t < TEAM_THREADS; t++) blk_fwd_p3(tile.data(), g_btw.p3f, t);
     for (int j = 0; j < N1; j++) out[j] = tile[bt_pad(j)];
 }
@@ -365,7 +369,11 @@ extern "C" void sim_block_inverse(const uint32_t* in, uint32_t* out)
     std::vector<uint32_t> tile(BT_WORDS);
     for (int j = 0; j < N1; j++) tile[bt_pad(j)] = in[j];
     for (int t = 0; t < TEAM_THREADS; t++) blk_inv_pA(tile.data(), g_btw.p3i, t);
-    for (int t = 0; t < TEAM_THREADS; t++) blk_inv_pB(tile.data(), g_btw.p2i, t);
+    for (int t = 0; t < TEAM_THREADS; t++) {
+        tw_t w[15];
+        blk_load_tw2(g_btw.p2i, t, w);
+        blk_inv_pB(tile.data(), w, t);
+    }
     for (int t = 0; t < TEAM_THREADS; t++) {
         uint32_t x[16];
         blk_load_p1(tile.data(), x, t);

@@ -41,6 +41,8 @@ KS_BYTES_PER_SWITCH = 1024 * 7 * 3 * 637 * 2 * 3 // 4    # 6,849,024 expected ro
 BYTES_PER_BOOTSTRAP = BK_BYTES_PER_ROTATION + KS_BYTES_PER_SWITCH + 3 * 1274   # 69,374,190
 BR_KERNEL_BYTES_PER_JOB = BK_BYTES_PER_ROTATION + 2 * 1274 + 4100               # key stream + TLWE in + lvl1 out
 KEY_SEED = 20261017
+KERNEL_NAMES = {(3, 6): "br3_kernel<6>", (3, 4): "br3_kernel<4>", (3, 2): "br3_kernel<2>", (4, 1): "br4_kernel", (5, 1): "br5_kernel",
+                (2, 1): "br2_kernel<1>", (2, 2): "br2_kernel<2>", (1, 4): "br_kernel<4>"}
 
 
 def measured_peak_hbm():
@@ -285,13 +287,14 @@ def main():
     ms_total, _ = timed(step_resident, args.steps)
     launches = ctx.launch_count - l0
     # per-launch duration of the dominant kernel, CUDA events on the launching stream
-    br_list, ks_list = [], []
+    br_list, ks_list, seg_runs = [], [], []
     for _ in range(min(args.steps, 5)):
         step_resident()
         ctx.sync()
         a, b = ctx.last_batch_ms()
         br_list.append(a)
         ks_list.append(b)
+        seg_runs.append(ctx.last_batch_segments())
     clocks = sampler.stop() if rank == 0 else None
 
     out_res = ctx.download(ids[3 * n:])
@@ -315,12 +318,19 @@ def main():
         peak, peak_src = measured_peak_hbm()
         value = world * n * args.steps / (ms_total / 1e3)
         br_ms = float(np.mean(br_list))
-        achieved = n * BR_KERNEL_BYTES_PER_JOB / (br_ms / 1e3) / 1e9
+        # launch plan of one step (same every step): the dominant kernel is the segment with most jobs
+        segs = [{**seg_runs[0][k], "ms": float(np.mean([r[k]["ms"] for r in seg_runs]))} for k in range(len(seg_runs[0]))]
+        for sg in segs:
+            sg["kernel"] = KERNEL_NAMES.get((sg["variant"], sg["jobs_per_cta"]), f"variant {sg['variant']}")
+        dom = max(segs, key=lambda sg: sg["jobs"])
+        achieved = dom["jobs"] * BR_KERNEL_BYTES_PER_JOB / (dom["ms"] / 1e3) / 1e9
         traffic = None
         tp = ROOT / "profiles" / "br_kernel_traffic.json"
-        if tp.exists():
+        if tp.exists():  # dram bytes of ONE launch of the dominant kernel, from the committed ncu --set full capture
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                if tj.get("kernel") == dom["kernel"] and tj.get("jobs_in_captured_launch") == dom["jobs"]:
+                    traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         line = {
@@ -336,9 +346,12 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "br_kernel (blind rotation)", "peak_source": peak_src,
-                         "kernel_ms_per_launch": br_ms, "ks_kernel_ms_per_launch": float(np.mean(ks_list)),
-                         "algorithmic_bytes_per_launch": n * BR_KERNEL_BYTES_PER_JOB,
+                         "traffic": traffic, "kernel": dom["kernel"] + " (blind rotation)", "peak_source": peak_src,
+                         "kernel_ms_per_launch": dom["ms"], "jobs_per_launch": dom["jobs"],
+                         "algorithmic_bytes_per_launch": dom["jobs"] * BR_KERNEL_BYTES_PER_JOB,
+                         "launch_plan": segs, "blind_rotation_ms_per_step": br_ms,
+                         "ks_kernel_ms_per_launch": float(np.mean(ks_list)),
+                         "whole_step_frac": n * BR_KERNEL_BYTES_PER_JOB / (br_ms / 1e3) / 1e9 / peak,
                          "gate_model_frac": (value / world) * BYTES_PER_BOOTSTRAP / (peak * 1e9)},
             "outputs_ok": all_ok,
         }

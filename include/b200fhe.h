@@ -69,7 +69,9 @@ int b200fhe_set_jobs_per_cta(b200fhe_ctx *ctx, int g);
  * job), 2 = one warp per transform (6 warps per job: lower latency per dependency level),
  * 3 = as 1 with the three transforms of a warp interleaved (more ILP per warp),
  * 4 = one job per CTA, 12 warps (6 teams of 64 threads), key staged into shared memory by bulk-async
- *     copies: the lowest latency for one dependency level (jobs-per-CTA is ignored) */
+ *     copies: low latency for one dependency level (jobs-per-CTA is ignored),
+ * 5 = one job per 2-CTA thread-block cluster (one accumulator polynomial per SM, digit tiles exchanged
+ *     by bulk-async copies through distributed shared memory): lowest latency, for <= 74 jobs */
 int b200fhe_set_kernel_variant(b200fhe_ctx *ctx, int variant);
 
 /* keys: raw bootstrapping key + key-switching key in the reference's memory layout.
@@ -112,6 +114,13 @@ uint64_t b200fhe_launch_count(const b200fhe_ctx *ctx);
 /* device time (ms, CUDA events on the context's stream) spent in the blind-rotation kernel /
  * key-switch kernel by the most recent b200fhe_gate_batch; valid after b200fhe_sync */
 int b200fhe_last_batch_ms(b200fhe_ctx *ctx, float *blind_rotate_ms, float *keyswitch_ms);
+/* the launch plan of that batch: a frontier is cut into at most four blind-rotation launches (full
+ * waves of the throughput kernels, the tail on the latency kernels).  Fills up to max_segments entries
+ * (kernel variant, jobs per CTA, rotation jobs, device ms) and returns the number of segments, -1 on error. */
+int b200fhe_last_batch_segments(b200fhe_ctx *ctx, int *variant, int *jobs_per_cta, int *jobs, float *ms,
+                                int max_segments);
+/* the plan the heuristic would choose for a frontier of `njobs` blind rotations (pure host logic, no device) */
+int b200fhe_plan_rotation(int njobs, int *variant, int *jobs_per_cta, int *jobs, int max_segments);
 void *b200fhe_stream(const b200fhe_ctx *ctx);
 
 /* test hooks: stage-level access used by the parity tests --------------------------------- */

@@ -16,6 +16,7 @@
 #include "../../include/b200fhe.h"
 #include "br2_phases.h"
 #include "br4_phases.h"
+#include "br5_phases.h"
 #include "br_phases.h"
 #include "gate_jobs.h"
 #include "ks_phases.h"
@@ -306,6 +307,107 @@ br4_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict
     br4_epilogue(sm, tid, ubuf + (size_t)job * U_STRIDE);
 }
 
+
+// ---- cluster shape: one job per 2-CTA cluster (br5_phases.h) ----
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// arrival that publishes no data (only "I have finished reading"): no fence, no store drain
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+template <class T>
+__device__ __forceinline__ T* map_to_cta(T* p, uint32_t rank)  // generic address of p in CTA `rank` of the cluster
+{
+    uint64_t out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((uint64_t)p), "r"(rank));
+    return reinterpret_cast<T*>(out);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BR5_THREADS, 1)
+br5_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ arena,
+           const uint32_t* __restrict__ bk_ntt, const BlockTw* __restrict__ tw_g, uint32_t* __restrict__ ubuf, int n_iter)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Br5Smem sm;
+    sm.carve(smem_raw);
+    const int tid = threadIdx.x, d = tid >> 6, t = tid & 63;
+    const int q = (int)cluster_ctarank();
+    const int job = blockIdx.x >> 1;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tw_g);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(sm.tw);
+        for (int k = tid; k < (int)(sizeof(BlockTw) / 4); k += BR5_THREADS) dst[k] = src[k];
+    }
+    if (tid == 0) mbar_init(sm.mbar, 1);
+    const BrJob jb = jobs[job];
+    br5_prologue(sm, jb, arena, q, tid);
+    __syncthreads();
+    const uint32_t* key0 = bk_ntt + (size_t)q * BR5_KEY_WORDS;  // columns 3q..3q+2 of step 0
+    auto stage = [&](int i) {
+        constexpr uint32_t BYTES = BR5_KEY_WORDS * 4;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(sm.mbar)), "r"(BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(sm.keyb)),
+                     "l"(key0 + (size_t)i * BR4_KEY_WORDS), "r"(BYTES), "r"(smem_u32(sm.mbar))
+                     : "memory");
+    };
+    // second mbarrier: counts the bytes of the three digit tiles the peer copies into this CTA per step
+    uint64_t* mbar_dig = sm.mbar + 1;
+    constexpr uint32_t TILE_BYTES = BT_WORDS * 4;
+    if (tid == 0) mbar_init(mbar_dig, 1);
+    __syncthreads();
+    const uint32_t my_tile = smem_u32(sm.in_tile(q * GL + d));   // source of this team's copy
+    uint32_t peer_tile, peer_bar;                                // same offsets inside the peer CTA
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_tile) : "r"(my_tile), "r"((uint32_t)(q ^ 1)));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_bar) : "r"(smem_u32(mbar_dig)), "r"((uint32_t)(q ^ 1)));
+    if (tid == 0 && n_iter > 0) stage(0);
+    cluster_arrive();  // both CTAs have initialised their barriers before anyone copies into the other
+    cluster_wait();
+    cluster_arrive_relaxed();  // phase (B) of "step -1": nothing of the peer's is being read yet
+
+    for (int i = 0; i < n_iter; i++) {
+        if (tid == 0)  // this step's three incoming tiles
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar_dig)),
+                         "r"(GL * TILE_BYTES)
+                         : "memory");
+        br5_fwd_p1(sm, i, q, d, t);
+        named_barrier_sync(1 + d, TEAM_THREADS);
+        br5_fwd_p2(sm, q, d, t);
+        named_barrier_sync(1 + d, TEAM_THREADS);
+        br5_fwd_p3(sm, q, d, t);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my tile writes -> visible to the copy engine
+        cluster_wait();    // (B) the peer's pointwise stage of the previous step no longer reads my copies
+        named_barrier_sync(1 + d, TEAM_THREADS);
+        if (t == 0)
+            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             peer_tile),
+                         "r"(my_tile), "r"(TILE_BYTES), "r"(peer_bar)
+                         : "memory");
+        mbar_wait(sm.mbar, (uint32_t)(i & 1));
+        uint64_t pacc[BR5_PW_PER_THREAD][4];
+        named_barrier_sync(7, BR5_THREADS);  // the local teams' tiles are complete (CTA-wide)
+        br5_pw_local(sm, q, tid, pacc);
+        mbar_wait(mbar_dig, (uint32_t)(i & 1));  // the peer's three tiles have landed
+        br5_pw_finish(sm, q, tid, pacc);
+        cluster_arrive_relaxed();  // (B) for the next step
+        __syncthreads();
+        if (tid == 0 && i + 1 < n_iter) stage(i + 1);
+        br5_inv_pA(sm, d, t);
+        named_barrier_sync(1 + d, TEAM_THREADS);
+        br5_inv_pB(sm, d, t);
+        named_barrier_sync(1 + d, TEAM_THREADS);
+        br5_inv_pC(sm, d, t);
+        __syncthreads();
+    }
+    cluster_wait();  // pairs with the last arrive: neither CTA exits while the other may still copy into it
+    br5_epilogue(sm, q, tid, ubuf + (size_t)job * U_STRIDE);
+}
+
 __global__ void __launch_bounds__(KS_THREADS * KS_GROUPS)
 ks_kernel(const KsJob* __restrict__ jobs, const uint32_t* __restrict__ ubuf,
           const uint32_t* __restrict__ ksk_words, uint16_t* __restrict__ arena)
@@ -421,6 +523,9 @@ struct b200fhe_ctx {
     uint32_t* d_unstage = nullptr;  // [cap][320]
     cudaEvent_t ev_staged = nullptr, ev_t[3] = {nullptr, nullptr, nullptr};
     bool staged_pending = false, timed = false;
+    // per-segment timing of the most recent launch plan (see plan_rotation)
+    cudaEvent_t ev_seg[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int seg_n = 0, seg_variant[4] = {0, 0, 0, 0}, seg_G[4] = {0, 0, 0, 0}, seg_count[4] = {0, 0, 0, 0};
     uint64_t launches = 0;
 };
 
@@ -462,32 +567,39 @@ static int br2_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
 }
 
 // Launch plan from the measured latency tables (profiles/r01_latency_table*.json, B200, ms per wave):
-//   variant 4 (one job per SM)          148 jobs per wave,  3.02 ms  -> 49.0 k rotations/s, lowest latency
-//   variant 3, 4 jobs per CTA           592 jobs per wave, 10.25 ms  -> 57.8 k/s
-//   variant 3, 6 jobs per CTA           888 jobs per wave, 14.68 ms  -> 60.5 k/s
-// A frontier is cut into at most three segments (full waves of the throughput shapes, the tail on the
-// latency shape) so that wave quantisation never costs more than one 3 ms wave; narrow dependency levels
-// (< 445 jobs) run entirely on the latency shape.
+//   variant 5 (one job per 2-SM cluster)  74 jobs per wave,  2.41 ms  -> lowest latency
+//   variant 4 (one job per SM)           148 jobs per wave,  3.02 ms  -> 49.0 k rotations/s
+//   variant 3, 4 jobs per CTA            592 jobs per wave, 10.25 ms  -> 57.8 k/s
+//   variant 3, 6 jobs per CTA            888 jobs per wave, 14.68 ms  -> 60.5 k/s
+// A frontier is cut into at most four segments (full waves of the throughput shapes, then the latency
+// shapes for the tail) so that wave quantisation never costs more than one 3 ms wave; narrow dependency
+// levels (< 445 jobs) run entirely on the latency shapes.
+constexpr int BR_MAX_SEGMENTS = 4;
 struct BrSegment { int variant, G, count; };
-static int plan_rotation(const b200fhe_ctx* c, int njobs, BrSegment (&seg)[3])
+static int plan_rotation(const b200fhe_ctx* c, int njobs, BrSegment (&seg)[BR_MAX_SEGMENTS])
 {
     if (!c->autotune) {
         seg[0] = BrSegment{c->variant, c->G, njobs};
         return 1;
     }
-    constexpr double T4 = 3.02, T34 = 10.25, T36 = 14.68;
-    constexpr int W4 = 148, W34 = 592, W36 = 888;
-    const int K = (njobs + W36 - 1) / W36;
+    constexpr double T5 = 2.41, T4 = 3.02, T34 = 10.25, T36 = 14.68;
+    constexpr int W5 = 74, W4 = 148, W34 = 592, W36 = 888;
+    auto waves = [](int count, int per_wave) { return (count + per_wave - 1) / per_wave; };
+    // tail on the latency shapes: full one-job-per-SM waves, the last partial wave on clusters if it fits
+    auto tail_ms = [&](int rest) {
+        const int r = rest % W4;
+        return (rest / W4) * T4 + (r == 0 ? 0.0 : (r <= W5 ? T5 : T4)) + 0.01 * ((rest >= W4) + (r > 0));
+    };
+    const int K = waves(njobs, W36);
     double best = 1e30;
     int b6 = 0, b4 = 0;
-    auto waves = [](int count, int per_wave) { return (count + per_wave - 1) / per_wave; };
     for (int k6 = K > 2 ? K - 2 : 0; k6 <= K; k6++)
         for (int k4 = 0; k4 <= 3; k4++) {
             const int c6 = k6 * W36 < njobs ? k6 * W36 : njobs;
             const int c4 = k4 * W34 < njobs - c6 ? k4 * W34 : njobs - c6;
             const int rest = njobs - c6 - c4;
-            const double ms = waves(c6, W36) * T36 + waves(c4, W34) * T34 + waves(rest, W4) * T4 +
-                              0.01 * ((c6 > 0) + (c4 > 0) + (rest > 0));  // launch overhead breaks ties
+            const double ms = waves(c6, W36) * T36 + waves(c4, W34) * T34 + tail_ms(rest) +
+                              0.01 * ((c6 > 0) + (c4 > 0));  // launch overhead breaks ties
             if (ms < best) best = ms, b6 = k6, b4 = k4;
         }
     int n = 0, left = njobs;
@@ -497,7 +609,13 @@ static int plan_rotation(const b200fhe_ctx* c, int njobs, BrSegment (&seg)[3])
     };
     push(3, 6, b6 * W36 < left ? b6 * W36 : left);
     push(3, 4, b4 * W34 < left ? b4 * W34 : left);
-    push(4, 1, left);
+    const int r = left % W4;
+    if (r > 0 && r <= W5) {
+        push(4, 1, left - r);
+        push(5, 1, r);
+    } else {
+        push(4, 1, left);
+    }
     return n;
 }
 
@@ -530,9 +648,23 @@ static int br4_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
     return 0;
 }
 
+static int br5_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+{
+    static bool attr_set[64] = {};
+    if (!attr_set[c->device]) {
+        CK(cudaFuncSetAttribute(br5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br5Smem::BYTES));
+        attr_set[c->device] = true;
+    }
+    br5_kernel<<<2 * njobs, BR5_THREADS, Br5Smem::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_blocktw, ubuf, N0);
+    CK(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
 static int br_dispatch_one(b200fhe_ctx* c, int variant, int G, int njobs, const uint16_t* arena, uint32_t* ubuf,
                            const BrJob* d_jobs)
 {
+    if (variant == 5) return br5_launch(c, njobs, arena, ubuf, d_jobs);
     if (variant == 4) return br4_launch(c, njobs, arena, ubuf, d_jobs);
     if (variant == 3) {
         switch (G) {
@@ -564,15 +696,21 @@ static int br_dispatch_one(b200fhe_ctx* c, int variant, int G, int njobs, const 
 // rotation job k writes ubuf[k]: segments are contiguous ranges of the job list
 static int br_dispatch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
 {
-    BrSegment seg[3];
+    BrSegment seg[BR_MAX_SEGMENTS];
     const int nseg = plan_rotation(c, njobs, seg);
     int first = 0;
+    CK(cudaEventRecord(c->ev_seg[0], c->stream));
     for (int k = 0; k < nseg; k++) {
         if (br_dispatch_one(c, seg[k].variant, seg[k].G, seg[k].count, arena, ubuf + (size_t)first * U_STRIDE,
                             d_jobs + first))
             return 1;
+        CK(cudaEventRecord(c->ev_seg[k + 1], c->stream));
+        c->seg_variant[k] = seg[k].variant;
+        c->seg_G[k] = seg[k].variant >= 4 ? 1 : seg[k].G;
+        c->seg_count[k] = seg[k].count;
         first += seg[k].count;
     }
+    c->seg_n = nseg;
     return 0;
 }
 
@@ -625,6 +763,7 @@ int b200fhe_create(b200fhe_ctx** out, int device)
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming));
     for (auto& e : c->ev_t) CK(cudaEventCreate(&e));
+    for (auto& e : c->ev_seg) CK(cudaEventCreate(&e));
     c->tab = new NttTables();
     ntt_tables_init(*c->tab);
     // every transfer goes through the context's non-blocking stream: the legacy default stream is not
@@ -666,6 +805,7 @@ void b200fhe_destroy(b200fhe_ctx* c)
     cudaFree(c->d_unstage);
     cudaEventDestroy(c->ev_staged);
     for (auto& e : c->ev_t) cudaEventDestroy(e);
+    for (auto& e : c->ev_seg) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c->tab;
     delete c;
@@ -689,7 +829,7 @@ int b200fhe_set_jobs_per_cta(b200fhe_ctx* c, int g)
 int b200fhe_set_kernel_variant(b200fhe_ctx* c, int variant)
 {
     if (!c) return fail("null context");
-    if (variant < 1 || variant > 4) return fail("kernel variant must be 1, 2, 3 or 4");
+    if (variant < 1 || variant > 5) return fail("kernel variant must be 1..5");
     c->variant = variant;
     c->autotune = false;
     return 0;
@@ -894,6 +1034,50 @@ int b200fhe_last_batch_ms(b200fhe_ctx* c, float* br_ms, float* ks_ms)
     if (br_ms) *br_ms = a;
     if (ks_ms) *ks_ms = b;
     return 0;
+}
+
+int b200fhe_plan_rotation(int njobs, int* variant, int* jobs_per_cta, int* jobs, int max_segments)
+{
+    if (njobs <= 0) return 0;
+    b200fhe_ctx tmp;  // default context state = heuristic on; no device is touched
+    BrSegment seg[BR_MAX_SEGMENTS];
+    const int nseg = plan_rotation(&tmp, njobs, seg);
+    const int n = nseg < max_segments ? nseg : max_segments;
+    for (int k = 0; k < n; k++) {
+        if (variant) variant[k] = seg[k].variant;
+        if (jobs_per_cta) jobs_per_cta[k] = seg[k].variant >= 4 ? 1 : seg[k].G;
+        if (jobs) jobs[k] = seg[k].count;
+    }
+    return n;
+}
+
+int b200fhe_last_batch_segments(b200fhe_ctx* c, int* variant, int* jobs_per_cta, int* jobs, float* ms, int max_segments)
+{
+    if (!c) {
+        fail("null context");
+        return -1;
+    }
+    if (!c->timed) {
+        fail("no timed batch");
+        return -1;
+    }
+    if (cudaEventSynchronize(c->ev_t[2]) != cudaSuccess) {
+        fail("cudaEventSynchronize failed");
+        return -1;
+    }
+    int n = c->seg_n < max_segments ? c->seg_n : max_segments;
+    for (int k = 0; k < n; k++) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, c->ev_seg[k], c->ev_seg[k + 1]) != cudaSuccess) {
+            fail("cudaEventElapsedTime failed");
+            return -1;
+        }
+        if (variant) variant[k] = c->seg_variant[k];
+        if (jobs_per_cta) jobs_per_cta[k] = c->seg_G[k];
+        if (jobs) jobs[k] = c->seg_count[k];
+        if (ms) ms[k] = t;
+    }
+    return n;
 }
 
 int b200fhe_gates_host(b200fhe_ctx* c, const uint8_t* opcode, const uint16_t* in0_host, const uint16_t* in1_host,

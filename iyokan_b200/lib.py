@@ -69,6 +69,8 @@ def load() -> ctypes.CDLL:
         "b200fhe_host_free": (ci, [vp]),
         "b200fhe_launch_count": (u64, [vp]),
         "b200fhe_last_batch_ms": (ci, [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
+        "b200fhe_last_batch_segments": (ci, [vp, vp, vp, vp, vp, ci]),
+        "b200fhe_plan_rotation": (ci, [ci, vp, vp, vp, ci]),
         "b200fhe_stream": (vp, [vp]),
         "b200fhe_test_bootstrap_lvl1": (ci, [vp, vp, vp, sz]),
         "b200fhe_test_keyswitch": (ci, [vp, vp, vp, sz]),
@@ -87,7 +89,7 @@ EXPORTS = [
     "b200fhe_arena_alloc", "b200fhe_arena_attach", "b200fhe_arena_slots", "b200fhe_arena_dev_ptr",
     "b200fhe_upload", "b200fhe_download", "b200fhe_gate_batch", "b200fhe_dff_tick", "b200fhe_sync",
     "b200fhe_query", "b200fhe_gates_host", "b200fhe_host_alloc", "b200fhe_host_free", "b200fhe_launch_count",
-    "b200fhe_last_batch_ms", "b200fhe_stream", "b200fhe_test_bootstrap_lvl1", "b200fhe_test_keyswitch",
+    "b200fhe_last_batch_ms", "b200fhe_last_batch_segments", "b200fhe_plan_rotation", "b200fhe_stream", "b200fhe_test_bootstrap_lvl1", "b200fhe_test_keyswitch",
     "b200fhe_test_read_bk_ntt",
 ]
 
@@ -124,6 +126,14 @@ class PinnedBuffer:
             self.array = None
             load().b200fhe_host_free(self._p)
             self._p = None
+
+
+def plan_rotation(njobs: int):
+    """Launch plan of the batch-size heuristic for `njobs` blind rotations: [(variant, jobs_per_cta, jobs)]."""
+    lib = load()
+    v, g, n = (np.zeros(4, np.int32) for _ in range(3))
+    k = lib.b200fhe_plan_rotation(int(njobs), _ptr(v), _ptr(g), _ptr(n), 4)
+    return [(int(v[i]), int(g[i]), int(n[i])) for i in range(k)]
 
 
 class Context:
@@ -235,6 +245,15 @@ class Context:
         a, b = ctypes.c_float(), ctypes.c_float()
         self._ck(self._lib.b200fhe_last_batch_ms(self._h, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
+
+    def last_batch_segments(self):
+        """Launch plan of the most recent gate_batch: list of dicts (variant, jobs_per_cta, jobs, ms)."""
+        v, g, n = (np.zeros(4, np.int32) for _ in range(3))
+        ms = np.zeros(4, np.float32)
+        k = self._lib.b200fhe_last_batch_segments(self._h, _ptr(v), _ptr(g), _ptr(n), _ptr(ms), 4)
+        if k < 0:
+            raise B200FheError(self._lib.b200fhe_last_error().decode())
+        return [{"variant": int(v[i]), "jobs_per_cta": int(g[i]), "jobs": int(n[i]), "ms": float(ms[i])} for i in range(k)]
 
     # ---- stage-level test hooks ----
     def test_bootstrap_lvl1(self, c: np.ndarray) -> np.ndarray:

@@ -26,7 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", default="cahp-pearl-mux")
     ap.add_argument("--cycles", type=int, default=2)
-    ap.add_argument("--min-shard-width", type=int, default=296)
+    ap.add_argument("--min-shard-width", type=int, default=150)
     args = ap.parse_args()
     import torch
     import torch.distributed as dist

@@ -12,6 +12,7 @@
 
 #include "../../iyokan_b200/csrc/br2_phases.h"
 #include "../../iyokan_b200/csrc/br4_phases.h"
+#include "../../iyokan_b200/csrc/br5_phases.h"
 #include "../../iyokan_b200/csrc/br_phases.h"
 #include "../../iyokan_b200/csrc/gate_jobs.h"
 #include "../../iyokan_b200/csrc/ks_phases.h"
@@ -429,6 +430,59 @@ extern "C" void sim_blind_rotate4(const void* jobs_raw, int njobs, const uint16_
     const BrJob* jobs = reinterpret_cast<const BrJob*>(jobs_raw);
 #pragma omp parallel for schedule(dynamic, 1)
     for (int job = 0; job < njobs; job++) sim_br4_cta(jobs, job, arena, bk_ntt, ubuf, n_iter);
+}
+
+
+// ---- variant 5: one job per 2-CTA cluster (br5_kernel); both CTAs advance phase by phase ----
+static void sim_br5_cluster(const BrJob* jobs, int job, const uint16_t* arena, const uint32_t* bk_ntt, uint32_t* ubuf,
+                            int n_iter)
+{
+    std::vector<uint8_t> smem[2] = {std::vector<uint8_t>(Br5Smem::BYTES + 128), std::vector<uint8_t>(Br5Smem::BYTES + 128)};
+    Br5Smem sm[2];
+    for (int q = 0; q < 2; q++) {
+        sm[q].carve(reinterpret_cast<void*>(((uintptr_t)smem[q].data() + 127) & ~(uintptr_t)127));
+        std::memcpy(sm[q].tw, &g_btw, sizeof(BlockTw));
+        for (int tid = 0; tid < BR5_THREADS; tid++) br5_prologue(sm[q], jobs[job], arena, q, tid);
+    }
+    auto each = [&](auto fn) {
+        for (int q = 0; q < 2; q++)
+            for (int tid = 0; tid < BR5_THREADS; tid++) fn(q, tid >> 6, tid & 63);
+    };
+    for (int i = 0; i < n_iter; i++) {
+        for (int q = 0; q < 2; q++)  // the bulk-async copy of this CTA's key columns
+            std::memcpy(sm[q].keyb, bk_ntt + (size_t)i * BR4_KEY_WORDS + (size_t)q * BR5_KEY_WORDS, (size_t)BR5_KEY_WORDS * 4);
+        each([&](int q, int d, int t) { br5_fwd_p1(sm[q], i, q, d, t); });
+        each([&](int q, int d, int t) { br5_fwd_p2(sm[q], q, d, t); });
+        each([&](int q, int d, int t) { br5_fwd_p3(sm[q], q, d, t); });
+        for (int q = 0; q < 2; q++)  // the tile copies into the peer (cp.async.bulk shared::cta -> shared::cluster)
+            for (int d = 0; d < GL; d++)
+                std::memcpy(sm[q ^ 1].in_tile(q * GL + d), sm[q].in_tile(q * GL + d), (size_t)BT_WORDS * 4);
+        {
+            std::vector<uint64_t> pacc((size_t)2 * BR5_THREADS * BR5_PW_PER_THREAD * 4);
+            auto acc_of = [&](int q, int tid) -> uint64_t(&)[BR5_PW_PER_THREAD][4] {
+                return *reinterpret_cast<uint64_t(*)[BR5_PW_PER_THREAD][4]>(
+                    pacc.data() + ((size_t)q * BR5_THREADS + tid) * BR5_PW_PER_THREAD * 4);
+            };
+            for (int q = 0; q < 2; q++)
+                for (int tid = 0; tid < BR5_THREADS; tid++) br5_pw_local(sm[q], q, tid, acc_of(q, tid));
+            for (int q = 0; q < 2; q++)
+                for (int tid = 0; tid < BR5_THREADS; tid++) br5_pw_finish(sm[q], q, tid, acc_of(q, tid));
+        }
+        each([&](int q, int d, int t) { br5_inv_pA(sm[q], d, t); });
+        each([&](int q, int d, int t) { br5_inv_pB(sm[q], d, t); });
+        each([&](int q, int d, int t) { br5_inv_pC(sm[q], d, t); });
+    }
+    for (int q = 0; q < 2; q++)
+        for (int tid = 0; tid < BR5_THREADS; tid++) br5_epilogue(sm[q], q, tid, ubuf + (size_t)job * U_STRIDE);
+}
+
+extern "C" void sim_blind_rotate5(const void* jobs_raw, int njobs, const uint16_t* arena, const uint32_t* bk_ntt,
+                                  uint32_t* ubuf, int n_iter)
+{
+    sim_init();
+    const BrJob* jobs = reinterpret_cast<const BrJob*>(jobs_raw);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int job = 0; job < njobs; job++) sim_br5_cluster(jobs, job, arena, bk_ntt, ubuf, n_iter);
 }
 
 // ksk_dev: uint16 [1024][7][3][640]; jobs: packed KsJob (16 bytes each)

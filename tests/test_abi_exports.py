@@ -43,3 +43,29 @@ def test_product_never_imports_oracle():
         if path.suffix in (".py", ".h", ".cu", ".cpp"):
             txt = path.read_text()
             assert "import oracle" not in txt and "tfhe_oracle" not in txt, path
+
+
+def test_launch_plan_covers_every_frontier_size():
+    # host-only logic (no device): segments cover the frontier exactly, throughput waves come first,
+    # narrow frontiers use the latency shapes, and the <= 74-job tail goes to the 2-SM cluster shape
+    from iyokan_b200 import build as B
+    from iyokan_b200.lib import plan_rotation
+
+    B.build_cuda()
+    for n in list(range(1, 1200)) + [2368, 4115, 8192, 8961, 100000]:
+        plan = plan_rotation(n)
+        assert 1 <= len(plan) <= 4
+        assert sum(c for _, _, c in plan) == n
+        order = [(v, g) for v, g, _ in plan]
+        assert order == sorted(order, key=lambda vg: {(3, 6): 0, (3, 4): 1, (4, 1): 2, (5, 1): 3}[vg])
+        for v, g, c in plan:
+            if (v, g) == (3, 6):
+                assert c % 888 == 0 or c == n
+            if (v, g) == (5, 1):
+                assert c <= 74
+    assert plan_rotation(30) == [(5, 1, 30)]
+    assert plan_rotation(74) == [(5, 1, 74)]
+    assert plan_rotation(100) == [(4, 1, 100)]
+    assert plan_rotation(148 + 20) == [(4, 1, 148), (5, 1, 20)]
+    assert plan_rotation(8192) == [(3, 6, 7992), (4, 1, 148), (5, 1, 52)]
+    assert plan_rotation(0) == []

@@ -86,6 +86,28 @@ def test_blind_rotate_variant4_bit_exact(gpu_ctx, keys, golden):
         gpu_ctx.set_jobs_per_cta(0)
 
 
+def test_blind_rotate_variant5_bit_exact(gpu_ctx, keys, golden):
+    # cluster shape: one job per 2-CTA cluster, digit tiles exchanged through distributed shared memory
+    gpu_ctx.set_kernel_variant(5)
+    try:
+        c = golden["br_in"][:5]
+        assert np.array_equal(gpu_ctx.test_bootstrap_lvl1(c), O.bootstrap_to_lvl1(keys, c))
+        edge = np.zeros((3, 637), np.uint16)
+        edge[0, :8] = [0xFFFF, 0xFFF0, 0, 15, 0x8000, 0x7FF0, 0x8010, 0x0010]
+        edge[0, 636] = 0x001F
+        edge[1, 600:636] = 0x8000
+        edge[1, 636] = 0xFFFF
+        edge[2, 636] = 1 << 13
+        assert np.array_equal(gpu_ctx.test_bootstrap_lvl1(edge), O.bootstrap_to_lvl1(keys, edge))
+        many = np.tile(golden["br_in"][:4], (50, 1))   # 200 clusters: more than one wave
+        got = gpu_ctx.test_bootstrap_lvl1(many)
+        want = O.bootstrap_to_lvl1(keys, golden["br_in"][:4])
+        assert np.array_equal(got, np.tile(want, (50, 1)))
+    finally:
+        gpu_ctx.set_kernel_variant(1)
+        gpu_ctx.set_jobs_per_cta(0)
+
+
 def test_blind_rotate_edge_inputs(gpu_ctx, keys):
     c = np.zeros((3, 637), np.uint16)
     c[0, :8] = [0xFFFF, 0xFFF0, 0, 15, 0x8000, 0x7FF0, 0x8010, 0x0010]   # a-bar = 2N, 0, N, ...

@@ -162,6 +162,26 @@ def test_blind_rotate_variant4_bit_exact(sim, keys, bk_ntt_sim):
     assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
 
 
+def test_blind_rotate_variant5_bit_exact(sim, keys, bk_ntt_sim):
+    # cluster shape (br5_phases.h): two CTAs per job, digit tiles pushed to the peer, per-polynomial key halves
+    rng = np.random.default_rng(55)
+    n = 3
+    pa, pb = rng.integers(0, 2, n, dtype=np.uint8), rng.integers(0, 2, n, dtype=np.uint8)
+    ca, cb = O.encrypt_bits(9, keys, pa), O.encrypt_bits(10, keys, pb)
+    arena = np.zeros((2 * n, 640), np.uint16)
+    arena[:n, :637], arena[n:, :637] = ca, cb
+    jobs = np.zeros(n, BRJOB)
+    for g in range(n):
+        jobs[g]["in"] = (g, n + g, 0)
+        jobs[g]["sgn"] = (-1, -1, 0)         # NAND: -a - b + mu
+        jobs[g]["off"] = 1 << 13
+    ubuf = np.zeros((n, 1028), np.uint32)
+    sim.sim_blind_rotate5(p(jobs), n, p(arena), p(bk_ntt_sim), p(ubuf), 636)
+    c = (-ca.astype(np.int32) - cb.astype(np.int32)).astype(np.uint16)
+    c[:, 636] += np.uint16(1 << 13)
+    assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
+
+
 def test_blind_rotate_abar_edges(sim, keys, bk_ntt_sim):
     # a-bar = 2N (c_i = 0xFFFF), a-bar = 0, a-bar = N and b-bar = 2N / 1
     c = np.zeros((2, 637), np.uint16)

@@ -56,7 +56,7 @@ def main():
                 d[r[ki].split("(")[0]].append(float(r[vi].replace(",", "")))
         tot = sum(sum(v) for v in d.values())
         lines = [f"# ncu launch list (gpu__time_duration.sum, --clock-control none), {ROUND}", "",
-                 "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv python bench.py --steps 1 --warmup 3`", "",
+                 "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv python bench.py --steps 1 --warmup 3` (scripts/gpu_round.sh)", "",
                  "| kernel | launches | total ms | share |", "|---|---|---|---|"]
         for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
             lines.append(f"| `{k}` | {len(v)} | {sum(v) / 1e6:.3f} | {sum(v) / tot:.3f} |")

@@ -121,6 +121,9 @@ int b200fhe_last_batch_segments(b200fhe_ctx *ctx, int *variant, int *jobs_per_ct
                                 int max_segments);
 /* the plan the heuristic would choose for a frontier of `njobs` blind rotations (pure host logic, no device) */
 int b200fhe_plan_rotation(int njobs, int *variant, int *jobs_per_cta, int *jobs, int max_segments);
+/* modelled blind-rotation time (ms, B200 tables) of that plan: what a scheduler uses to decide whether
+ * splitting a dependency level across GPUs pays for the exchange */
+double b200fhe_plan_ms(int njobs);
 void *b200fhe_stream(const b200fhe_ctx *ctx);
 
 /* test hooks: stage-level access used by the parity tests --------------------------------- */

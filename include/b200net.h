@@ -39,6 +39,7 @@ const char *b200net_last_error(void);
 size_t b200net_num_nodes(const b200net *net);
 size_t b200net_num_levels(const b200net *net);              /* combinational depth in gate levels */
 size_t b200net_level_width(const b200net *net, size_t level); /* gates (incl. NOT/COPY/CONST) in a level */
+size_t b200net_level_bootstraps(const b200net *net, size_t level); /* blind rotations the level costs */
 size_t b200net_bootstraps_per_cycle(const b200net *net);    /* 2-input gates = 1, MUX = 2, others 0 */
 size_t b200net_num_dff(const b200net *net);
 int32_t b200net_node_level(const b200net *net, size_t node); /* 0 for INPUT/DFF, k for gates */

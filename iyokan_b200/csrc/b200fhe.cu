@@ -576,10 +576,11 @@ static int br2_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
 // levels (< 445 jobs) run entirely on the latency shapes.
 constexpr int BR_MAX_SEGMENTS = 4;
 struct BrSegment { int variant, G, count; };
-static int plan_rotation(const b200fhe_ctx* c, int njobs, BrSegment (&seg)[BR_MAX_SEGMENTS])
+static int plan_rotation(const b200fhe_ctx* c, int njobs, BrSegment (&seg)[BR_MAX_SEGMENTS], double* model_ms = nullptr)
 {
     if (!c->autotune) {
         seg[0] = BrSegment{c->variant, c->G, njobs};
+        if (model_ms) *model_ms = 0.0;
         return 1;
     }
     constexpr double T5 = 2.41, T4 = 3.02, T34 = 10.25, T36 = 14.68;
@@ -602,6 +603,7 @@ static int plan_rotation(const b200fhe_ctx* c, int njobs, BrSegment (&seg)[BR_MA
                               0.01 * ((c6 > 0) + (c4 > 0));  // launch overhead breaks ties
             if (ms < best) best = ms, b6 = k6, b4 = k4;
         }
+    if (model_ms) *model_ms = best;
     int n = 0, left = njobs;
     auto push = [&](int variant, int G, int count) {
         if (count > 0) seg[n++] = BrSegment{variant, G, count};
@@ -1049,6 +1051,16 @@ int b200fhe_plan_rotation(int njobs, int* variant, int* jobs_per_cta, int* jobs,
         if (jobs) jobs[k] = seg[k].count;
     }
     return n;
+}
+
+double b200fhe_plan_ms(int njobs)
+{
+    if (njobs <= 0) return 0.0;
+    b200fhe_ctx tmp;
+    BrSegment seg[BR_MAX_SEGMENTS];
+    double ms = 0.0;
+    plan_rotation(&tmp, njobs, seg, &ms);
+    return ms;
 }
 
 int b200fhe_last_batch_segments(b200fhe_ctx* c, int* variant, int* jobs_per_cta, int* jobs, float* ms, int max_segments)

@@ -162,6 +162,13 @@ void b200net_destroy(b200net* net) { delete net; }
 size_t b200net_num_nodes(const b200net* net) { return net->n; }
 size_t b200net_num_levels(const b200net* net) { return net->levels.size(); }
 size_t b200net_level_width(const b200net* net, size_t l) { return l < net->levels.size() ? net->levels[l].size() : 0; }
+size_t b200net_level_bootstraps(const b200net* net, size_t l)
+{
+    if (l >= net->levels.size()) return 0;
+    size_t n = 0;
+    for (uint32_t node : net->levels[l]) n += bootstraps(net->kind[node]);
+    return n;
+}
 size_t b200net_bootstraps_per_cycle(const b200net* net) { return net->n_boot; }
 size_t b200net_num_dff(const b200net* net) { return net->dffs.size(); }
 int32_t b200net_node_level(const b200net* net, size_t node) { return node < net->n ? net->level[node] : -1; }

@@ -71,6 +71,7 @@ def load() -> ctypes.CDLL:
         "b200fhe_last_batch_ms": (ci, [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
         "b200fhe_last_batch_segments": (ci, [vp, vp, vp, vp, vp, ci]),
         "b200fhe_plan_rotation": (ci, [ci, vp, vp, vp, ci]),
+        "b200fhe_plan_ms": (ctypes.c_double, [ci]),
         "b200fhe_stream": (vp, [vp]),
         "b200fhe_test_bootstrap_lvl1": (ci, [vp, vp, vp, sz]),
         "b200fhe_test_keyswitch": (ci, [vp, vp, vp, sz]),
@@ -89,7 +90,7 @@ EXPORTS = [
     "b200fhe_arena_alloc", "b200fhe_arena_attach", "b200fhe_arena_slots", "b200fhe_arena_dev_ptr",
     "b200fhe_upload", "b200fhe_download", "b200fhe_gate_batch", "b200fhe_dff_tick", "b200fhe_sync",
     "b200fhe_query", "b200fhe_gates_host", "b200fhe_host_alloc", "b200fhe_host_free", "b200fhe_launch_count",
-    "b200fhe_last_batch_ms", "b200fhe_last_batch_segments", "b200fhe_plan_rotation", "b200fhe_stream", "b200fhe_test_bootstrap_lvl1", "b200fhe_test_keyswitch",
+    "b200fhe_last_batch_ms", "b200fhe_last_batch_segments", "b200fhe_plan_rotation", "b200fhe_plan_ms", "b200fhe_stream", "b200fhe_test_bootstrap_lvl1", "b200fhe_test_keyswitch",
     "b200fhe_test_read_bk_ntt",
 ]
 
@@ -134,6 +135,11 @@ def plan_rotation(njobs: int):
     v, g, n = (np.zeros(4, np.int32) for _ in range(3))
     k = lib.b200fhe_plan_rotation(int(njobs), _ptr(v), _ptr(g), _ptr(n), 4)
     return [(int(v[i]), int(g[i]), int(n[i])) for i in range(k)]
+
+
+def plan_ms(njobs: int) -> float:
+    """Modelled blind-rotation time (ms) of a frontier of `njobs` rotations under the launch plan."""
+    return float(load().b200fhe_plan_ms(int(njobs)))
 
 
 class Context:

@@ -194,7 +194,8 @@ def load_net():
             "b200net_destroy": (None, [vp]),
             "b200net_last_error": (ctypes.c_char_p, []),
             "b200net_num_nodes": (sz, [vp]), "b200net_num_levels": (sz, [vp]),
-            "b200net_level_width": (sz, [vp, sz]), "b200net_bootstraps_per_cycle": (sz, [vp]),
+            "b200net_level_width": (sz, [vp, sz]), "b200net_level_bootstraps": (sz, [vp, sz]),
+            "b200net_bootstraps_per_cycle": (sz, [vp]),
             "b200net_num_dff": (sz, [vp]), "b200net_node_level": (ctypes.c_int32, [vp, sz]),
             "b200net_slot_of": (ctypes.c_uint32, [vp, sz]), "b200net_num_slots": (sz, [vp]),
             "b200net_level_slot_base": (ctypes.c_uint32, [vp, sz]),
@@ -212,7 +213,7 @@ def load_net():
 
 NET_EXPORTS = [
     "b200net_create", "b200net_destroy", "b200net_last_error", "b200net_num_nodes", "b200net_num_levels",
-    "b200net_level_width", "b200net_bootstraps_per_cycle", "b200net_num_dff", "b200net_node_level",
+    "b200net_level_width", "b200net_level_bootstraps", "b200net_bootstraps_per_cycle", "b200net_num_dff", "b200net_node_level",
     "b200net_slot_of", "b200net_num_slots", "b200net_level_slot_base", "b200net_plain_eval", "b200net_plain_tick",
     "b200net_layout", "b200net_bind", "b200net_set", "b200net_get", "b200net_tick", "b200net_run", "b200net_run_level_shard",
 ]
@@ -254,6 +255,10 @@ class NetEngine:
     @property
     def level_widths(self):
         return [int(self.lib.b200net_level_width(self._h, l)) for l in range(self.num_levels)]
+
+    @property
+    def level_bootstraps(self):
+        return [int(self.lib.b200net_level_bootstraps(self._h, l)) for l in range(self.num_levels)]
 
     @property
     def bootstraps_per_cycle(self):

@@ -120,13 +120,25 @@ class ShardedRunner:
     """Runs the levels of a bound netlist on `world` ranks.  All ranks hold identical arenas between levels."""
 
     def __init__(self, nl: Netlist, eng: NetEngine, backend, rank: int, world: int, group=None,
-                 min_shard_width: int = 0):
+                 min_shard_width: int | None = 0, collective_ms: float = 0.1):
+        """min_shard_width: levels with fewer gates are computed redundantly on every rank.  None selects the
+        cost model instead: a level is split only when the launch plan of one share plus the exchange
+        (`collective_ms`) is faster than the plan of the whole level (b200fhe_plan_ms, measured B200 tables) -
+        e.g. a 100-rotation level fits one 3.0 ms wave either way, but its 50-rotation halves fit the 2.4 ms
+        cluster kernel."""
         self.nl, self.eng, self.be = nl, eng, backend
         self.rank, self.world, self.group = rank, world, group
         self.widths = eng.level_widths
         self.min_shard_width = min_shard_width
         self.exchanged_slots = 0
         self.collectives = 0
+        if min_shard_width is None:
+            from .lib import plan_ms
+
+            jobs = eng.level_bootstraps
+            self.replicate = [world == 1 or plan_ms(j) <= plan_ms(-(-j // world)) + collective_ms for j in jobs]
+        else:
+            self.replicate = [world == 1 or w < min_shard_width for w in self.widths]
 
     def _share(self, level):
         w = self.widths[level]
@@ -152,7 +164,7 @@ class ShardedRunner:
         import torch.distributed as dist
 
         for level, w in enumerate(self.widths):
-            replicate = self.world == 1 or w < self.min_shard_width
+            replicate = self.replicate[level]
             self._compute(level, everyone=replicate)
             if replicate:
                 continue

@@ -26,7 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", default="cahp-pearl-mux")
     ap.add_argument("--cycles", type=int, default=2)
-    ap.add_argument("--min-shard-width", type=int, default=150)
+    ap.add_argument("--min-shard-width", type=int, default=-1, help="-1 = cost model (b200fhe_plan_ms)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -43,7 +43,7 @@ def main():
     ctx = Context(local)
     ctx.load_keys(keys.bk, keys.ksk)
     be = GpuBackend(nl, eng, ctx, world)
-    run = ShardedRunner(nl, eng, be, rank, world, min_shard_width=args.min_shard_width)
+    run = ShardedRunner(nl, eng, be, rank, world, min_shard_width=None if args.min_shard_width < 0 else args.min_shard_width)
     enc = lambda bits: O.encrypt_bits(31, keys, bits)  # same seed on every rank -> identical ciphertexts  # noqa: E731
     req = case["request"]
     dffs = np.nonzero(nl.kind == N.DFF)[0]

@@ -101,6 +101,31 @@ def test_cahp_pearl_processor_runs_the_program(gpu_ctx, keys):
     assert N.bytes_of(ram[:e["size"]]) == e["bytes"]
 
 
+def _run_case_encrypted(gpu_ctx, keys, name, seed):
+    case = CASES[name]
+    nl = N.Netlist.load(NL / f"{name}.npz")
+    r = N.EncryptedRunner(nl, gpu_ctx, lambda bits: O.encrypt_bits(seed, keys, bits))
+    req = case["request"]
+    out = r.run(case["cycles"], inputs={p: N.bits_of(e["bytes"], e["size"]) for p, e in req["bits"].items()},
+                rams={p: N.bits_of(e["bytes"], e["size"]) for p, e in req["ram"].items()},
+                roms={p: N.bits_of(e["bytes"], e["size"]) for p, e in req["rom"].items()})
+    for port, e in case["expected"]["bits"].items():
+        assert N.bytes_of(O.decrypt_bits(keys, out[port])[:e["size"]]) == e["bytes"], (name, port)
+    for mem, e in case["expected"]["ram"].items():
+        got = O.decrypt_bits(keys, r.get_mem(mem))
+        assert N.bytes_of(got[:e["size"]]) == e["bytes"], (name, mem)
+
+
+def test_mux_ram_golden_eight_cycles(gpu_ctx, keys):
+    """test/in/test08.in -> test/out/test08.out: 8 write/read cycles, rdata and the whole 4096-bit RAM image."""
+    _run_case_encrypted(gpu_ctx, keys, "mux-ram-8-16-16", 29)
+
+
+def test_cahp_ruby_processor_golden(gpu_ctx, keys):
+    """VSP CAHP-ruby with MUX ROM/RAM, test09 program, 7 cycles (test/out/test09-ruby.out)."""
+    _run_case_encrypted(gpu_ctx, keys, "cahp-ruby-mux", 31)
+
+
 @pytest.mark.skipif(not O.have_iyokan_packet(), reason="oracle/_ref/iyokan-packet not built")
 def test_drop_in_with_the_reference_packet_tools(tmp_path):
     """Keys and encrypted request from the reference's own `iyokan-packet` (genkey, genevalkey, enc); this

@@ -58,7 +58,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("name,min_width", [("mux-ram-8-16-16", 0), ("cahp-pearl-mux", 64)])
+@pytest.mark.parametrize("name,min_width", [("mux-ram-8-16-16", 0), ("cahp-pearl-mux", 64), ("cahp-ruby-mux", None)])
 def test_two_rank_sharded_run_matches_reference_golden(name, min_width):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")

@@ -71,7 +71,8 @@ int b200fhe_set_jobs_per_cta(b200fhe_ctx *ctx, int g);
  * 4 = one job per CTA, 12 warps (6 teams of 64 threads), key staged into shared memory by bulk-async
  *     copies: low latency for one dependency level (jobs-per-CTA is ignored),
  * 5 = one job per 2-CTA thread-block cluster (one accumulator polynomial per SM, digit tiles exchanged
- *     by bulk-async copies through distributed shared memory): lowest latency, for <= 74 jobs */
+ *     by bulk-async copies through distributed shared memory), 6 teams x 64 threads x 16 points,
+ * 6 = as 5 with 128-thread x 8-point teams (12 warps per SM): lowest latency, for <= 74 jobs */
 int b200fhe_set_kernel_variant(b200fhe_ctx *ctx, int variant);
 
 /* keys: raw bootstrapping key + key-switching key in the reference's memory layout.

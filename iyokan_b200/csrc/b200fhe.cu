@@ -17,6 +17,7 @@
 #include "br2_phases.h"
 #include "br4_phases.h"
 #include "br5_phases.h"
+#include "br6_phases.h"
 #include "br_phases.h"
 #include "gate_jobs.h"
 #include "ks_phases.h"
@@ -408,6 +409,95 @@ br5_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict
     br5_epilogue(sm, q, tid, ubuf + (size_t)job * U_STRIDE);
 }
 
+
+// ---- fine-grained cluster shape: one job per 2-CTA cluster, 3 teams of 128 threads per CTA (br6_phases.h) ----
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BR6_THREADS, 1)
+br6_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ arena,
+           const uint32_t* __restrict__ bk_ntt, const Block8Tw* __restrict__ tw_g, uint32_t* __restrict__ ubuf, int n_iter)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Br6Smem sm;
+    sm.carve(smem_raw);
+    const int tid = threadIdx.x, d = tid >> 7, t = tid & 127;
+    const int q = (int)cluster_ctarank();
+    const int job = blockIdx.x >> 1;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tw_g);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(sm.tw);
+        for (int k = tid; k < (int)(sizeof(Block8Tw) / 4); k += BR6_THREADS) dst[k] = src[k];
+    }
+    uint64_t* mbar_dig = sm.mbar + 1;  // counts the bytes of the three digit tiles the peer copies in per step
+    if (tid == 0) {
+        mbar_init(sm.mbar, 1);
+        mbar_init(mbar_dig, 1);
+    }
+    const BrJob jb = jobs[job];
+    br6_prologue(sm, jb, arena, q, tid);
+    __syncthreads();
+    const uint32_t* key0 = bk_ntt + (size_t)q * BR5_KEY_WORDS;  // columns 3q..3q+2 of step 0
+    auto stage = [&](int i) {
+        constexpr uint32_t BYTES = BR5_KEY_WORDS * 4;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(sm.mbar)), "r"(BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(sm.keyb)),
+                     "l"(key0 + (size_t)i * BR4_KEY_WORDS), "r"(BYTES), "r"(smem_u32(sm.mbar))
+                     : "memory");
+    };
+    constexpr uint32_t TILE_BYTES = B8_WORDS * 4;
+    const uint32_t my_tile = smem_u32(sm.in_tile(q * GL + d));
+    uint32_t peer_tile, peer_bar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_tile) : "r"(my_tile), "r"((uint32_t)(q ^ 1)));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_bar) : "r"(smem_u32(mbar_dig)), "r"((uint32_t)(q ^ 1)));
+    if (tid == 0 && n_iter > 0) stage(0);
+    cluster_arrive();  // both CTAs have initialised their barriers before anyone copies into the other
+    cluster_wait();
+    cluster_arrive_relaxed();  // phase (B) of "step -1"
+
+    for (int i = 0; i < n_iter; i++) {
+        if (tid == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar_dig)),
+                         "r"(GL * TILE_BYTES)
+                         : "memory");
+        br6_fwd_p1(sm, i, q, d, t);
+        named_barrier_sync(1 + d, TEAM8_THREADS);
+        br6_fwd_p2(sm, q, d, t);
+        named_barrier_sync(1 + d, TEAM8_THREADS);
+        br6_fwd_p3(sm, q, d, t);
+        named_barrier_sync(1 + d, TEAM8_THREADS);
+        br6_fwd_p4(sm, q, d, t);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        cluster_wait();    // (B) the peer's pointwise stage of the previous step no longer reads my copies
+        named_barrier_sync(1 + d, TEAM8_THREADS);
+        if (t == 0)
+            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             peer_tile),
+                         "r"(my_tile), "r"(TILE_BYTES), "r"(peer_bar)
+                         : "memory");
+        mbar_wait(sm.mbar, (uint32_t)(i & 1));
+        uint64_t pacc[BR6_PW_PER_THREAD][4];
+        named_barrier_sync(7, BR6_THREADS);  // the local teams' tiles are complete
+        br6_pw_local(sm, q, tid, pacc);
+        mbar_wait(mbar_dig, (uint32_t)(i & 1));  // the peer's three tiles have landed
+        br6_pw_finish(sm, q, tid, pacc);
+        cluster_arrive_relaxed();  // (B) for the next step
+        __syncthreads();
+        if (tid == 0 && i + 1 < n_iter) stage(i + 1);
+        br6_inv_pA(sm, d, t);
+        named_barrier_sync(1 + d, TEAM8_THREADS);
+        br6_inv_pB(sm, d, t);
+        named_barrier_sync(1 + d, TEAM8_THREADS);
+        br6_inv_pC(sm, d, t);
+        named_barrier_sync(1 + d, TEAM8_THREADS);
+        br6_inv_pD(sm, d, t);
+        __syncthreads();
+    }
+    cluster_wait();
+    br6_epilogue(sm, q, tid, ubuf + (size_t)job * U_STRIDE);
+}
+
+
+
 __global__ void __launch_bounds__(KS_THREADS * KS_GROUPS)
 ks_kernel(const KsJob* __restrict__ jobs, const uint32_t* __restrict__ ubuf,
           const uint32_t* __restrict__ ksk_words, uint16_t* __restrict__ arena)
@@ -507,7 +597,8 @@ struct b200fhe_ctx {
     NttTables* tab = nullptr;
     tw_t* d_tw2f = nullptr;
     tw_t* d_tw2i = nullptr;
-    BlockTw* d_blocktw = nullptr;   // team-NTT twiddles (br4_kernel)
+    BlockTw* d_blocktw = nullptr;   // team-NTT twiddles (br4_kernel, br5_kernel)
+    Block8Tw* d_block8tw = nullptr; // 128-thread team NTT (br6_kernel)
     uint32_t* d_bk_ntt = nullptr;   // [636][6][6][1024]
     uint16_t* d_ksk = nullptr;      // [1024][7][3][640]
     bool keys = false;
@@ -567,7 +658,7 @@ static int br2_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
 }
 
 // Launch plan from the measured latency tables (profiles/r01_latency_table*.json, B200, ms per wave):
-//   variant 5 (one job per 2-SM cluster)  74 jobs per wave,  2.41 ms  -> lowest latency
+//   variant 6 (one job per 2-SM cluster)  74 jobs per wave,  2.09 ms  -> lowest latency
 //   variant 4 (one job per SM)           148 jobs per wave,  3.02 ms  -> 49.0 k rotations/s
 //   variant 3, 4 jobs per CTA            592 jobs per wave, 10.25 ms  -> 57.8 k/s
 //   variant 3, 6 jobs per CTA            888 jobs per wave, 14.68 ms  -> 60.5 k/s
@@ -583,7 +674,7 @@ static int plan_rotation(const b200fhe_ctx* c, int njobs, BrSegment (&seg)[BR_MA
         if (model_ms) *model_ms = 0.0;
         return 1;
     }
-    constexpr double T5 = 2.41, T4 = 3.02, T34 = 10.25, T36 = 14.68;
+    constexpr double T5 = 2.09, T4 = 3.02, T34 = 10.25, T36 = 14.68;
     constexpr int W5 = 74, W4 = 148, W34 = 592, W36 = 888;
     auto waves = [](int count, int per_wave) { return (count + per_wave - 1) / per_wave; };
     // tail on the latency shapes: full one-job-per-SM waves, the last partial wave on clusters if it fits
@@ -614,7 +705,7 @@ static int plan_rotation(const b200fhe_ctx* c, int njobs, BrSegment (&seg)[BR_MA
     const int r = left % W4;
     if (r > 0 && r <= W5) {
         push(4, 1, left - r);
-        push(5, 1, r);
+        push(6, 1, r);
     } else {
         push(4, 1, left);
     }
@@ -663,9 +754,23 @@ static int br5_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
     return 0;
 }
 
+static int br6_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+{
+    static bool attr_set[64] = {};
+    if (!attr_set[c->device]) {
+        CK(cudaFuncSetAttribute(br6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br6Smem::BYTES));
+        attr_set[c->device] = true;
+    }
+    br6_kernel<<<2 * njobs, BR6_THREADS, Br6Smem::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_block8tw, ubuf, N0);
+    CK(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
 static int br_dispatch_one(b200fhe_ctx* c, int variant, int G, int njobs, const uint16_t* arena, uint32_t* ubuf,
                            const BrJob* d_jobs)
 {
+    if (variant == 6) return br6_launch(c, njobs, arena, ubuf, d_jobs);
     if (variant == 5) return br5_launch(c, njobs, arena, ubuf, d_jobs);
     if (variant == 4) return br4_launch(c, njobs, arena, ubuf, d_jobs);
     if (variant == 3) {
@@ -780,8 +885,13 @@ int b200fhe_create(b200fhe_ctx** out, int device)
     block_tw_init(*c->tab, *btw);
     CK(cudaMalloc(&c->d_blocktw, sizeof(BlockTw)));
     CK(cudaMemcpyAsync(c->d_blocktw, btw, sizeof(BlockTw), cudaMemcpyHostToDevice, c->stream));
+    Block8Tw* b8tw = new Block8Tw();
+    block8_tw_init(*c->tab, *b8tw);
+    CK(cudaMalloc(&c->d_block8tw, sizeof(Block8Tw)));
+    CK(cudaMemcpyAsync(c->d_block8tw, b8tw, sizeof(Block8Tw), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     delete btw;
+    delete b8tw;
     *out = c;
     return 0;
 }
@@ -794,6 +904,7 @@ void b200fhe_destroy(b200fhe_ctx* c)
     cudaFree(c->d_tw2f);
     cudaFree(c->d_tw2i);
     cudaFree(c->d_blocktw);
+    cudaFree(c->d_block8tw);
     cudaFree(c->d_bk_ntt);
     cudaFree(c->d_ksk);
     if (c->arena_owned) cudaFree(c->d_arena);
@@ -831,7 +942,7 @@ int b200fhe_set_jobs_per_cta(b200fhe_ctx* c, int g)
 int b200fhe_set_kernel_variant(b200fhe_ctx* c, int variant)
 {
     if (!c) return fail("null context");
-    if (variant < 1 || variant > 5) return fail("kernel variant must be 1..5");
+    if (variant < 1 || variant > 6) return fail("kernel variant must be 1..6");
     c->variant = variant;
     c->autotune = false;
     return 0;

@@ -13,6 +13,7 @@
 #include "../../iyokan_b200/csrc/br2_phases.h"
 #include "../../iyokan_b200/csrc/br4_phases.h"
 #include "../../iyokan_b200/csrc/br5_phases.h"
+#include "../../iyokan_b200/csrc/br6_phases.h"
 #include "../../iyokan_b200/csrc/br_phases.h"
 #include "../../iyokan_b200/csrc/gate_jobs.h"
 #include "../../iyokan_b200/csrc/ks_phases.h"
@@ -21,6 +22,7 @@ using namespace b200;
 
 static NttTables g_tab;
 static BlockTw g_btw;
+static Block8Tw g_b8tw;
 static bool g_init = false;
 
 extern "C" void sim_init()
@@ -28,6 +30,7 @@ extern "C" void sim_init()
     if (!g_init) {
         ntt_tables_init(g_tab);
         block_tw_init(g_tab, g_btw);
+        block8_tw_init(g_tab, g_b8tw);
         g_init = true;
     }
 }
@@ -484,6 +487,92 @@ extern "C" void sim_blind_rotate5(const void* jobs_raw, int njobs, const uint16_
 #pragma omp parallel for schedule(dynamic, 1)
     for (int job = 0; job < njobs; job++) sim_br5_cluster(jobs, job, arena, bk_ntt, ubuf, n_iter);
 }
+
+
+// ---- variant 6: cluster shape with 128-thread x 8-point teams (br6_kernel) ----
+extern "C" void sim_block8_forward(const uint32_t* in, uint32_t* out)
+{
+    sim_init();
+    std::vector<uint32_t> tile(B8_WORDS);
+    for (int t = 0; t < TEAM8_THREADS; t++) {
+        uint32_t x[8];
+        for (int a = 0; a < 8; a++) x[a] = in[128 * a + t];
+        blk8_fwd_p1(x);
+        blk8_store_p1(tile.data(), x, t);
+    }
+    for (int t = 0; t < TEAM8_THREADS; t++) blk8_fwd_p2(tile.data(), g_b8tw.q2f, t);
+    for (int t = 0; t < TEAM8_THREADS; t++) blk8_fwd_p3(tile.data(), g_b8tw.q3f, t);
+    for (int t = 0; t < TEAM8_THREADS; t++) blk8_fwd_p4(tile.data(), g_b8tw.q4f, t);
+    for (int j = 0; j < N1; j++) out[j] = tile[b8_pad(j)];
+}
+extern "C" void sim_block8_inverse(const uint32_t* in, uint32_t* out)
+{
+    sim_init();
+    std::vector<uint32_t> tile(B8_WORDS);
+    for (int j = 0; j < N1; j++) tile[b8_pad(j)] = in[j];
+    for (int t = 0; t < TEAM8_THREADS; t++) blk8_inv_pA(tile.data(), g_b8tw.q4i, t);
+    for (int t = 0; t < TEAM8_THREADS; t++) blk8_inv_pB(tile.data(), g_b8tw.q3i, t);
+    for (int t = 0; t < TEAM8_THREADS; t++) blk8_inv_pC(tile.data(), g_b8tw.q2i, t);
+    for (int t = 0; t < TEAM8_THREADS; t++) {
+        uint32_t x[8];
+        blk8_load_p1(tile.data(), x, t);
+        blk8_inv_pD(x);
+        for (int a = 0; a < 8; a++) out[128 * a + t] = x[a];
+    }
+}
+
+static void sim_br6_cluster(const BrJob* jobs, int job, const uint16_t* arena, const uint32_t* bk_ntt, uint32_t* ubuf,
+                            int n_iter)
+{
+    std::vector<uint8_t> smem[2] = {std::vector<uint8_t>(Br6Smem::BYTES + 128), std::vector<uint8_t>(Br6Smem::BYTES + 128)};
+    Br6Smem sm[2];
+    for (int q = 0; q < 2; q++) {
+        sm[q].carve(reinterpret_cast<void*>(((uintptr_t)smem[q].data() + 127) & ~(uintptr_t)127));
+        std::memcpy(sm[q].tw, &g_b8tw, sizeof(Block8Tw));
+        for (int tid = 0; tid < BR6_THREADS; tid++) br6_prologue(sm[q], jobs[job], arena, q, tid);
+    }
+    auto each = [&](auto fn) {
+        for (int q = 0; q < 2; q++)
+            for (int tid = 0; tid < BR6_THREADS; tid++) fn(q, tid >> 7, tid & 127);
+    };
+    std::vector<uint64_t> pacc((size_t)2 * BR6_THREADS * BR6_PW_PER_THREAD * 4);
+    auto acc_of = [&](int q, int tid) -> uint64_t(&)[BR6_PW_PER_THREAD][4] {
+        return *reinterpret_cast<uint64_t(*)[BR6_PW_PER_THREAD][4]>(
+            pacc.data() + ((size_t)q * BR6_THREADS + tid) * BR6_PW_PER_THREAD * 4);
+    };
+    for (int i = 0; i < n_iter; i++) {
+        for (int q = 0; q < 2; q++)
+            std::memcpy(sm[q].keyb, bk_ntt + (size_t)i * BR4_KEY_WORDS + (size_t)q * BR5_KEY_WORDS, (size_t)BR5_KEY_WORDS * 4);
+        each([&](int q, int d, int t) { br6_fwd_p1(sm[q], i, q, d, t); });
+        each([&](int q, int d, int t) { br6_fwd_p2(sm[q], q, d, t); });
+        each([&](int q, int d, int t) { br6_fwd_p3(sm[q], q, d, t); });
+        each([&](int q, int d, int t) { br6_fwd_p4(sm[q], q, d, t); });
+        for (int q = 0; q < 2; q++)
+            for (int d = 0; d < GL; d++)
+                std::memcpy(sm[q ^ 1].in_tile(q * GL + d), sm[q].in_tile(q * GL + d), (size_t)B8_WORDS * 4);
+        for (int q = 0; q < 2; q++)
+            for (int tid = 0; tid < BR6_THREADS; tid++) br6_pw_local(sm[q], q, tid, acc_of(q, tid));
+        for (int q = 0; q < 2; q++)
+            for (int tid = 0; tid < BR6_THREADS; tid++) br6_pw_finish(sm[q], q, tid, acc_of(q, tid));
+        each([&](int q, int d, int t) { br6_inv_pA(sm[q], d, t); });
+        each([&](int q, int d, int t) { br6_inv_pB(sm[q], d, t); });
+        each([&](int q, int d, int t) { br6_inv_pC(sm[q], d, t); });
+        each([&](int q, int d, int t) { br6_inv_pD(sm[q], d, t); });
+    }
+    for (int q = 0; q < 2; q++)
+        for (int tid = 0; tid < BR6_THREADS; tid++) br6_epilogue(sm[q], q, tid, ubuf + (size_t)job * U_STRIDE);
+}
+
+extern "C" void sim_blind_rotate6(const void* jobs_raw, int njobs, const uint16_t* arena, const uint32_t* bk_ntt,
+                                  uint32_t* ubuf, int n_iter)
+{
+    sim_init();
+    const BrJob* jobs = reinterpret_cast<const BrJob*>(jobs_raw);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int job = 0; job < njobs; job++) sim_br6_cluster(jobs, job, arena, bk_ntt, ubuf, n_iter);
+}
+
+
 
 // ksk_dev: uint16 [1024][7][3][640]; jobs: packed KsJob (16 bytes each)
 extern "C" void sim_keyswitch(const void* jobs_raw, int njobs, const uint32_t* ubuf, const uint16_t* ksk_dev,

@@ -57,15 +57,15 @@ def test_launch_plan_covers_every_frontier_size():
         assert 1 <= len(plan) <= 4
         assert sum(c for _, _, c in plan) == n
         order = [(v, g) for v, g, _ in plan]
-        assert order == sorted(order, key=lambda vg: {(3, 6): 0, (3, 4): 1, (4, 1): 2, (5, 1): 3}[vg])
+        assert order == sorted(order, key=lambda vg: {(3, 6): 0, (3, 4): 1, (4, 1): 2, (6, 1): 3}[vg])
         for v, g, c in plan:
             if (v, g) == (3, 6):
                 assert c % 888 == 0 or c == n
-            if (v, g) == (5, 1):
+            if (v, g) == (6, 1):
                 assert c <= 74
-    assert plan_rotation(30) == [(5, 1, 30)]
-    assert plan_rotation(74) == [(5, 1, 74)]
+    assert plan_rotation(30) == [(6, 1, 30)]
+    assert plan_rotation(74) == [(6, 1, 74)]
     assert plan_rotation(100) == [(4, 1, 100)]
-    assert plan_rotation(148 + 20) == [(4, 1, 148), (5, 1, 20)]
-    assert plan_rotation(8192) == [(3, 6, 7992), (4, 1, 148), (5, 1, 52)]
+    assert plan_rotation(148 + 20) == [(4, 1, 148), (6, 1, 20)]
+    assert plan_rotation(8192) == [(3, 6, 7992), (4, 1, 148), (6, 1, 52)]
     assert plan_rotation(0) == []

@@ -86,9 +86,11 @@ def test_blind_rotate_variant4_bit_exact(gpu_ctx, keys, golden):
         gpu_ctx.set_jobs_per_cta(0)
 
 
-def test_blind_rotate_variant5_bit_exact(gpu_ctx, keys, golden):
-    # cluster shape: one job per 2-CTA cluster, digit tiles exchanged through distributed shared memory
-    gpu_ctx.set_kernel_variant(5)
+@pytest.mark.parametrize("variant", [5, 6])
+def test_blind_rotate_cluster_shapes_bit_exact(gpu_ctx, keys, golden, variant):
+    # cluster shapes: one job per 2-CTA cluster, digit tiles exchanged through distributed shared memory
+    # (5: 64-thread x 16-point teams, 6: 128-thread x 8-point teams)
+    gpu_ctx.set_kernel_variant(variant)
     try:
         c = golden["br_in"][:5]
         assert np.array_equal(gpu_ctx.test_bootstrap_lvl1(c), O.bootstrap_to_lvl1(keys, c))

@@ -140,6 +140,13 @@ def test_team_ntt_equals_warp_ntt(sim):
         sim.sim_warp_inverse(p(x), p(a))
         sim.sim_block_inverse(p(x), p(b))
         assert np.array_equal(a, b)
+        # 128-thread x 8-point transform (ntt_block8.h)
+        sim.sim_warp_forward(p(x), p(a))
+        sim.sim_block8_forward(p(x), p(b))
+        assert np.array_equal(a, b)
+        sim.sim_warp_inverse(p(x), p(a))
+        sim.sim_block8_inverse(p(x), p(b))
+        assert np.array_equal(a, b)
 
 
 def test_blind_rotate_variant4_bit_exact(sim, keys, bk_ntt_sim):
@@ -179,6 +186,26 @@ def test_blind_rotate_variant5_bit_exact(sim, keys, bk_ntt_sim):
     sim.sim_blind_rotate5(p(jobs), n, p(arena), p(bk_ntt_sim), p(ubuf), 636)
     c = (-ca.astype(np.int32) - cb.astype(np.int32)).astype(np.uint16)
     c[:, 636] += np.uint16(1 << 13)
+    assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
+
+
+def test_blind_rotate_variant6_bit_exact(sim, keys, bk_ntt_sim):
+    # fine-grained cluster shape (br6_phases.h): 128-thread x 8-point teams
+    rng = np.random.default_rng(66)
+    n = 3
+    pa, pb = rng.integers(0, 2, n, dtype=np.uint8), rng.integers(0, 2, n, dtype=np.uint8)
+    ca, cb = O.encrypt_bits(11, keys, pa), O.encrypt_bits(12, keys, pb)
+    arena = np.zeros((2 * n, 640), np.uint16)
+    arena[:n, :637], arena[n:, :637] = ca, cb
+    jobs = np.zeros(n, BRJOB)
+    for g in range(n):
+        jobs[g]["in"] = (g, n + g, 0)
+        jobs[g]["sgn"] = (1, -1, 0)          # ANDYN: a - b - mu
+        jobs[g]["off"] = (-(1 << 13)) & 0xFFFF
+    ubuf = np.zeros((n, 1028), np.uint32)
+    sim.sim_blind_rotate6(p(jobs), n, p(arena), p(bk_ntt_sim), p(ubuf), 636)
+    c = (ca.astype(np.int32) - cb.astype(np.int32)).astype(np.uint16)
+    c[:, 636] -= np.uint16(1 << 13)
     assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
 
 

@@ -65,6 +65,7 @@ def main():
     for name in ("bench.log", "bench_ref.log", "pytest_gpu.log", "microbench_pipes.txt", "latency_table.json",
                  "net_mux-ram-8-16-16_n1.log", "net_cahp-pearl-mux_n1.log", "net_cahp-ruby-mux_n1.log",
                  "net_mux-ram-8-16-16_n2.log", "net_cahp-pearl-mux_n2.log", "net_cahp-ruby-mux_n2.log",
+                 "net_mux-ram-8-16-16_n4.log", "net_cahp-pearl-mux_n4.log", "net_cahp-ruby-mux_n4.log",
                  "net_mux-ram-8-16-16_n8.log", "net_cahp-pearl-mux_n8.log", "net_cahp-ruby-mux_n8.log",
                  "bench_n1.log", "bench_n2.log", "bench_n4.log", "bench_n8.log"):
         if (OUT / name).exists():

@@ -475,7 +475,7 @@ br6_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict
                          "r"(my_tile), "r"(TILE_BYTES), "r"(peer_bar)
                          : "memory");
         mbar_wait(sm.mbar, (uint32_t)(i & 1));
-        uint64_t pacc[BR6_PW_PER_THREAD][4];
+        uint64_t pacc[LIMBS][4];
         named_barrier_sync(7, BR6_THREADS);  // the local teams' tiles are complete
         br6_pw_local(sm, q, tid, pacc);
         mbar_wait(mbar_dig, (uint32_t)(i & 1));  // the peer's three tiles have landed

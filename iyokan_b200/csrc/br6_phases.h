@@ -14,7 +14,6 @@
 namespace b200 {
 
 constexpr int BR6_THREADS = GL * TEAM8_THREADS;              // 384
-constexpr int BR6_PW_PER_THREAD = BR5_PW_ITEMS / BR6_THREADS;  // 2 items = (quad, limb column) per thread
 
 struct Br6Smem {
     static constexpr size_t BYTES = (size_t)BR5_KEY_WORDS * 4 + (size_t)(ROWS + LIMBS) * B8_WORDS * 4 + (size_t)N1 * 4 +
@@ -88,39 +87,43 @@ B200_HD void br6_fwd_p2(const Br6Smem& sm, int q, int d, int t) { blk8_fwd_p2(sm
 B200_HD void br6_fwd_p3(const Br6Smem& sm, int q, int d, int t) { blk8_fwd_p3(sm.in_tile(q * GL + d), sm.tw->q3f, t); }
 B200_HD void br6_fwd_p4(const Br6Smem& sm, int q, int d, int t) { blk8_fwd_p4(sm.in_tile(q * GL + d), sm.tw->q4f, t); }
 
-// pointwise stage, split around the arrival of the peer's tiles exactly as br5_pw_local / br5_pw_finish
-B200_HD void br6_pw_rows(const Br6Smem& sm, int tid, int row0, uint64_t (&acc)[BR6_PW_PER_THREAD][4])
+// Pointwise stage, split around the arrival of the peer's tiles like br5_pw_local / br5_pw_finish.
+// A thread (tid < 256) owns quad m = tid of NTT positions for ALL three limb columns of the CTA's
+// polynomial, so each digit quad is read once instead of three times: the stage is bound by
+// shared-memory wavefronts (key 576 + digits 216 per step), not by the multiplies, and eight busy
+// warps already saturate them.
+constexpr int BR6_PW_THREADS = N1 / 4;  // 256
+B200_HD void br6_pw_rows(const Br6Smem& sm, int m, int row0, uint64_t (&acc)[LIMBS][4])
 {
+    const int toff = b8_quad(m);
     B200_UNROLL
-    for (int k = 0; k < BR6_PW_PER_THREAD; k++) {
-        const int item = tid + k * BR6_THREADS, m = item & 255, l = item >> 8;
-        const int toff = b8_quad(m);
+    for (int rr = 0; rr < GL; rr++) {
+        const u32x4 dv = *reinterpret_cast<const u32x4*>(sm.in_tile(row0 + rr) + toff);
         B200_UNROLL
-        for (int rr = 0; rr < GL; rr++) {
-            const u32x4 dv = *reinterpret_cast<const u32x4*>(sm.in_tile(row0 + rr) + toff);
+        for (int l = 0; l < LIMBS; l++) {
             const u32x4 kk = *reinterpret_cast<const u32x4*>(sm.keyb + (size_t)(l * ROWS + row0 + rr) * N1 + 4 * m);
-            acc[k][0] += (uint64_t)dv.x * kk.x;
-            acc[k][1] += (uint64_t)dv.y * kk.y;
-            acc[k][2] += (uint64_t)dv.z * kk.z;
-            acc[k][3] += (uint64_t)dv.w * kk.w;
+            acc[l][0] += (uint64_t)dv.x * kk.x;
+            acc[l][1] += (uint64_t)dv.y * kk.y;
+            acc[l][2] += (uint64_t)dv.z * kk.z;
+            acc[l][3] += (uint64_t)dv.w * kk.w;
         }
     }
 }
-B200_HD void br6_pw_local(const Br6Smem& sm, int q, int tid, uint64_t (&acc)[BR6_PW_PER_THREAD][4])
+B200_HD void br6_pw_local(const Br6Smem& sm, int q, int tid, uint64_t (&acc)[LIMBS][4])
 {
+    if (tid >= BR6_PW_THREADS) return;
     B200_UNROLL
-    for (int k = 0; k < BR6_PW_PER_THREAD; k++) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0;
+    for (int l = 0; l < LIMBS; l++) acc[l][0] = acc[l][1] = acc[l][2] = acc[l][3] = 0;
     br6_pw_rows(sm, tid, q * GL, acc);
 }
-B200_HD void br6_pw_finish(const Br6Smem& sm, int q, int tid, uint64_t (&acc)[BR6_PW_PER_THREAD][4])
+B200_HD void br6_pw_finish(const Br6Smem& sm, int q, int tid, uint64_t (&acc)[LIMBS][4])
 {
+    if (tid >= BR6_PW_THREADS) return;
     br6_pw_rows(sm, tid, (q ^ 1) * GL, acc);
     B200_UNROLL
-    for (int k = 0; k < BR6_PW_PER_THREAD; k++) {
-        const int item = tid + k * BR6_THREADS, m = item & 255, l = item >> 8;
-        *reinterpret_cast<u32x4*>(sm.out_tile(l) + b8_quad(m)) =
-            u32x4{redc64(acc[k][0]), redc64(acc[k][1]), redc64(acc[k][2]), redc64(acc[k][3])};
-    }
+    for (int l = 0; l < LIMBS; l++)
+        *reinterpret_cast<u32x4*>(sm.out_tile(l) + b8_quad(tid)) =
+            u32x4{redc64(acc[l][0]), redc64(acc[l][1]), redc64(acc[l][2]), redc64(acc[l][3])};
 }
 
 B200_HD void br6_inv_pA(const Br6Smem& sm, int l, int t) { blk8_inv_pA(sm.out_tile(l), sm.tw->q4i, t); }

@@ -535,10 +535,9 @@ static void sim_br6_cluster(const BrJob* jobs, int job, const uint16_t* arena, c
         for (int q = 0; q < 2; q++)
             for (int tid = 0; tid < BR6_THREADS; tid++) fn(q, tid >> 7, tid & 127);
     };
-    std::vector<uint64_t> pacc((size_t)2 * BR6_THREADS * BR6_PW_PER_THREAD * 4);
-    auto acc_of = [&](int q, int tid) -> uint64_t(&)[BR6_PW_PER_THREAD][4] {
-        return *reinterpret_cast<uint64_t(*)[BR6_PW_PER_THREAD][4]>(
-            pacc.data() + ((size_t)q * BR6_THREADS + tid) * BR6_PW_PER_THREAD * 4);
+    std::vector<uint64_t> pacc((size_t)2 * BR6_THREADS * LIMBS * 4);
+    auto acc_of = [&](int q, int tid) -> uint64_t(&)[LIMBS][4] {
+        return *reinterpret_cast<uint64_t(*)[LIMBS][4]>(pacc.data() + ((size_t)q * BR6_THREADS + tid) * LIMBS * 4);
     };
     for (int i = 0; i < n_iter; i++) {
         for (int q = 0; q < 2; q++)

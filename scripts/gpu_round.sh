@@ -2,6 +2,7 @@
 # One GPU call: parity tests, bench (both arms), netlist runs, ncu launch list, ncu full capture of the hot kernel.
 set -x
 mkdir -p gpurun_out
+timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -2 | tee gpurun_out/smoke.log
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench.log
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 2>&1 | tail -1 | tee gpurun_out/bench_ref.log
@@ -17,5 +18,5 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:br3_
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 # latency shapes at the sizes they serve
 VARIANT=4 NB=148 GLIST=1 bash scripts/gpu_ncu.sh > /dev/null 2>&1
-VARIANT=5 NB=74 GLIST=1 bash scripts/gpu_ncu.sh > /dev/null 2>&1
+VARIANT=6 NB=74 GLIST=1 bash scripts/gpu_ncu.sh > /dev/null 2>&1
 ls -la gpurun_out

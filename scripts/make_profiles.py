@@ -62,7 +62,7 @@ def main():
             lines.append(f"| `{k}` | {len(v)} | {sum(v) / 1e6:.3f} | {sum(v) / tot:.3f} |")
         (PROF / f"{ROUND}_launch_list.md").write_text("\n".join(lines) + "\n")
         (PROF / f"{ROUND}_launches.csv").write_text(open(lc).read())
-    for name in ("bench.log", "bench_ref.log", "pytest_gpu.log", "microbench_pipes.txt", "latency_table.json",
+    for name in ("bench.log", "bench_ref.log", "pytest_gpu.log", "smoke.log", "microbench_pipes.txt", "latency_table.json",
                  "net_mux-ram-8-16-16_n1.log", "net_cahp-pearl-mux_n1.log", "net_cahp-ruby-mux_n1.log",
                  "net_mux-ram-8-16-16_n2.log", "net_cahp-pearl-mux_n2.log", "net_cahp-ruby-mux_n2.log",
                  "net_mux-ram-8-16-16_n4.log", "net_cahp-pearl-mux_n4.log", "net_cahp-ruby-mux_n4.log",

@@ -527,6 +527,56 @@ ks_kernel(const KsJob* __restrict__ jobs, const uint32_t* __restrict__ ubuf,
     }
 }
 
+
+// Narrow frontiers: one key switch split over KS_SPLIT CTAs (256 coefficients each) + a tiny combine
+// kernel, so that a level of a few dozen gates uses all SMs for its key switch as well.
+__global__ void __launch_bounds__(KS_THREADS * KS_GROUPS)
+ks_split_kernel(const KsJob* __restrict__ jobs, const uint32_t* __restrict__ ubuf,
+                const uint32_t* __restrict__ ksk_words, uint32_t* __restrict__ partial)
+{
+    constexpr int SPAN = N1 / KS_SPLIT;
+    __shared__ uint16_t codes[SPAN];
+    __shared__ uint32_t part[KS_GROUPS - 1][2][KS_THREADS];
+    const int gate = blockIdx.x / KS_SPLIT, piece = blockIdx.x % KS_SPLIT, i0 = piece * SPAN;
+    const KsJob job = jobs[gate];
+    const int k = threadIdx.x, y = threadIdx.y, tid = y * KS_THREADS + k;
+    for (int i = tid; i < SPAN; i += KS_THREADS * KS_GROUPS) codes[i] = ks_code(ubuf, job, i0 + i);
+    __syncthreads();
+    uint32_t lo, hi;
+    ks_accumulate_range(ksk_words, codes, k, y, KS_GROUPS, i0, i0 + SPAN, lo, hi);
+    if (y > 0) {
+        part[y - 1][0][k] = lo;
+        part[y - 1][1][k] = hi;
+    }
+    __syncthreads();
+    if (y == 0) {
+#pragma unroll
+        for (int g = 0; g < KS_GROUPS - 1; g++) {
+            lo += part[g][0][k];
+            hi += part[g][1][k];
+        }
+        uint32_t* out = partial + (size_t)blockIdx.x * 2 * KS_THREADS;
+        out[k] = lo;
+        out[KS_THREADS + k] = hi;
+    }
+}
+__global__ void __launch_bounds__(KS_THREADS)
+ks_combine_kernel(const KsJob* __restrict__ jobs, const uint32_t* __restrict__ ubuf,
+                  const uint32_t* __restrict__ partial, uint16_t* __restrict__ arena)
+{
+    const KsJob job = jobs[blockIdx.x];
+    const int k = threadIdx.x;
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int p = 0; p < KS_SPLIT; p++) {
+        const uint32_t* in = partial + (size_t)(blockIdx.x * KS_SPLIT + p) * 2 * KS_THREADS;
+        lo += in[k];
+        hi += in[KS_THREADS + k];
+    }
+    reinterpret_cast<uint32_t*>(arena + (size_t)job.out * SLOT_STRIDE)[k] =
+        ks_finish(lo, hi, ks_b_rounded(ubuf, job), job.post, k);
+}
+
 // Reads every source before any destination is written (two launches: gather, scatter) so that
 // a DFF chain Q1 <- D1 = Q0 ticks correctly even when src and dst sets overlap.
 __global__ void __launch_bounds__(KS_THREADS)
@@ -612,6 +662,7 @@ struct b200fhe_ctx {
     UnaryJob *h_un = nullptr, *d_un = nullptr;
     uint32_t* d_ubuf = nullptr;     // [2*cap][U_STRIDE]
     uint32_t* d_unstage = nullptr;  // [cap][320]
+    uint32_t* d_kspart = nullptr;   // [KS_SPLIT_MAX_GATES][KS_SPLIT][2][320] partial sums of the split key switch
     cudaEvent_t ev_staged = nullptr, ev_t[3] = {nullptr, nullptr, nullptr};
     bool staged_pending = false, timed = false;
     // per-segment timing of the most recent launch plan (see plan_rotation)
@@ -821,6 +872,22 @@ static int br_dispatch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_
     return 0;
 }
 
+// key switch of `nks` gates: one CTA per gate, or KS_SPLIT CTAs per gate + combine for narrow frontiers
+static int ks_dispatch(b200fhe_ctx* c, size_t nks, const KsJob* d_jobs, const uint32_t* ubuf, uint16_t* arena)
+{
+    const uint32_t* ksk = reinterpret_cast<const uint32_t*>(c->d_ksk);
+    if (nks <= (size_t)KS_SPLIT_MAX_GATES) {
+        ks_split_kernel<<<(unsigned)(nks * KS_SPLIT), dim3(KS_THREADS, KS_GROUPS), 0, c->stream>>>(d_jobs, ubuf, ksk, c->d_kspart);
+        ks_combine_kernel<<<(unsigned)nks, KS_THREADS, 0, c->stream>>>(d_jobs, ubuf, c->d_kspart, arena);
+        c->launches += 2;
+    } else {
+        ks_kernel<<<(unsigned)nks, dim3(KS_THREADS, KS_GROUPS), 0, c->stream>>>(d_jobs, ubuf, ksk, arena);
+        c->launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 static int ensure_cap(b200fhe_ctx* c, size_t n)
 {
     if (n <= c->cap) return 0;
@@ -889,6 +956,7 @@ int b200fhe_create(b200fhe_ctx** out, int device)
     block8_tw_init(*c->tab, *b8tw);
     CK(cudaMalloc(&c->d_block8tw, sizeof(Block8Tw)));
     CK(cudaMemcpyAsync(c->d_block8tw, b8tw, sizeof(Block8Tw), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMalloc(&c->d_kspart, (size_t)KS_SPLIT_MAX_GATES * KS_SPLIT * 2 * KS_THREADS * 4));
     CK(cudaStreamSynchronize(c->stream));
     delete btw;
     delete b8tw;
@@ -916,6 +984,7 @@ void b200fhe_destroy(b200fhe_ctx* c)
     cudaFree(c->d_un);
     cudaFree(c->d_ubuf);
     cudaFree(c->d_unstage);
+    cudaFree(c->d_kspart);
     cudaEventDestroy(c->ev_staged);
     for (auto& e : c->ev_t) cudaEventDestroy(e);
     for (auto& e : c->ev_seg) cudaEventDestroy(e);
@@ -1085,10 +1154,7 @@ int b200fhe_gate_batch(b200fhe_ctx* c, const uint8_t* opcode, const uint32_t* in
         CK(cudaEventRecord(c->ev_t[0], c->stream));
         if (br_dispatch(c, (int)nbr, c->d_arena, c->d_ubuf, c->d_br)) return 1;
         CK(cudaEventRecord(c->ev_t[1], c->stream));
-        ks_kernel<<<(unsigned)nks, dim3(KS_THREADS, KS_GROUPS), 0, c->stream>>>(c->d_ks, c->d_ubuf,
-                                                               reinterpret_cast<const uint32_t*>(c->d_ksk), c->d_arena);
-        CK(cudaGetLastError());
-        c->launches++;
+        if (ks_dispatch(c, nks, c->d_ks, c->d_ubuf, c->d_arena)) return 1;
         CK(cudaEventRecord(c->ev_t[2], c->stream));
         c->timed = true;
     }
@@ -1284,9 +1350,7 @@ int b200fhe_test_keyswitch(b200fhe_ctx* c, const uint32_t* tlwe1_host, uint16_t*
     CK(cudaMemcpy2DAsync(d_u, U_STRIDE * 4, tlwe1_host, TLWE1_LEN * 4, TLWE1_LEN * 4, n, cudaMemcpyHostToDevice,
                          c->stream));
     CK(cudaMemcpyAsync(d_jobs, jobs.data(), n * sizeof(KsJob), cudaMemcpyHostToDevice, c->stream));
-    ks_kernel<<<(unsigned)n, dim3(KS_THREADS, KS_GROUPS), 0, c->stream>>>(d_jobs, d_u, reinterpret_cast<const uint32_t*>(c->d_ksk), d_out);
-    CK(cudaGetLastError());
-    c->launches++;
+    if (ks_dispatch(c, n, d_jobs, d_u, d_out)) return 1;
     CK(cudaMemcpy2DAsync(tlwe0_host, TLWE0_LEN * 2, d_out, SLOT_STRIDE * 2, TLWE0_LEN * 2, n, cudaMemcpyDeviceToHost,
                          c->stream));
     CK(cudaStreamSynchronize(c->stream));

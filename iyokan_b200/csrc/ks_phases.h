@@ -42,6 +42,8 @@ B200_HD uint32_t ks_b_rounded(const uint32_t* ubuf, const KsJob& job)
 }
 
 constexpr int KS_GROUPS = 3;  // row groups per CTA: group y walks coefficients i = y, y+3, ... (latency / 3)
+constexpr int KS_SPLIT = 4;   // CTAs per key switch on the narrow-frontier path (256 coefficients each)
+constexpr int KS_SPLIT_MAX_GATES = 148;  // frontiers up to this size use the split path
 
 // phase 2: thread (k, y) accumulates word k of every selected row of its coefficient group.
 // ksk_words: [1024][7][3][320] uint32 (row padded to 640 uint16).  Returns the two partial sums.
@@ -51,6 +53,27 @@ B200_HD void ks_accumulate_group(const uint32_t* ksk_words, const uint16_t* code
     uint32_t lo = 0, hi = 0;
     for (int i = y; i < N1; i += ngroups) {
         const uint32_t code = codes[i];
+        B200_UNROLL
+        for (int j = 0; j < KS_T; j++) {
+            const uint32_t g = (code >> (2 * (KS_T - 1 - j))) & 3u;
+            const uint32_t* row = ksk_words + (size_t)((i * KS_T + j) * 3 + (g ? g - 1 : 0)) * KS_THREADS;
+            const uint32_t w = g ? row[k] : 0u;
+            lo += w;
+            hi += w >> 16;
+        }
+    }
+    lo_out = lo;
+    hi_out = hi;
+}
+// same walk restricted to coefficients [i0, i1), i = i0 + y, i0 + y + ngroups, ...: used when ONE key
+// switch is split over several CTAs (narrow frontiers, where half the SMs would otherwise idle).
+// `codes` holds the digit codes of that range only (codes[i - i0]).
+B200_HD void ks_accumulate_range(const uint32_t* ksk_words, const uint16_t* codes, int k, int y, int ngroups, int i0,
+                                 int i1, uint32_t& lo_out, uint32_t& hi_out)
+{
+    uint32_t lo = 0, hi = 0;
+    for (int i = i0 + y; i < i1; i += ngroups) {
+        const uint32_t code = codes[i - i0];
         B200_UNROLL
         for (int j = 0; j < KS_T; j++) {
             const uint32_t g = (code >> (2 * (KS_T - 1 - j))) & 3u;

@@ -15,7 +15,7 @@ ctx.upload(ids[:N], a); ctx.upload(ids[N:2 * N], b)
 ops = np.full(N, OPS["NAND"], np.uint8)
 table = {}
 import itertools
-sel = os.environ.get('VARIANTS', '4:1,2:1,2:2,3:4,3:6')
+sel = os.environ.get('VARIANTS', '6:1,5:1,4:1,2:1,3:4,3:6')
 sizes = [int(x) for x in os.environ.get('SIZES', '1,74,148,296,444,592,888,1184,1776,2368').split(',')]
 for variant, g in (tuple(int(y) for y in x.split(':')) for x in sel.split(',')):
     ctx.set_kernel_variant(variant)

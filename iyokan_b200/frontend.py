@@ -1,0 +1,200 @@
+"""Front end: the cycle protocol of `iyokan plain` / `iyokan tfhe` over a flat netlist, with snapshot / resume.
+
+Mirrors TFHEppFrontend / PlainFrontend (src/iyokan_tfhepp.cpp:116-573, src/iyokan_plain.cpp:115-) for all-gate
+blueprints:
+  * request packet -> ROM contents at construction, RAM contents and `@`-port bit streams from the first cycle on
+    (setInitialRAM / setCircularInputs, iyokan_tfhepp.cpp:274-296): bit b of port p at cycle c =
+    stream[(width * c + b) mod size];
+  * optional reset pass (reset <- 1, one run), then per cycle: tick (every DFF / RAM cell Q <- D), reset <- 0 on
+    the first cycle, inputs, run; no tick after the last run (iyokan_tfhepp.cpp:486-561);
+  * result packet = OUTPUT ports + RAM cells as they are, numCycles = cycles executed so far (:176-227);
+  * `--snapshot` / `--resume` (iyokan_tfhepp.cpp:568-572,603-617): the reference serialises its whole Task graph
+    with cereal; here the state is the netlist plus one value (bit or TLWE) per node, the cycle counter and the
+    request streams, stored as one .npz.  A run of N cycles equals a run of k cycles, snapshot, resume for N - k.
+The two back-ends share every line of the protocol: `plain` evaluates bits on the host engine
+(b200net_plain_eval, the reference's plain back-end), `tfhe` evaluates ciphertexts on the GPU through the
+C ABI (b200net_run -> b200fhe_gate_batch).  Key material never enters this module.
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+
+from .lib import TLWE0_LEN
+from .netlist import DFF, INPUT, NetEngine, Netlist, trivial
+from .packet import PlainPacket, TFHEPacket
+
+SNAPSHOT_MAGIC = "iyokan_b200-snapshot-1"
+
+
+class FrontendError(ValueError):
+    pass
+
+
+class Frontend:
+    def __init__(self, nl: Netlist, mode: str, ctx=None):
+        if mode not in ("plain", "tfhe"):
+            raise FrontendError("mode must be 'plain' or 'tfhe'")
+        if mode == "tfhe" and ctx is None:
+            raise FrontendError("tfhe mode needs a b200fhe Context with keys loaded (there is no CPU fallback)")
+        self.nl, self.mode, self.ctx = nl, mode, ctx
+        self.eng = NetEngine(nl)
+        self.cycle = 0            # clock cycles executed so far
+        self.reset_done = False
+        self.streams: dict = {}   # port -> bits / TLWEs of the request packet
+        self.rams: dict = {}
+        self._all = np.arange(nl.n, dtype=np.uint32)
+        if mode == "plain":
+            self.v = np.zeros(nl.n, np.uint8)
+        else:
+            self.eng.bind(ctx, 1)
+            dffs = np.nonzero(nl.kind == DFF)[0]
+            if dffs.size:  # DFF initial value: trivial 0 (iyokan_tfhepp.hpp:23-27)
+                self.eng.set(dffs, np.tile(trivial(0), (dffs.size, 1)))
+
+    # ---- state access, uniform over the two back-ends ----
+    def _set(self, nodes, values):
+        keep = [i for i, n in enumerate(nodes) if n >= 0 and i < len(values)]
+        if not keep:
+            return
+        idx = np.array([nodes[i] for i in keep], np.uint32)
+        if self.mode == "plain":
+            self.v[idx] = np.asarray(values, np.uint8)[keep]
+        else:
+            self.eng.set(idx, np.ascontiguousarray(np.asarray(values, np.uint16)[keep]))
+
+    def _get(self, nodes):
+        nodes = np.asarray(nodes, np.int64)
+        idx = np.maximum(nodes, 0).astype(np.uint32)
+        out = self.v[idx].copy() if self.mode == "plain" else self.eng.get(idx)
+        out[nodes < 0] = 0 if self.mode == "plain" else trivial(0)  # port bits tied to ground (blueprint TOGND)
+        return out
+
+    def _const(self, bit):
+        return np.array([bit], np.uint8) if self.mode == "plain" else trivial(bit)[None]
+
+    def _eval(self):
+        if self.mode == "plain":
+            self.eng.plain_eval(self.v)
+        else:
+            self.eng.run()
+
+    def _tick(self):
+        if self.mode == "plain":
+            self.eng.plain_tick(self.v)
+        else:
+            self.eng.tick()
+
+    # ---- request ----
+    def load_request(self, req):
+        want = PlainPacket if self.mode == "plain" else TFHEPacket
+        if not isinstance(req, want):
+            raise FrontendError(f"{self.mode} mode takes a {want.__name__}")
+        bits = req.bits
+        rams = req.ram if self.mode == "plain" else req.ram_in_tlwe
+        roms = req.rom if self.mode == "plain" else req.rom_in_tlwe
+        if self.mode == "tfhe" and (req.ram or req.rom):
+            raise FrontendError("request carries CMUX-memory (TRLWE) contents: this back-end runs mux-rom / mux-ram blueprints")
+        for name in bits:
+            if name == "reset":
+                raise FrontendError("@reset cannot be set by the request (iyokan_tfhepp.cpp:284-285)")
+            if name not in self.nl.in_ports:
+                raise FrontendError(f"request drives unknown input port @{name}")
+        for name in list(rams) + list(roms):
+            if name not in self.nl.mem:
+                raise FrontendError(f"request initialises unknown memory {name!r}")
+        self.streams = {k: np.asarray(v) for k, v in bits.items()}
+        self.rams = {k: np.asarray(v) for k, v in rams.items() if self.nl.kind[self.nl.mem[k][0]] == DFF}
+        for name, v in roms.items():
+            self._set(self.nl.mem[name], np.asarray(v))
+        for name, v in rams.items():  # a "RAM" made of INPUT wires is a ROM in disguise
+            if name not in self.rams:
+                self._set(self.nl.mem[name], np.asarray(v))
+
+    # ---- protocol ----
+    def run(self, cycles: int, skip_reset: bool = False):
+        if cycles < 0:
+            raise FrontendError("number of cycles must be >= 0")
+        has_reset = "reset" in self.nl.in_ports
+        if self.cycle == 0 and not self.reset_done and has_reset and not skip_reset:
+            self._set(self.nl.in_ports["reset"], self._const(1))
+            self._eval()
+        self.reset_done = True
+        for _ in range(cycles):
+            c = self.cycle
+            self._tick()
+            if c == 0:
+                if has_reset:
+                    self._set(self.nl.in_ports["reset"], self._const(0))
+                for name, v in self.rams.items():
+                    self._set(self.nl.mem[name], v)
+            for port, stream in self.streams.items():
+                nodes = self.nl.in_ports[port]
+                w = len(nodes)
+                self._set(nodes, stream[[(w * c + b) % len(stream) for b in range(w)]])
+            self._eval()
+            self.cycle += 1
+        if self.mode == "tfhe":
+            self.ctx.sync()
+
+    def result(self):
+        """Result packet: OUTPUT ports, RAM cells (ROM is not returned), numCycles."""
+        out = {p: self._get(nodes) for p, nodes in self.nl.out_ports.items()}
+        ram = {m: self._get(nodes) for m, nodes in self.nl.mem.items() if self.nl.kind[nodes[0]] == DFF}
+        if self.mode == "plain":
+            return PlainPacket(ram=ram, bits=out, num_cycles=self.cycle)
+        return TFHEPacket(ram_in_tlwe=ram, bits=out, num_cycles=self.cycle)
+
+    # ---- snapshot / resume ----
+    def snapshot(self, path):
+        meta = {"magic": SNAPSHOT_MAGIC, "mode": self.mode, "cycle": self.cycle, "reset_done": self.reset_done,
+                "in_ports": self.nl.in_ports, "out_ports": self.nl.out_ports, "mem": self.nl.mem,
+                "streams": sorted(self.streams), "rams": sorted(self.rams)}
+        arrays = {"kind": self.nl.kind, "in0": self.nl.in0, "in1": self.nl.in1, "in2": self.nl.in2,
+                  "state": self.v if self.mode == "plain" else self.eng.get(self._all),
+                  "meta": np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)}
+        for k, v in self.streams.items():
+            arrays[f"stream__{k}"] = v
+        for k, v in self.rams.items():
+            arrays[f"ram__{k}"] = v
+        with open(path, "wb") as f:  # np.savez would append ".npz" to a bare path
+            np.savez_compressed(f, **arrays)
+
+    @staticmethod
+    def is_snapshot(path) -> bool:
+        try:
+            with np.load(path) as z:
+                return json.loads(bytes(z["meta"]).decode()).get("magic") == SNAPSHOT_MAGIC
+        except Exception:  # noqa: BLE001
+            return False
+
+    @staticmethod
+    def snapshot_mode(path) -> str:
+        with np.load(path) as z:
+            return json.loads(bytes(z["meta"]).decode())["mode"]
+
+    @staticmethod
+    def resume(path, ctx=None) -> "Frontend":
+        if not Frontend.is_snapshot(path):
+            raise FrontendError(f"Invalid resume file: {path}")
+        z = np.load(path)
+        meta = json.loads(bytes(z["meta"]).decode())
+        nl = Netlist(z["kind"], z["in0"], z["in1"], z["in2"], meta["in_ports"], meta["out_ports"], meta["mem"])
+        fe = Frontend(nl, meta["mode"], ctx)
+        fe.cycle, fe.reset_done = int(meta["cycle"]), bool(meta["reset_done"])
+        fe.streams = {k: z[f"stream__{k}"] for k in meta["streams"]}
+        fe.rams = {k: z[f"ram__{k}"] for k in meta["rams"]}
+        state = z["state"]
+        if fe.mode == "plain":
+            fe.v = state.astype(np.uint8).copy()
+        else:
+            if state.shape != (nl.n, TLWE0_LEN):
+                raise FrontendError("snapshot state has the wrong shape")
+            real = np.nonzero(nl.kind != 34)[0].astype(np.uint32)  # OUTPUT wires alias their drivers
+            fe.eng.set(real, np.ascontiguousarray(state[real]))
+        return fe
+
+
+__all__ = ["Frontend", "FrontendError", "INPUT"]

@@ -176,6 +176,45 @@ class PlainPacket:
         return w.bytes()
 
 
+    @staticmethod
+    def load(path) -> "PlainPacket":
+        return PlainPacket.loads(Path(path).read_bytes())
+
+    def save(self, path):
+        Path(path).write_bytes(self.dumps())
+
+    # TOML form of `iyokan-packet toml2packet / packet2toml` (src/iyokan-packet.cpp:253-326; test/in/*.in):
+    # cycles = N, [[bits]] / [[ram]] / [[rom]] entries with name, size (bits) and little-endian bytes
+    @staticmethod
+    def from_toml(text: str) -> "PlainPacket":
+        import tomllib
+
+        t = tomllib.loads(text)
+        p = PlainPacket(num_cycles=t.get("cycles"))
+        for kind, dst in (("bits", p.bits), ("ram", p.ram), ("rom", p.rom)):
+            for e in t.get(kind, []):
+                size, data = int(e["size"]), list(e["bytes"])
+                bits = np.zeros(size, np.uint8)
+                for i in range(min(size, 8 * len(data))):
+                    bits[i] = (int(data[i // 8]) >> (i % 8)) & 1
+                dst[e["name"]] = bits
+        return p
+
+    def to_toml(self) -> str:
+        lines = [] if self.num_cycles is None else [f"cycles = {self.num_cycles}", ""]
+        for kind, src in (("ram", self.ram), ("rom", self.rom), ("bits", self.bits)):
+            for name in sorted(src):
+                bits = np.asarray(src[name], np.uint8) & 1
+                data = [0] * ((bits.size + 7) // 8)
+                for i, b in enumerate(bits):
+                    data[i // 8] |= int(b) << (i % 8)
+                lines += [f"[[{kind}]]", f'name = "{name}"', f"size = {bits.size}", f"bytes = {data}", ""]
+        return "\n".join(lines)
+
+
+LWE_PARAMS_BYTES = 112  # serialised lweParams of the pinned TFHEpp (128-bit set): what precedes bklvl01 in an EvalKey
+
+
 def read_secret_key_lvl0(path) -> np.ndarray:
     """lvl0 secret key (636 x uint16, binary) from an `iyokan-packet genkey` file."""
     data = Path(path).read_bytes()
@@ -189,7 +228,7 @@ def secret_key_params_bytes(path) -> int:
     return Path(path).stat().st_size - 1 - SK_KEY_BYTES
 
 
-def read_eval_key(path, params_bytes: int):
+def read_eval_key(path, params_bytes: int = LWE_PARAMS_BYTES):
     """(bklvl01 raw uint32 [636][6][2][1024], iksklvl10 uint16 [1024][7][3][637]) from `iyokan-packet genevalkey`.
 
     Streams only the two members the gate path needs out of the ~2.2 GB file."""
@@ -199,7 +238,7 @@ def read_eval_key(path, params_bytes: int):
         if f.read(1) != b"\x01":
             raise PacketError("not a little-endian cereal PortableBinary archive")
         off = 1 + params_bytes
-        found = {}
+        found, seen = {}, []
         for name, nbytes in _EVALKEY_ORDER:
             f.seek(off)
             raw = f.read(4)
@@ -209,8 +248,10 @@ def read_eval_key(path, params_bytes: int):
             off += 4
             if pid == 0:
                 continue
-            if not pid & 0x80000000:
-                raise PacketError(f"unexpected shared_ptr back-reference for {name}")
+            if not pid & 0x80000000 or (pid & 0x7FFFFFFF) != len(seen) + 1:
+                raise PacketError(f"EvalKey layout not recognised at {name} (shared_ptr id {pid:#x}): "
+                                  "was the file written by `iyokan-packet genevalkey` of the pinned TFHEpp?")
+            seen.append(name)
             if off + nbytes > size:
                 raise PacketError(f"truncated EvalKey while reading {name}")
             if name in ("bklvl01", "iksklvl10"):

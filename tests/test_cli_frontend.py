@@ -1,0 +1,138 @@
+"""`python -m iyokan_b200 plain ...`: blueprint loader, cycle protocol, packets and snapshot/resume on the
+plaintext back-end (no GPU).  Hand-written fixtures run everywhere; the reference's own test.rb cases
+(test/config-toml + test/in -> test/out) run where the reference tree is mounted."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from iyokan_b200 import blueprint as B
+from iyokan_b200.cli import main
+from iyokan_b200.frontend import Frontend, FrontendError
+from iyokan_b200.packet import PlainPacket
+
+ROOT = Path(__file__).resolve().parents[1]
+FIX = ROOT / "tests" / "fixtures"
+REF = Path("/root/reference")
+
+
+def word(bits):
+    return sum(int(b) << i for i, b in enumerate(bits))
+
+
+def run_cli(*argv):
+    try:
+        return main([str(a) for a in argv])
+    except SystemExit as e:
+        return e.code
+
+
+def test_counter_blueprint_yosys_reader_and_protocol(tmp_path):
+    nl = B.read_blueprint(FIX / "counter-2bit.toml")
+    assert sorted(nl.in_ports) == ["reset"] and sorted(nl.out_ports) == ["one", "out"]
+    (tmp_path / "req.in").write_text("cycles = 3\n")
+    for cycles, want in ((1, 0), (2, 1), (3, 2), (6, 1)):
+        assert run_cli("plain", "--blueprint", FIX / "counter-2bit.toml", "-i", tmp_path / "req.in", "-o",
+                       tmp_path / "res", "-c", cycles, "--quiet") == 0
+        res = PlainPacket.load(tmp_path / "res")
+        assert res.num_cycles == cycles and word(res.bits["out"]) == want and word(res.bits["one"]) == 1
+    # cycles from the packet when -c is absent
+    assert run_cli("plain", "--blueprint", FIX / "counter-2bit.toml", "-i", tmp_path / "req.in", "-o", tmp_path / "res",
+                   "--quiet") == 0
+    assert word(PlainPacket.load(tmp_path / "res").bits["out"]) == 2
+
+
+def test_rom_ram_builtins_and_circular_inputs(tmp_path):
+    rom_words = [0x3, 0xC, 0x5, 0xA]
+    rom_bits = [(w >> b) & 1 for w in rom_words for b in range(4)]
+    req = PlainPacket(rom={"rom": np.array(rom_bits, np.uint8)}, ram={"ram": np.zeros(16, np.uint8)},
+                      bits={"raddr": np.array([1, 0, 0, 1, 1, 1], np.uint8),     # 1, 2, 3 (2 bits per cycle, LSB first)
+                            "waddr": np.array([0, 0, 1, 0, 0, 1], np.uint8),     # 0, 1, 2
+                            "wren": np.array([1, 1, 0], np.uint8)})              # third cycle does not write
+    req.save(tmp_path / "req")
+    assert run_cli("plain", "--blueprint", FIX / "lookup.toml", "-i", tmp_path / "req", "-o", tmp_path / "res", "-c", 4,
+                   "--quiet") == 0
+    res = PlainPacket.load(tmp_path / "res")
+    ram = [word(res.ram["ram"][4 * a: 4 * a + 4]) for a in range(4)]
+    # cycle 3 wraps around to the first stream entries: raddr 1, waddr 0, wren 1 again (written at the next tick,
+    # which never comes: the result shows the RAM as the last tick left it)
+    assert ram == [rom_words[1], rom_words[2], 0, 0]
+    assert word(res.bits["rdata"]) == ram[0]
+    assert "rom" not in res.ram and res.num_cycles == 4
+    # packet <-> TOML round trip (iyokan-packet packet2toml / toml2packet)
+    assert run_cli("packet", "packet2toml", "--in", tmp_path / "res", "--out", tmp_path / "res.toml") == 0
+    assert run_cli("packet", "toml2packet", "--in", tmp_path / "res.toml", "--out", tmp_path / "res2") == 0
+    assert (tmp_path / "res2").read_bytes() == (tmp_path / "res").read_bytes()
+
+
+def test_snapshot_resume_equals_one_run(tmp_path):
+    bp, req = FIX / "counter-2bit.toml", tmp_path / "req.in"
+    req.write_text("cycles = 1\n")
+    assert run_cli("plain", "--blueprint", bp, "-i", req, "-o", tmp_path / "a", "-c", 5, "--quiet") == 0
+    assert run_cli("plain", "--blueprint", bp, "-i", req, "-o", tmp_path / "b1", "-c", 2, "--snapshot", tmp_path / "snap",
+                   "--quiet") == 0
+    assert Frontend.is_snapshot(tmp_path / "snap")
+    assert run_cli("plain", "--resume", tmp_path / "snap", "-o", tmp_path / "b2", "-c", 3, "--quiet") == 0
+    assert (tmp_path / "a").read_bytes() == (tmp_path / "b2").read_bytes()
+    assert PlainPacket.load(tmp_path / "b2").num_cycles == 5
+    # a snapshot of the other mode, or a file that is no snapshot, is refused like the reference does
+    assert run_cli("tfhe", "--evalkey", tmp_path / "nokey", "--resume", tmp_path / "snap", "-o", tmp_path / "x", "-c", 1) == 1
+    assert run_cli("plain", "--resume", req, "-o", tmp_path / "x", "-c", 1) == 1
+
+
+def test_error_behaviour(tmp_path):
+    bp = FIX / "counter-2bit.toml"
+    (tmp_path / "bad.in").write_text('[[bits]]\nname = "nosuchport"\nsize = 1\nbytes = [1]\n')
+    assert run_cli("plain", "--blueprint", bp, "-i", tmp_path / "bad.in", "-o", tmp_path / "r", "-c", 1) == 1
+    (tmp_path / "rst.in").write_text('[[bits]]\nname = "reset"\nsize = 1\nbytes = [1]\n')
+    assert run_cli("plain", "--blueprint", bp, "-i", tmp_path / "rst.in", "-o", tmp_path / "r", "-c", 1) == 1
+    (tmp_path / "none.in").write_text("")
+    assert run_cli("plain", "--blueprint", bp, "-i", tmp_path / "none.in", "-o", tmp_path / "r") == 1   # no cycle count
+    (tmp_path / "cmux.toml").write_text('[[builtin]]\ntype = "ram"\nname = "ram"\nin_addr_width = 8\n'
+                                        'in_wdata_width = 8\nout_rdata_width = 8\n')
+    assert run_cli("plain", "--blueprint", tmp_path / "cmux.toml", "-i", tmp_path / "none.in", "-o", tmp_path / "r",
+                   "-c", 1) == 1
+    with pytest.raises(FrontendError):
+        Frontend(B.read_blueprint(bp), "tfhe", None)   # encrypted mode never falls back to the CPU
+
+
+def test_module_entry_point(tmp_path):
+    (tmp_path / "req.in").write_text("cycles = 2\n")
+    r = subprocess.run([sys.executable, "-m", "iyokan_b200", "plain", "--blueprint", str(FIX / "counter-2bit.toml"), "-i",
+                        str(tmp_path / "req.in"), "-o", str(tmp_path / "res"), "--stdout-csv"], cwd=ROOT,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "2,out,1" in r.stdout and "done." in r.stderr
+
+
+# ---- the reference's own end-to-end cases (test.rb:384-548), all-gate blueprints, plain mode ----
+TEST_RB = [  # (blueprint, request, golden result, cycles)
+    ("cahp-diamond-mux", "test00.in", "test00-diamond.out", 8), ("cahp-emerald-mux", "test00.in", "test00-emerald.out", 6),
+    ("cahp-ruby-mux", "test09.in", "test09-ruby.out", 7), ("cahp-pearl-mux", "test09.in", "test09-pearl.out", 3),
+    ("cahp-diamond-mux", "test01.in", "test01-diamond.out", 346), ("cahp-emerald-mux", "test01.in", "test01-emerald.out", 261),
+    ("cahp-ruby-mux", "test10.in", "test10-ruby.out", 362), ("cahp-pearl-mux", "test10.in", "test10-pearl.out", 264),
+    ("cahp-ruby-mux-1KiB", "test11.in", "test11.out", 7), ("const-4bit", "test22.in", "test22.out", 1),
+    ("addr-4bit", "test04.in", "test04.out", 1), ("pass-addr-pass-4bit", "test04.in", "test04.out", 1),
+    ("addr-register-4bit", "test16.in", "test16.out", 3), ("div-8bit", "test05.in", "test05.out", 1),
+    ("mux-ram-addr8bit", "test06.in", "test06.out", 16), ("mux-ram-addr9bit", "test07.in", "test07.out", 16),
+    ("mux-ram-8-16-16", "test08.in", "test08.out", 8), ("counter-4bit", "test13.in", "test13.out", 3),
+    ("big-mult", "test21.in", "test21.out", 1),
+]
+
+
+@pytest.mark.skipif(not (REF / "test" / "config-toml").exists(), reason="reference tree not mounted")
+@pytest.mark.parametrize("bp,fin,fout,cycles", TEST_RB, ids=[f"{c[0]}-{c[1][4:6]}" for c in TEST_RB])
+def test_reference_test_rb_cases_plain(tmp_path, bp, fin, fout, cycles):
+    assert run_cli("plain", "--blueprint", REF / "test" / "config-toml" / f"{bp}.toml", "-i", REF / "test" / "in" / fin,
+                   "-o", tmp_path / "res", "-c", cycles, "--quiet") == 0
+    got = PlainPacket.load(tmp_path / "res")
+    want = PlainPacket.from_toml((REF / "test" / "out" / fout).read_text())
+    assert got.num_cycles == want.num_cycles == cycles
+    assert sorted(got.bits) == sorted(want.bits)
+    for name, bits in want.bits.items():
+        assert np.array_equal(got.bits[name][:bits.size], bits), name
+    for name, bits in want.ram.items():
+        assert np.array_equal(got.ram[name][:bits.size], bits), name

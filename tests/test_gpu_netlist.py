@@ -155,3 +155,46 @@ def test_drop_in_with_the_reference_packet_tools(tmp_path):
             assert plain.num_cycles == case["cycles"]
             for port, e in case["expected"]["bits"].items():
                 assert N.bytes_of(plain.bits[port][:e["size"]]) == e["bytes"], (name, port)
+
+
+@pytest.mark.skipif(not O.have_iyokan_packet(), reason="oracle/_ref/iyokan-packet not built")
+def test_cli_tfhe_end_to_end_with_reference_tools_and_resume(tmp_path):
+    """`python -m iyokan_b200 tfhe` in place of `iyokan tfhe` (test.rb:287-315): blueprint -> netlist, EvalKey and
+    encrypted request written by the reference's iyokan-packet, result decrypted by it; equals the plain run.
+    Then snapshot after 2 cycles + resume for 2 more == one 4-cycle run, byte for byte."""
+    from iyokan_b200.cli import main
+    from iyokan_b200.packet import PlainPacket
+
+    fix = Path(__file__).resolve().parent / "fixtures"
+    sk, ek = tmp_path / "sk", tmp_path / "ek"
+    O.iyokan_packet("genkey", "--type", "tfhepp", "--out", sk)
+    O.iyokan_packet("genevalkey", "--in", sk, "--out", ek)
+    rom_words = [0x3, 0xC, 0x5, 0xA]
+    req = PlainPacket(rom={"rom": np.array([(w >> b) & 1 for w in rom_words for b in range(4)], np.uint8)},
+                      ram={"ram": np.zeros(16, np.uint8)},
+                      bits={"raddr": np.array([1, 0, 0, 1, 1, 1], np.uint8), "waddr": np.array([0, 0, 1, 0, 0, 1], np.uint8),
+                            "wren": np.array([1, 1, 0], np.uint8)})
+    (tmp_path / "req.toml").write_text(req.to_toml())
+    O.iyokan_packet("toml2packet", "--in", tmp_path / "req.toml", "--out", tmp_path / "req")
+    O.iyokan_packet("enc", "--key", sk, "--in", tmp_path / "req", "--out", tmp_path / "req.enc")
+
+    def cli(*argv):
+        try:
+            return main([str(a) for a in argv])
+        except SystemExit as e:
+            return e.code
+
+    bp = fix / "lookup.toml"
+    assert cli("tfhe", "--blueprint", bp, "--evalkey", ek, "-i", tmp_path / "req.enc", "-o", tmp_path / "res.enc", "-c", 4,
+               "--quiet") == 0
+    O.iyokan_packet("dec", "--key", sk, "--in", tmp_path / "res.enc", "--out", tmp_path / "res")
+    assert cli("plain", "--blueprint", bp, "-i", tmp_path / "req", "-o", tmp_path / "res.plain", "-c", 4, "--quiet") == 0
+    got, want = PlainPacket.load(tmp_path / "res"), PlainPacket.load(tmp_path / "res.plain")
+    assert got.num_cycles == want.num_cycles == 4
+    assert np.array_equal(got.bits["rdata"], want.bits["rdata"]) and np.array_equal(got.ram["ram"], want.ram["ram"])
+    # snapshot / resume on the encrypted back-end
+    assert cli("tfhe", "--blueprint", bp, "--evalkey", ek, "-i", tmp_path / "req.enc", "-o", tmp_path / "half.enc", "-c", 2,
+               "--snapshot", tmp_path / "snap", "--quiet") == 0
+    assert cli("tfhe", "--evalkey", ek, "--resume", tmp_path / "snap", "-o", tmp_path / "resumed.enc", "-c", 2, "--quiet") == 0
+    assert (tmp_path / "resumed.enc").read_bytes() == (tmp_path / "res.enc").read_bytes()
+    ek.unlink()

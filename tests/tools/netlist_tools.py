@@ -1,185 +1,9 @@
-"""Readers for the REFERENCE's netlist formats (test tooling; runs where /root/reference exists).
-
-Converts Yosys JSON (reader semantics: src/iyokan.hpp:2130-2351), IyokanL1 JSON (:2354-2482) and TOML
-blueprints ([[file]], [[builtin]], [connect]; :1731-1895) into iyokan_b200.netlist.Netlist, i.e. performs
-in Python what Iyokan's front end does before the DAG reaches the scheduler.  The results are stored as
-derived fixtures under tests/golden/netlists/ by tests/golden/make_netlists.py.
-"""
-from __future__ import annotations
-
-import json
-import re
-import tomllib
-from pathlib import Path
-
-from iyokan_b200.netlist import NetBuilder, mux_rom
-
-YOSYS_GATES = {"$_AND_": "AND", "$_NAND_": "NAND", "$_ANDNOT_": "ANDNOT", "$_OR_": "OR", "$_NOR_": "NOR",
-               "$_ORNOT_": "ORNOT", "$_XOR_": "XOR", "$_XNOR_": "XNOR"}
-
-
-class SubNet:
-    """Ports of one sub-network inside the shared builder: name -> node id per bit."""
-
-    def __init__(self):
-        self.inputs: dict[str, dict[int, int]] = {}
-        self.outputs: dict[str, dict[int, int]] = {}
-
-
-def read_yosys(b: NetBuilder, path) -> SubNet:
-    mod = next(iter(json.load(open(path))["modules"].values()))
-    sn = SubNet()
-    driver: dict[int, int] = {}
-    for pname, port in mod["ports"].items():
-        if port["direction"] != "input" or pname == "clock":
-            continue
-        for i, bit in enumerate(port["bits"]):
-            n = b._add(32)  # INPUT
-            sn.inputs.setdefault(pname, {})[i] = n
-            driver[bit] = n
-    cells = list(mod["cells"].values())
-    ids = []
-    for c in cells:
-        t, con = c["type"], c["connections"]
-        if t in YOSYS_GATES:
-            n = b.gate(YOSYS_GATES[t], -1, -1)
-        elif t == "$_NOT_":
-            n = b.gate("NOT", -1)
-        elif t == "$_MUX_":
-            n = b.gate("MUX", -1, -1, -1)
-        elif t == "$_DFF_P_":
-            n = b.dff(-1)
-        else:
-            raise ValueError(f"unsupported cell type {t}")
-        ids.append(n)
-        driver[con["Q" if t == "$_DFF_P_" else "Y"][0]] = n
-    const = {}
-
-    def src(bit):
-        if isinstance(bit, str):  # constant driver "0" / "1" (iyokan.hpp:2170-2193)
-            if bit not in const:
-                const[bit] = b.gate("CONST1" if bit == "1" else "CONST0")
-            return const[bit]
-        return driver[bit]
-
-    for c, n in zip(cells, ids):
-        t, con = c["type"], c["connections"]
-        if t == "$_DFF_P_":
-            b.ins[n] = [src(con["D"][0]), -1, -1]
-        elif t == "$_NOT_":
-            b.ins[n] = [src(con["A"][0]), -1, -1]
-        elif t == "$_MUX_":
-            b.ins[n] = [src(con["A"][0]), src(con["B"][0]), src(con["S"][0])]
-        else:
-            b.ins[n] = [src(con["A"][0]), src(con["B"][0]), -1]
-    for pname, port in mod["ports"].items():
-        if port["direction"] != "output":
-            continue
-        for i, bit in enumerate(port["bits"]):
-            sn.outputs.setdefault(pname, {})[i] = b._add(34, src(bit))  # OUTPUT wire
-    return sn
-
-
-def read_iyokanl1(b: NetBuilder, path, mem_name="ram", width=None) -> SubNet:
-    obj = json.load(open(path))
-    sn = SubNet()
-    node = {}
-    for p in obj["ports"]:
-        if p["type"] == "input":
-            node[p["id"]] = b._add(32)
-            sn.inputs.setdefault(p["portName"], {})[p["portBit"]] = node[p["id"]]
-    kinds = {"DFFP": None, "RAM": None}
-    for c in obj["cells"]:
-        t = c["type"]
-        if t in ("DFFP", "RAM"):
-            n = b.dff(-1)
-            if t == "RAM":
-                lst = b.mem.setdefault(mem_name, [])
-                idx = c["ramAddress"] * width + c["ramBit"]
-                lst.extend([-1] * (idx + 1 - len(lst)))
-                lst[idx] = n
-        elif t == "MUX":
-            n = b.gate("MUX", -1, -1, -1)
-        elif t == "NOT":
-            n = b.gate("NOT", -1)
-        else:
-            n = b.gate(t, -1, -1)
-        node[c["id"]] = n
-    del kinds
-    for c in obj["cells"]:
-        t, i, n = c["type"], c["input"], node[c["id"]]
-        if t in ("DFFP", "RAM"):
-            b.ins[n] = [node[i["D"]], -1, -1]
-        elif t == "NOT":
-            b.ins[n] = [node[i["A"]], -1, -1]
-        elif t == "MUX":
-            b.ins[n] = [node[i["A"]], node[i["B"]], node[i["S"]]]
-        else:
-            b.ins[n] = [node[i["A"]], node[i["B"]], -1]
-    for p in obj["ports"]:
-        if p["type"] == "output":
-            sn.outputs.setdefault(p["portName"], {})[p["portBit"]] = b._add(34, node[p["bits"][0]])
-    return sn
-
-
-PORT_RE = re.compile(r"^(@?)([^/\[\]]+)(?:/([^\[\]]+))?(?:\[(\d+)(?::(\d+))?\])?$")
-
-
-def parse_ref(s):
-    m = PORT_RE.match(s.strip())
-    ext, a, bname, lo, hi = m.groups()
-    lo = int(lo) if lo is not None else 0
-    hi = int(hi) if hi is not None else lo
-    if ext:
-        return ("@", a, list(range(lo, hi + 1)))
-    return (a, bname, list(range(lo, hi + 1)))
+"""Fixture tooling: the blueprint loader lives in the product (iyokan_b200/blueprint.py); here it is pointed at the
+REFERENCE's pre-synthesised mux-ram netlists so that derived fixtures have the reference's exact gate counts
+(runs where /root/reference exists; see tests/golden/make_netlists.py)."""
+from iyokan_b200.blueprint import *  # noqa: F401,F403
+from iyokan_b200 import blueprint as _bp
 
 
 def read_blueprint(toml_path, reference_src="/root/reference/src"):
-    """Flatten a blueprint into one Netlist (what TFHEppFrontend's constructor does, iyokan_tfhepp.cpp:312-458)."""
-    toml_path = Path(toml_path)
-    bp = tomllib.load(open(toml_path, "rb"))
-    b = NetBuilder()
-    subs: dict[str, SubNet] = {}
-    for f in bp.get("file", []):
-        path = (toml_path.parent / f["path"]).resolve()
-        if f["type"] == "yosys-json":
-            subs[f["name"]] = read_yosys(b, path)
-        elif f["type"] == "iyokanl1-json":
-            subs[f["name"]] = read_iyokanl1(b, path)
-        else:
-            raise ValueError(f["type"])
-    for bi in bp.get("builtin", []):
-        name = bi["name"]
-        sn = SubNet()
-        if bi["type"] == "mux-rom":
-            addr = [b._add(32) for _ in range(bi["in_addr_width"])]
-            sn.inputs["addr"] = dict(enumerate(addr))
-            outs = mux_rom(b, addr, bi["out_rdata_width"], name=name)
-            sn.outputs["rdata"] = {i: b._add(34, o) for i, o in enumerate(outs)}
-        elif bi["type"] == "mux-ram":
-            a, w, r = bi["in_addr_width"], bi["in_wdata_width"], bi["out_rdata_width"]
-            assert w == r
-            sn = read_iyokanl1(b, Path(reference_src) / f"mux-ram-{a}-{w}-{r}.min.json", mem_name=name, width=w)
-        else:
-            raise ValueError(f"builtin {bi['type']} (CMUX memory) is out of scope")
-        subs[name] = sn
-    for dst, src in bp.get("connect", {}).items():
-        d, s = parse_ref(dst), parse_ref(src)
-        assert len(d[2]) == len(s[2]), (dst, src)
-        for db, sb in zip(d[2], s[2]):
-            if d[0] == "@":      # external output  "@out[i]" = "net/port[j]"
-                lst = b.out_ports.setdefault(d[1], [])
-                lst.extend([-1] * (db + 1 - len(lst)))
-                lst[db] = subs[s[0]].outputs[s[1]][sb]
-            elif s[0] == "@":    # external input   "net/port[i]" = "@in[j]"
-                lst = b.in_ports.setdefault(s[1], [])
-                lst.extend([-1] * (sb + 1 - len(lst)))
-                node = subs[d[0]].inputs[d[1]][db]
-                if lst[sb] == -1:
-                    lst[sb] = node
-                else:            # one external bit feeding several inputs: alias the later ones
-                    b.alias(node, lst[sb])
-            else:                # internal edge: the consumer's INPUT wire becomes an alias of the producer
-                b.alias(subs[d[0]].inputs[d[1]][db], subs[s[0]].outputs[s[1]][sb])
-    return b.build()
+    return _bp.read_blueprint(toml_path, mux_ram_json_dir=reference_src)

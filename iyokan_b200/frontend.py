@@ -95,8 +95,12 @@ class Frontend:
         bits = req.bits
         rams = req.ram if self.mode == "plain" else req.ram_in_tlwe
         roms = req.rom if self.mode == "plain" else req.rom_in_tlwe
-        if self.mode == "tfhe" and (req.ram or req.rom):
-            raise FrontendError("request carries CMUX-memory (TRLWE) contents: this back-end runs mux-rom / mux-ram blueprints")
+        if self.mode == "tfhe":
+            # `iyokan-packet enc` writes every memory twice: as TRLWEs (for CMUX memories) and as TLWEs (for MUX
+            # memories, src/packet.hpp:208-220); this back-end runs mux-rom / mux-ram blueprints and uses the latter
+            for name in list(req.ram) + list(req.rom):
+                if name in self.nl.mem and name not in rams and name not in roms:
+                    raise FrontendError(f"memory {name!r} is given only in CMUX (TRLWE) form")
         for name in bits:
             if name == "reset":
                 raise FrontendError("@reset cannot be set by the request (iyokan_tfhepp.cpp:284-285)")
@@ -193,7 +197,7 @@ class Frontend:
             if state.shape != (nl.n, TLWE0_LEN):
                 raise FrontendError("snapshot state has the wrong shape")
             real = np.nonzero(nl.kind != 34)[0].astype(np.uint32)  # OUTPUT wires alias their drivers
-            fe.eng.set(real, np.ascontiguousarray(state[real]))
+            fe.eng.restore(real, np.ascontiguousarray(state[real]))
         return fe
 
 

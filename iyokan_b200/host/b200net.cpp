@@ -268,6 +268,19 @@ int b200net_set(b200net* net, const uint32_t* nodes, const uint16_t* tlwe, size_
     return 0;
 }
 
+int b200net_restore(b200net* net, const uint32_t* nodes, const uint16_t* tlwe, size_t n)
+{
+    if (!net || !net->ctx) return fail("netlist is not bound to a context");
+    std::vector<uint32_t> s(n);
+    for (size_t i = 0; i < n; i++) {
+        if (nodes[i] >= net->n) return fail("node out of range");
+        if (net->kind[nodes[i]] == B200NET_OUTPUT) return fail("OUTPUT wires alias their driver and hold no state");
+        s[i] = net->slot[nodes[i]];
+    }
+    if (b200fhe_upload(net->ctx, s.data(), tlwe, n) || b200fhe_sync(net->ctx)) return fail(b200fhe_last_error());
+    return 0;
+}
+
 int b200net_get(b200net* net, const uint32_t* nodes, uint16_t* tlwe, size_t n)
 {
     if (!net || !net->ctx) return fail("netlist is not bound to a context");

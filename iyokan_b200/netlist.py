@@ -200,7 +200,7 @@ def load_net():
             "b200net_slot_of": (ctypes.c_uint32, [vp, sz]), "b200net_num_slots": (sz, [vp]),
             "b200net_level_slot_base": (ctypes.c_uint32, [vp, sz]),
             "b200net_plain_eval": (ci, [vp, vp]), "b200net_plain_tick": (ci, [vp, vp]),
-            "b200net_layout": (ci, [vp, ci]), "b200net_bind": (ci, [vp, vp, ci]), "b200net_set": (ci, [vp, vp, vp, sz]),
+            "b200net_layout": (ci, [vp, ci]), "b200net_bind": (ci, [vp, vp, ci]), "b200net_set": (ci, [vp, vp, vp, sz]), "b200net_restore": (ci, [vp, vp, vp, sz]),
             "b200net_get": (ci, [vp, vp, vp, sz]), "b200net_tick": (ci, [vp]), "b200net_run": (ci, [vp]),
             "b200net_run_level_shard": (ci, [vp, sz, ci, ci]),
         }
@@ -215,7 +215,7 @@ NET_EXPORTS = [
     "b200net_create", "b200net_destroy", "b200net_last_error", "b200net_num_nodes", "b200net_num_levels",
     "b200net_level_width", "b200net_level_bootstraps", "b200net_bootstraps_per_cycle", "b200net_num_dff", "b200net_node_level",
     "b200net_slot_of", "b200net_num_slots", "b200net_level_slot_base", "b200net_plain_eval", "b200net_plain_tick",
-    "b200net_layout", "b200net_bind", "b200net_set", "b200net_get", "b200net_tick", "b200net_run", "b200net_run_level_shard",
+    "b200net_layout", "b200net_bind", "b200net_set", "b200net_restore", "b200net_get", "b200net_tick", "b200net_run", "b200net_run_level_shard",
 ]
 
 
@@ -299,6 +299,12 @@ class NetEngine:
         tlwe = np.ascontiguousarray(tlwe, np.uint16)
         assert tlwe.size == nodes.size * TLWE0_LEN
         self._ck(self.lib.b200net_set(self._h, _p(nodes), _p(tlwe), nodes.size))
+
+    def restore(self, nodes, tlwe):
+        nodes = np.ascontiguousarray(nodes, np.uint32)
+        tlwe = np.ascontiguousarray(tlwe, np.uint16)
+        assert tlwe.size == nodes.size * TLWE0_LEN
+        self._ck(self.lib.b200net_restore(self._h, _p(nodes), _p(tlwe), nodes.size))
 
     def get(self, nodes) -> np.ndarray:
         nodes = np.ascontiguousarray(nodes, np.uint32)

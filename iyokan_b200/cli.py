@@ -5,6 +5,7 @@ for all-gate blueprints, on the plaintext host engine and on the B200 back-end.
     python -m iyokan_b200 tfhe  --blueprint B.toml --evalkey EK -i req.enc -o res.enc -c N [--snapshot S]
     python -m iyokan_b200 plain|tfhe --resume S -c N -o res            (tfhe also needs --evalkey)
     python -m iyokan_b200 packet toml2packet|packet2toml --in X --out Y (plain packets, as iyokan-packet does)
+    python -m torch.distributed.run --nproc-per-node N -m iyokan_b200 tfhe ...   (N GPUs of one box, NCCL)
 
 Same option names as the reference; options that only tune its CPU scheduler (--cpu, --sched, --gpu, --num-gpu,
 --show-combinational-progress, --dump-*) are accepted and ignored.  Requests may be given as binary packets
@@ -58,8 +59,29 @@ def _common(sp):
         sp.add_argument(ignored, action="store_true", help=argparse.SUPPRESS)
 
 
+def _init_distributed(mode):
+    """One process per GPU under torchrun (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the environment)."""
+    import os
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        return 0, 0, 1
+    import torch
+    import torch.distributed as dist
+
+    rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if mode == "tfhe":
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo")
+    return rank, local, world
+
+
 def _run(args, mode):
-    log = (lambda *a: None) if args.quiet else (lambda *a: print("[info]", *a, file=sys.stderr))
+    rank, local, world = _init_distributed(mode)
+    log = (lambda *a: None) if args.quiet or rank else (lambda *a: print("[info]", *a, file=sys.stderr))
     if bool(args.blueprint) == bool(args.resume):
         die("exactly one of --blueprint (a new run) and --resume (from a snapshot) is required")
     if not args.output:
@@ -71,7 +93,7 @@ def _run(args, mode):
         from .lib import B200FheError, Context
 
         try:
-            ctx = Context(args.gpu_index)
+            ctx = Context(local if world > 1 else args.gpu_index)
             bk, ksk = read_eval_key(args.evalkey)
             ctx.load_keys(bk, ksk)
         except (B200FheError, PacketError, OSError) as e:
@@ -80,7 +102,7 @@ def _run(args, mode):
         if args.resume:
             if not Frontend.is_snapshot(args.resume) or Frontend.snapshot_mode(args.resume) != mode:
                 die("Invalid resume file:", args.resume)
-            fe = Frontend.resume(args.resume, ctx)
+            fe = Frontend.resume(args.resume, ctx, rank, world)
             cycles = args.cycles
             if cycles is None:
                 die("-c is required with --resume")
@@ -88,27 +110,34 @@ def _run(args, mode):
             if not args.input:
                 die("-i/--in is required")
             nl = read_blueprint(args.blueprint)
-            fe = Frontend(nl, mode, ctx)
+            fe = Frontend(nl, mode, ctx, rank, world)
             req = _load_plain_request(args.input) if mode == "plain" else TFHEPacket.load(args.input)
             fe.load_request(req)
             cycles = args.cycles if args.cycles is not None else req.num_cycles
             if cycles is None or cycles < 0:
                 die("the number of cycles is given neither by -c nor by the request packet")
-        log(f"{mode}: {fe.nl.n} nodes, {fe.eng.num_levels} levels, {fe.eng.bootstraps_per_cycle} bootstraps/cycle, "
+        log(f"{mode} on {world} process(es): {fe.nl.n} nodes, {fe.eng.num_levels} levels, {fe.eng.bootstraps_per_cycle} bootstraps/cycle, "
             f"{fe.eng.num_dff} DFF; running {cycles} cycle(s) from cycle {fe.cycle}")
         t0 = time.time()
         fe.run(cycles, skip_reset=args.skip_reset)
         log(f"done. ({int((time.time() - t0) * 1e6)} us)")
         res = fe.result()
-        res.save(args.output)
-        if args.snapshot:
-            fe.snapshot(args.snapshot)
-        if args.stdout_csv and mode == "plain":
+        if rank == 0:
+            res.save(args.output)
+            if args.snapshot:
+                fe.snapshot(args.snapshot)
+        if rank == 0 and args.stdout_csv and mode == "plain":
             for name in sorted(res.bits):
                 print(f"{fe.cycle},{name},{sum(int(b) << i for i, b in enumerate(res.bits[name]))}")
     except (FrontendError, PacketError, ValueError, OSError) as e:
         die(e)
     finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            if dist.is_initialized():
+                dist.barrier()
+                dist.destroy_process_group()
         if ctx is not None:
             ctx.close()
     return 0

@@ -34,22 +34,33 @@ class FrontendError(ValueError):
 
 
 class Frontend:
-    def __init__(self, nl: Netlist, mode: str, ctx=None):
+    def __init__(self, nl: Netlist, mode: str, ctx=None, rank: int = 0, world: int = 1, group=None):
+        """rank / world / group: one process per GPU under torch.distributed (`torchrun -m iyokan_b200 tfhe ...`):
+        every rank holds the whole state, each dependency level is split between the ranks when that pays and its
+        outputs are all-gathered (iyokan_b200/shard.py); rank 0 writes the result."""
         if mode not in ("plain", "tfhe"):
             raise FrontendError("mode must be 'plain' or 'tfhe'")
         if mode == "tfhe" and ctx is None:
             raise FrontendError("tfhe mode needs a b200fhe Context with keys loaded (there is no CPU fallback)")
         self.nl, self.mode, self.ctx = nl, mode, ctx
+        self.rank, self.world = rank, world
         self.eng = NetEngine(nl)
         self.cycle = 0            # clock cycles executed so far
         self.reset_done = False
         self.streams: dict = {}   # port -> bits / TLWEs of the request packet
         self.rams: dict = {}
         self._all = np.arange(nl.n, dtype=np.uint32)
-        if mode == "plain":
+        self.be = self.runner = None
+        if world > 1:
+            from .shard import GpuBackend, PlainBackend, ShardedRunner
+
+            self.be = PlainBackend(nl, self.eng, world) if mode == "plain" else GpuBackend(nl, self.eng, ctx, world)
+            self.runner = ShardedRunner(nl, self.eng, self.be, rank, world, group=group, min_shard_width=None)
+        elif mode == "plain":
             self.v = np.zeros(nl.n, np.uint8)
         else:
             self.eng.bind(ctx, 1)
+        if mode == "tfhe":
             dffs = np.nonzero(nl.kind == DFF)[0]
             if dffs.size:  # DFF initial value: trivial 0 (iyokan_tfhepp.hpp:23-27)
                 self.eng.set(dffs, np.tile(trivial(0), (dffs.size, 1)))
@@ -61,14 +72,21 @@ class Frontend:
             return
         idx = np.array([nodes[i] for i in keep], np.uint32)
         if self.mode == "plain":
-            self.v[idx] = np.asarray(values, np.uint8)[keep]
+            vals = np.asarray(values, np.uint8)[keep]
+            if self.be is not None:
+                self.be.set_nodes(idx, vals)
+            else:
+                self.v[idx] = vals
         else:
             self.eng.set(idx, np.ascontiguousarray(np.asarray(values, np.uint16)[keep]))
 
     def _get(self, nodes):
         nodes = np.asarray(nodes, np.int64)
         idx = np.maximum(nodes, 0).astype(np.uint32)
-        out = self.v[idx].copy() if self.mode == "plain" else self.eng.get(idx)
+        if self.mode == "plain":
+            out = self.be.get_nodes(idx) if self.be is not None else self.v[idx].copy()
+        else:
+            out = self.eng.get(idx)
         out[nodes < 0] = 0 if self.mode == "plain" else trivial(0)  # port bits tied to ground (blueprint TOGND)
         return out
 
@@ -76,13 +94,17 @@ class Frontend:
         return np.array([bit], np.uint8) if self.mode == "plain" else trivial(bit)[None]
 
     def _eval(self):
-        if self.mode == "plain":
+        if self.runner is not None:
+            self.runner.run()
+        elif self.mode == "plain":
             self.eng.plain_eval(self.v)
         else:
             self.eng.run()
 
     def _tick(self):
-        if self.mode == "plain":
+        if self.runner is not None:
+            self.runner.tick()
+        elif self.mode == "plain":
             self.eng.plain_tick(self.v)
         else:
             self.eng.tick()
@@ -157,7 +179,7 @@ class Frontend:
                 "in_ports": self.nl.in_ports, "out_ports": self.nl.out_ports, "mem": self.nl.mem,
                 "streams": sorted(self.streams), "rams": sorted(self.rams)}
         arrays = {"kind": self.nl.kind, "in0": self.nl.in0, "in1": self.nl.in1, "in2": self.nl.in2,
-                  "state": self.v if self.mode == "plain" else self.eng.get(self._all),
+                  "state": self._get(self._all),
                   "meta": np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)}
         for k, v in self.streams.items():
             arrays[f"stream__{k}"] = v
@@ -180,23 +202,26 @@ class Frontend:
             return json.loads(bytes(z["meta"]).decode())["mode"]
 
     @staticmethod
-    def resume(path, ctx=None) -> "Frontend":
+    def resume(path, ctx=None, rank: int = 0, world: int = 1, group=None) -> "Frontend":
         if not Frontend.is_snapshot(path):
             raise FrontendError(f"Invalid resume file: {path}")
         z = np.load(path)
         meta = json.loads(bytes(z["meta"]).decode())
         nl = Netlist(z["kind"], z["in0"], z["in1"], z["in2"], meta["in_ports"], meta["out_ports"], meta["mem"])
-        fe = Frontend(nl, meta["mode"], ctx)
+        fe = Frontend(nl, meta["mode"], ctx, rank, world, group)
         fe.cycle, fe.reset_done = int(meta["cycle"]), bool(meta["reset_done"])
         fe.streams = {k: z[f"stream__{k}"] for k in meta["streams"]}
         fe.rams = {k: z[f"ram__{k}"] for k in meta["rams"]}
         state = z["state"]
+        real = np.nonzero(nl.kind != 34)[0].astype(np.uint32)  # OUTPUT wires alias their drivers
         if fe.mode == "plain":
-            fe.v = state.astype(np.uint8).copy()
+            if fe.be is not None:
+                fe.be.set_nodes(real, state[real].astype(np.uint8))
+            else:
+                fe.v = state.astype(np.uint8).copy()
         else:
             if state.shape != (nl.n, TLWE0_LEN):
                 raise FrontendError("snapshot state has the wrong shape")
-            real = np.nonzero(nl.kind != 34)[0].astype(np.uint32)  # OUTPUT wires alias their drivers
             fe.eng.restore(real, np.ascontiguousarray(state[real]))
         return fe
 

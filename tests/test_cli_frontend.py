@@ -108,6 +108,42 @@ def test_module_entry_point(tmp_path):
     assert "2,out,1" in r.stdout and "done." in r.stderr
 
 
+def _torchrun(nproc, port, *argv):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), "-m", "iyokan_b200", *[str(a) for a in argv]]
+    return subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+
+
+def test_two_process_run_equals_single_process(tmp_path):
+    """`torchrun -m iyokan_b200 plain` (gloo, world size 2): level-sliced sharding + all-gather behind the same
+    command line; result and snapshot/resume identical to the single-process run."""
+    import socket
+
+    def port():
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        p = s.getsockname()[1]
+        s.close()
+        return p
+
+    rom_words = [0x9, 0x6, 0xF, 0x1]
+    req = PlainPacket(rom={"rom": np.array([(w >> b) & 1 for w in rom_words for b in range(4)], np.uint8)},
+                      bits={"raddr": np.array([0, 0, 1, 0, 0, 1, 1, 1], np.uint8), "waddr": np.array([1, 1, 0, 1, 1, 0, 0, 0], np.uint8),
+                            "wren": np.array([1], np.uint8)})
+    req.save(tmp_path / "req")
+    bp = FIX / "lookup.toml"
+    assert run_cli("plain", "--blueprint", bp, "-i", tmp_path / "req", "-o", tmp_path / "one", "-c", 5, "--quiet") == 0
+    r = _torchrun(2, port(), "plain", "--blueprint", bp, "-i", tmp_path / "req", "-o", tmp_path / "two", "-c", 5, "--quiet")
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert (tmp_path / "two").read_bytes() == (tmp_path / "one").read_bytes()
+    r = _torchrun(2, port(), "plain", "--blueprint", bp, "-i", tmp_path / "req", "-o", tmp_path / "h", "-c", 2, "--snapshot",
+                  tmp_path / "snap", "--quiet")
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = _torchrun(2, port(), "plain", "--resume", tmp_path / "snap", "-o", tmp_path / "resumed", "-c", 3, "--quiet")
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert (tmp_path / "resumed").read_bytes() == (tmp_path / "one").read_bytes()
+
+
 # ---- the reference's own end-to-end cases (test.rb:384-548), all-gate blueprints, plain mode ----
 TEST_RB = [  # (blueprint, request, golden result, cycles)
     ("cahp-diamond-mux", "test00.in", "test00-diamond.out", 8), ("cahp-emerald-mux", "test00.in", "test00-emerald.out", 6),

@@ -198,3 +198,42 @@ def test_cli_tfhe_end_to_end_with_reference_tools_and_resume(tmp_path):
     assert cli("tfhe", "--evalkey", ek, "--resume", tmp_path / "snap", "-o", tmp_path / "resumed.enc", "-c", 2, "--quiet") == 0
     assert (tmp_path / "resumed.enc").read_bytes() == (tmp_path / "res.enc").read_bytes()
     ek.unlink()
+
+
+@pytest.mark.skipif(not O.have_iyokan_packet(), reason="oracle/_ref/iyokan-packet not built")
+def test_cli_tfhe_two_gpus(tmp_path):
+    """`torchrun --nproc-per-node 2 -m iyokan_b200 tfhe`: same result bits as the plain run (needs 2 GPUs)."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from iyokan_b200.cli import main
+    from iyokan_b200.packet import PlainPacket
+
+    root = Path(__file__).resolve().parents[1]
+    bp = root / "tests" / "fixtures" / "lookup.toml"
+    sk, ek = tmp_path / "sk", tmp_path / "ek"
+    O.iyokan_packet("genkey", "--type", "tfhepp", "--out", sk)
+    O.iyokan_packet("genevalkey", "--in", sk, "--out", ek)
+    req = PlainPacket(rom={"rom": np.array([(w >> b) & 1 for w in (7, 8, 2, 13) for b in range(4)], np.uint8)},
+                      bits={"raddr": np.array([1, 1, 0, 1], np.uint8), "waddr": np.array([0, 1, 1, 0], np.uint8),
+                            "wren": np.array([1], np.uint8)})
+    (tmp_path / "req.toml").write_text(req.to_toml())
+    O.iyokan_packet("toml2packet", "--in", tmp_path / "req.toml", "--out", tmp_path / "req")
+    O.iyokan_packet("enc", "--key", sk, "--in", tmp_path / "req", "--out", tmp_path / "req.enc")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", "-m", "iyokan_b200", "tfhe", "--blueprint", str(bp), "--evalkey", str(ek), "-i",
+           str(tmp_path / "req.enc"), "-o", str(tmp_path / "res.enc"), "-c", "3", "--quiet"]
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    O.iyokan_packet("dec", "--key", sk, "--in", tmp_path / "res.enc", "--out", tmp_path / "res")
+    try:
+        main(["plain", "--blueprint", str(bp), "-i", str(tmp_path / "req"), "-o", str(tmp_path / "res.plain"), "-c", "3", "--quiet"])
+    except SystemExit as e:
+        assert e.code == 0
+    got, want = PlainPacket.load(tmp_path / "res"), PlainPacket.load(tmp_path / "res.plain")
+    assert np.array_equal(got.bits["rdata"], want.bits["rdata"]) and np.array_equal(got.ram["ram"], want.ram["ram"])
+    ek.unlink()

@@ -597,6 +597,43 @@ extern "C" void sim_keyswitch(const void* jobs_raw, int njobs, const uint32_t* u
     }
 }
 
+// narrow-frontier path: KS_SPLIT CTAs per switch (ks_split_kernel) + ks_combine_kernel
+extern "C" void sim_keyswitch_split(const void* jobs_raw, int njobs, const uint32_t* ubuf, const uint16_t* ksk_dev,
+                                    uint16_t* arena)
+{
+    const KsJob* jobs = reinterpret_cast<const KsJob*>(jobs_raw);
+    constexpr int SPAN = N1 / KS_SPLIT;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int n = 0; n < njobs; n++) {
+        std::vector<uint32_t> partial((size_t)KS_SPLIT * 2 * KS_THREADS);
+        for (int piece = 0; piece < KS_SPLIT; piece++) {  // one CTA each
+            uint16_t codes[SPAN];
+            const int i0 = piece * SPAN;
+            for (int i = 0; i < SPAN; i++) codes[i] = ks_code(ubuf, jobs[n], i0 + i);
+            for (int k = 0; k < KS_THREADS; k++) {
+                uint32_t lo = 0, hi = 0;
+                for (int y = 0; y < KS_GROUPS; y++) {
+                    uint32_t l, h;
+                    ks_accumulate_range(reinterpret_cast<const uint32_t*>(ksk_dev), codes, k, y, KS_GROUPS, i0, i0 + SPAN, l, h);
+                    lo += l;
+                    hi += h;
+                }
+                partial[(size_t)piece * 2 * KS_THREADS + k] = lo;
+                partial[(size_t)piece * 2 * KS_THREADS + KS_THREADS + k] = hi;
+            }
+        }
+        uint32_t* out = reinterpret_cast<uint32_t*>(arena + (size_t)jobs[n].out * SLOT_STRIDE);
+        for (int k = 0; k < KS_THREADS; k++) {  // combine kernel
+            uint32_t lo = 0, hi = 0;
+            for (int piece = 0; piece < KS_SPLIT; piece++) {
+                lo += partial[(size_t)piece * 2 * KS_THREADS + k];
+                hi += partial[(size_t)piece * 2 * KS_THREADS + KS_THREADS + k];
+            }
+            out[k] = ks_finish(lo, hi, ks_b_rounded(ubuf, jobs[n]), jobs[n].post, k);
+        }
+    }
+}
+
 extern "C" void sim_unary(const void* jobs_raw, int njobs, uint16_t* arena)
 {
     const UnaryJob* jobs = reinterpret_cast<const UnaryJob*>(jobs_raw);

@@ -238,6 +238,17 @@ def test_keyswitch_bit_exact(sim, keys, ksk_dev, golden):
     sim.sim_keyswitch(p(jobs), n, p(ubuf), p(ksk_dev), p(arena))
     assert np.array_equal(arena[:, :637], golden["ks_out_tfhepp"])  # == the reference, bit for bit
     assert np.all(arena[:, 637:] == 0)
+    # narrow-frontier path: four CTAs per switch + combine
+    arena2 = np.full((n, 640), 0xABCD, np.uint16)
+    sim.sim_keyswitch_split(p(jobs), n, p(ubuf), p(ksk_dev), p(arena2))
+    assert np.array_equal(arena2, arena)
+    # MUX tail: two summed lvl1 samples and + mu after the switch go through both paths alike
+    mux = np.zeros(1, KSJOB)
+    mux["u0"], mux["u1"], mux["out"], mux["post"] = 0, 1, 0, 1 << 13
+    a1, a2 = np.zeros((1, 640), np.uint16), np.zeros((1, 640), np.uint16)
+    sim.sim_keyswitch(p(mux), 1, p(ubuf), p(ksk_dev), p(a1))
+    sim.sim_keyswitch_split(p(mux), 1, p(ubuf), p(ksk_dev), p(a2))
+    assert np.array_equal(a1, a2) and not np.array_equal(a1[0], arena[0])
 
 
 def run_batch(sim, G, ops, arena, in0, in1, in2, out, bk_ntt_sim, ksk_dev):

@@ -20,6 +20,7 @@ HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "libtfhe_oracle.so"
 REF_DRIVER = HERE / "_ref" / "ref_driver"
 IYOKAN_PACKET = HERE / "_ref" / "iyokan-packet"   # the reference's own packet tool, built unmodified
+REF_LINK_TEST = HERE / "_ref" / "b200_gate_test"  # tests/ref_link/b200_gate_test.cpp: TFHEpp types over the C ABI
 
 N0, N1, L, T = 636, 1024, 3, 7
 TLWE0, TLWE1, ROWS = N0 + 1, N1 + 1, 6
@@ -58,6 +59,12 @@ def build(force: bool = False) -> None:
         if (force or not REF_DRIVER.exists() or not IYOKAN_PACKET.exists()
                 or REF_DRIVER.stat().st_mtime < (HERE / "ref_driver.cpp").stat().st_mtime):
             subprocess.run(["make", "-C", str(HERE), "-j8", "ref"], check=True, capture_output=True)
+        # reference-side binding test (TFHEpp types + the product's C ABI); needs the CUDA library built first
+        so = HERE.parent / "iyokan_b200" / "csrc" / "libb200fhe.so"
+        src = HERE.parent / "tests" / "ref_link" / "b200_gate_test.cpp"
+        if so.exists() and src.exists() and (force or not REF_LINK_TEST.exists()
+                                             or REF_LINK_TEST.stat().st_mtime < max(so.stat().st_mtime, src.stat().st_mtime)):
+            subprocess.run(["make", "-C", str(HERE), "reflink"], check=True, capture_output=True)
 
 
 _lib = None

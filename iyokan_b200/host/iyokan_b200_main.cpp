@@ -1,0 +1,315 @@
+// iyokan-b200: `iyokan tfhe` with the gate workers replaced by the B200 back-end.
+//
+// This translation unit is compiled AGAINST THE UNMODIFIED REFERENCE (it includes its src/iyokan.hpp and
+// src/packet.hpp and links its TFHEpp objects; `make -C oracle iyokan-b200`, in the container that holds the
+// reference tree).  Everything that is not the hot path is the reference's own code, used as it is:
+//   NetworkBlueprint                        TOML blueprint parser                      (src/iyokan.hpp:1671-1945)
+//   readNetwork / YosysJSONReader / IyokanL1JSONReader                                 (:2064-2515)
+//   makeROMWithMUX / makeRAMWithMUX         builtin MUX memories (incl. the embedded mux-ram netlists, :2517-2762)
+//   TFHEPacket, readFromArchive / writeToArchive, TFHEpp::EvalKey   packet and key I/O (src/packet.hpp:208-340)
+// What is replaced is the back-end: instead of instantiating Task<>/Worker<> templates per gate
+// (src/iyokan_tfhepp.hpp:109-192) the readers are pointed at `FlatBuilder`, a NetworkBuilder that records the
+// DAG as flat arrays; the sub-networks are merged along the blueprint's [connect] edges exactly as
+// TFHEppFrontend's constructor does (src/iyokan_tfhepp.cpp:312-458) and handed to the level-replay engine
+// (include/b200net.h -> include/b200fhe.h), which evaluates one frontier of independent gates per CUDA launch
+// plan.  The cycle protocol is TFHEppFrontend::go (src/iyokan_tfhepp.cpp:465-566).
+//
+// Usage (option names of src/main.cpp:100-175):
+//   iyokan-b200 tfhe --blueprint B.toml --evalkey EK -i req.enc -o res.enc -c N [--skip-reset] [--quiet]
+// Snapshot/resume and the plaintext mode live in the Python front end (python -m iyokan_b200).
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "iyokan.hpp"
+#include "packet.hpp"
+
+extern "C" {
+#include "../../include/b200fhe.h"
+#include "../../include/b200net.h"
+}
+
+// ---- a NetworkBuilder (duck-typed to what the reference's readers call) that records flat arrays ----
+// (global namespace, like the reference's builders: makeROMWithMUX / makeRAMWithMUX find their helpers by ADL)
+struct FlatNet;
+class FlatBuilder {
+    friend struct FlatNet;
+
+protected:
+    std::vector<uint8_t> kind_;
+    std::vector<std::array<int32_t, 3>> in_;
+    std::vector<uint8_t> nin_;
+    std::map<TaskLabel, int> named_;  // ("input"|"output"|"rom"|"ram", port name, bit) -> node id
+
+    int add(uint8_t kind)
+    {
+        kind_.push_back(kind);
+        in_.push_back({-1, -1, -1});
+        nin_.push_back(0);
+        return (int)kind_.size() - 1;
+    }
+    int addNamed(uint8_t kind, const char* label, const std::string& port, int bit)
+    {
+        const int id = add(kind);
+        if (!named_.emplace(TaskLabel{label, port, bit}, id).second)
+            error::die("duplicate port ", label, " ", port, "[", bit, "]");
+        return id;
+    }
+    // what RAMNetworkBuilder<NetworkBuilder>::RAM expects from its base (src/iyokan.hpp:1285-1300)
+    struct IdHandle {
+        int id;
+        const IdHandle* operator->() const { return this; }
+        const IdHandle* depnode() const { return this; }
+        IdHandle label() const { return *this; }
+    };
+    IdHandle addNamedDFF(const std::string& label, const std::string& port, int bit)
+    {
+        return IdHandle{addNamed(B200NET_DFF, label.c_str(), port, bit)};
+    }
+
+public:
+    using NetworkType = FlatNet;
+    int AND() { return add(B200FHE_AND); }
+    int NAND() { return add(B200FHE_NAND); }
+    int ANDNOT() { return add(B200FHE_ANDNOT); }
+    int OR() { return add(B200FHE_OR); }
+    int NOR() { return add(B200FHE_NOR); }
+    int ORNOT() { return add(B200FHE_ORNOT); }
+    int XOR() { return add(B200FHE_XOR); }
+    int XNOR() { return add(B200FHE_XNOR); }
+    int MUX() { return add(B200FHE_MUX); }
+    int NOT() { return add(B200FHE_NOT); }
+    int CONSTONE() { return add(B200FHE_CONST1); }
+    int CONSTZERO() { return add(B200FHE_CONST0); }
+    int DFF() { return add(B200NET_DFF); }
+    int ROM(const std::string& port, int bit) { return addNamed(B200NET_INPUT, "rom", port, bit); }
+    int INPUT(const std::string& port, int bit) { return addNamed(B200NET_INPUT, "input", port, bit); }
+    int OUTPUT(const std::string& port, int bit) { return addNamed(B200NET_OUTPUT, "output", port, bit); }
+    void connect(int from, int to)
+    {
+        if (nin_.at(to) >= 3) error::die("node ", to, " has too many inputs");
+        in_[to][nin_[to]++] = from;
+    }
+};
+
+struct FlatNet {
+    std::vector<uint8_t> kind;
+    std::vector<std::array<int32_t, 3>> in;
+    std::map<TaskLabel, int> named;
+    FlatNet(FlatBuilder&& b) : kind(std::move(b.kind_)), in(std::move(b.in_)), named(std::move(b.named_)) {}
+    void checkValid(error::Stack&) const {}  // arities are validated by b200net_create on the merged design
+};
+
+namespace {
+
+// ---- TLWE helpers: trivial ciphertexts (0,...,0, +-mu), iyokan_tfhepp.hpp:23-27 ----
+TLWELvl0 trivial(bool bit)
+{
+    TLWELvl0 t{};
+    t[TFHEpp::lvl0param::n] = bit ? TFHEpp::lvl0param::μ : static_cast<TFHEpp::lvl0param::T>(-TFHEpp::lvl0param::μ);
+    return t;
+}
+static_assert(sizeof(TLWELvl0) == B200FHE_TLWE0_LEN * sizeof(uint16_t), "TLWELvl0 is the wire format of the C ABI");
+
+void ck(int rc, const char* what)
+{
+    if (rc) error::die("b200: ", what, ": ", b200net_last_error(), " / ", b200fhe_last_error());
+}
+
+struct Design {
+    std::vector<uint8_t> kind;
+    std::vector<int32_t> in0, in1, in2;
+    std::map<std::string, std::pair<int, const FlatNet*>> nets;  // name -> (offset into the merged arrays, net)
+    int node(const blueprint::Port& p) const
+    {
+        auto it = nets.find(p.nodeName);
+        if (it == nets.end()) error::die("Invalid network name: ", p.nodeName);
+        auto jt = it->second.second->named.find(p.portLabel);
+        if (jt == it->second.second->named.end())
+            error::die("Invalid port: ", p.nodeName, "/", p.portLabel.portName, "[", p.portLabel.portBit, "] (", p.portLabel.kind, ")");
+        return it->second.first + jt->second;
+    }
+    int node(const std::string& net, const char* label, const std::string& port, int bit) const
+    {
+        return node(blueprint::Port{net, TaskLabel{label, port, bit}});
+    }
+};
+
+}  // namespace
+
+int main(int argc, char** argv)
+{
+    std::string blueprintPath, evalkeyPath, inPath, outPath;
+    int numCycles = -1;
+    bool skipReset = false, quiet = false;
+    if (argc < 2 || std::string(argv[1]) != "tfhe") error::die("usage: iyokan-b200 tfhe --blueprint B --evalkey EK -i IN -o OUT -c N");
+    for (int i = 2; i < argc; i++) {
+        const std::string a = argv[i];
+        auto next = [&]() -> std::string {
+            if (i + 1 >= argc) error::die("missing value for ", a);
+            return argv[++i];
+        };
+        if (a == "--blueprint") blueprintPath = next();
+        else if (a == "--evalkey") evalkeyPath = next();
+        else if (a == "-i" || a == "--in") inPath = next();
+        else if (a == "-o" || a == "--out") outPath = next();
+        else if (a == "-c") numCycles = std::stoi(next());
+        else if (a == "--skip-reset") skipReset = true;
+        else if (a == "--quiet") quiet = true;
+        else if (a == "--verbose" || a == "--enable-gpu" || a == "--show-combinational-progress") {}
+        else if (a == "--cpu" || a == "--gpu" || a == "--num-gpu" || a == "--gpu_num" || a == "--sched") next();  // CPU scheduler knobs
+        else error::die("unknown option ", a);
+    }
+    if (blueprintPath.empty() || evalkeyPath.empty() || inPath.empty() || outPath.empty())
+        error::die("--blueprint, --evalkey, -i and -o are required");
+    if (quiet) spdlog::set_level(spdlog::level::err);
+
+    // ---- the reference's loader: blueprint, netlists, builtin MUX memories ----
+    const NetworkBlueprint bp{blueprintPath};
+    if (bp.needsCircuitKey())
+        error::die("blueprint uses CMUX memories (circuit bootstrapping): use the mux-rom / mux-ram builtins with this back-end");
+    std::map<std::string, std::shared_ptr<FlatNet>> name2net;
+    for (const auto& file : bp.files()) name2net.emplace(file.name, readNetwork<FlatBuilder>(file));
+    for (const auto& rom : bp.builtinROMs()) name2net.emplace(rom.name, makeROMWithMUX<FlatBuilder>(rom.inAddrWidth, rom.outRdataWidth));
+    for (const auto& ram : bp.builtinRAMs()) {
+        if (ram.inWdataWidth != ram.outRdataWidth) error::die("Invalid RAM size; wdata and rdata widths differ");
+        name2net.emplace(ram.name, makeRAMWithMUX<FlatBuilder>(ram.inAddrWidth, ram.outRdataWidth));
+    }
+
+    // ---- merge the sub-networks into one DAG (what connectTasks does across networks, iyokan_tfhepp.cpp:428-435) ----
+    Design d;
+    for (auto& [name, net] : name2net) {
+        const int off = (int)d.kind.size();
+        d.nets.emplace(name, std::make_pair(off, net.get()));
+        for (size_t i = 0; i < net->kind.size(); i++) {
+            d.kind.push_back(net->kind[i]);
+            auto rel = [&](int v) { return v < 0 ? -1 : v + off; };
+            d.in0.push_back(rel(net->in[i][0]));
+            d.in1.push_back(rel(net->in[i][1]));
+            d.in2.push_back(rel(net->in[i][2]));
+        }
+    }
+    for (auto&& [key, port] : bp.atPorts()) d.node(port);  // existence check, as the reference does first
+    for (const auto& [src, dst] : bp.edges()) {            // the consumer's INPUT wire becomes an alias of the producer
+        const int s = d.node(src), t = d.node(dst);
+        if (d.kind[t] != B200NET_INPUT) error::die("port connected twice: ", dst.nodeName, "/", dst.portLabel.portName);
+        d.kind[t] = B200NET_OUTPUT;
+        d.in0[t] = s;
+    }
+
+    // ---- keys and request, read by the reference's own (cereal) code ----
+    const auto ek = readFromArchive<TFHEpp::EvalKey>(evalkeyPath);
+    if (!ek.bklvl01 || !ek.iksklvl10) error::die("EvalKey lacks bklvl01 / iksklvl10 (run iyokan-packet genevalkey)");
+    const auto req = readFromArchive<TFHEPacket>(inPath);
+    if (numCycles < 0) numCycles = req.numCycles.value_or(-1);
+    if (numCycles < 0) error::die("the number of cycles is given neither by -c nor by the request packet");
+
+    b200fhe_ctx* ctx = nullptr;
+    if (b200fhe_create(&ctx, 0)) error::die("b200fhe_create: ", b200fhe_last_error());
+    if (b200fhe_load_keys(ctx, reinterpret_cast<const uint32_t*>(ek.bklvl01.get()),
+                          reinterpret_cast<const uint16_t*>(ek.iksklvl10.get())))
+        error::die("b200fhe_load_keys: ", b200fhe_last_error());
+    b200net* net = nullptr;
+    ck(b200net_create(&net, d.kind.size(), d.kind.data(), d.in0.data(), d.in1.data(), d.in2.data()), "b200net_create");
+    ck(b200net_bind(net, ctx, 1), "b200net_bind");
+    spdlog::info("{} nodes, {} levels, {} bootstraps per cycle, {} DFF", b200net_num_nodes(net), b200net_num_levels(net),
+                 b200net_bootstraps_per_cycle(net), b200net_num_dff(net));
+
+    auto set = [&](const std::vector<uint32_t>& nodes, const std::vector<TLWELvl0>& vals) {
+        if (nodes.empty()) return;
+        ck(b200net_set(net, nodes.data(), reinterpret_cast<const uint16_t*>(vals.data()), nodes.size()), "b200net_set");
+    };
+    {  // DFF / RAM cells start at trivial 0
+        std::vector<uint32_t> nodes;
+        for (size_t i = 0; i < d.kind.size(); i++)
+            if (d.kind[i] == B200NET_DFF) nodes.push_back((uint32_t)i);
+        set(nodes, std::vector<TLWELvl0>(nodes.size(), trivial(false)));
+    }
+    // memories named in the request: MUX ROM contents now, MUX RAM contents on the first cycle
+    auto memNodes = [&](const std::string& name, const char* label, const char* port, size_t n) {
+        std::vector<uint32_t> nodes;
+        for (size_t i = 0; i < n; i++) nodes.push_back((uint32_t)d.node(name, label, port, (int)i));
+        return nodes;
+    };
+    for (const auto& rom : bp.builtinROMs()) {
+        auto it = req.romInTLWE.find(rom.name);
+        if (it == req.romInTLWE.end()) continue;
+        const size_t n = (size_t(1) << rom.inAddrWidth) * rom.outRdataWidth;
+        if (it->second.size() != n) error::die("Invalid request packet: wrong length of ROM ", rom.name);
+        set(memNodes(rom.name, "rom", "romdata", n), it->second);
+    }
+    // external ports
+    const bool hasReset = bp.at("reset").has_value();
+    auto resetNode = [&] { return std::vector<uint32_t>{(uint32_t)d.node(*bp.at("reset"))}; };
+    for (const auto& [name, stream] : req.bits) {
+        if (name == "reset") error::die("@reset cannot be set by the request");
+        if (!bp.atPortWidths().count(name)) error::die("Invalid request packet: unknown port @", name);
+    }
+
+    // ---- cycle protocol (TFHEppFrontend::go) ----
+    const auto t0 = std::chrono::steady_clock::now();
+    if (hasReset && !skipReset) {
+        set(resetNode(), {trivial(true)});
+        ck(b200net_run(net), "b200net_run");
+    }
+    for (int c = 0; c < numCycles; c++) {
+        ck(b200net_tick(net), "b200net_tick");
+        if (c == 0) {
+            if (hasReset) set(resetNode(), {trivial(false)});
+            for (const auto& ram : bp.builtinRAMs()) {
+                auto it = req.ramInTLWE.find(ram.name);
+                if (it == req.ramInTLWE.end()) continue;
+                const size_t n = (size_t(1) << ram.inAddrWidth) * ram.outRdataWidth;
+                if (it->second.size() != n) error::die("Invalid request packet: wrong length of RAM ", ram.name);
+                set(memNodes(ram.name, "ram", "ramdata", n), it->second);
+            }
+        }
+        for (const auto& [name, stream] : req.bits) {  // setCircularInputs (iyokan_tfhepp.cpp:274-296)
+            const int width = bp.atPortWidths().at(name);
+            std::vector<uint32_t> nodes;
+            std::vector<TLWELvl0> vals;
+            for (int b = 0; b < width; b++) {
+                const auto port = bp.at(name, b);
+                if (!port || port->portLabel.kind != "input") continue;
+                nodes.push_back((uint32_t)d.node(*port));
+                vals.push_back(stream.at((size_t(width) * c + b) % stream.size()));
+            }
+            set(nodes, vals);
+        }
+        ck(b200net_run(net), "b200net_run");
+    }
+    if (b200fhe_sync(ctx)) error::die("b200fhe_sync: ", b200fhe_last_error());
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    spdlog::info("done. ({} us, {:.0f} bootstraps/s)", (long long)(secs * 1e6),
+                 secs > 0 ? b200net_bootstraps_per_cycle(net) * (double)numCycles / secs : 0.0);
+
+    // ---- result packet (makeResPacket, iyokan_tfhepp.cpp:176-227) ----
+    auto get = [&](const std::vector<uint32_t>& nodes) {
+        std::vector<TLWELvl0> vals(nodes.size());
+        if (!nodes.empty()) ck(b200net_get(net, nodes.data(), reinterpret_cast<uint16_t*>(vals.data()), nodes.size()), "b200net_get");
+        return vals;
+    };
+    TFHEPacket res{{}, {}, {}, {}, {}, numCycles};
+    for (const auto& [name, width] : bp.atPortWidths()) {
+        std::vector<uint32_t> nodes;
+        bool isOutput = false;
+        for (int b = 0; b < width; b++)
+            if (const auto port = bp.at(name, b); port && port->portLabel.kind == "output") {
+                isOutput = true;
+                nodes.push_back((uint32_t)d.node(*port));
+            }
+        if (isOutput) res.bits.emplace(name, get(nodes));
+    }
+    for (const auto& ram : bp.builtinRAMs()) {
+        const size_t n = (size_t(1) << ram.inAddrWidth) * ram.outRdataWidth;
+        res.ramInTLWE.emplace(ram.name, get(memNodes(ram.name, "ram", "ramdata", n)));
+    }
+    writeToArchive(outPath, res);
+    b200net_destroy(net);
+    b200fhe_destroy(ctx);
+    return 0;
+}

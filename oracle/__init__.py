@@ -21,6 +21,7 @@ LIB_PATH = HERE / "libtfhe_oracle.so"
 REF_DRIVER = HERE / "_ref" / "ref_driver"
 IYOKAN_PACKET = HERE / "_ref" / "iyokan-packet"   # the reference's own packet tool, built unmodified
 REF_LINK_TEST = HERE / "_ref" / "b200_gate_test"  # tests/ref_link/b200_gate_test.cpp: TFHEpp types over the C ABI
+IYOKAN_B200 = HERE / "_ref" / "iyokan-b200"       # iyokan_b200/host/iyokan_b200_main.cpp: the reference's loader + our engine
 
 N0, N1, L, T = 636, 1024, 3, 7
 TLWE0, TLWE1, ROWS = N0 + 1, N1 + 1, 6
@@ -62,9 +63,12 @@ def build(force: bool = False) -> None:
         # reference-side binding test (TFHEpp types + the product's C ABI); needs the CUDA library built first
         so = HERE.parent / "iyokan_b200" / "csrc" / "libb200fhe.so"
         src = HERE.parent / "tests" / "ref_link" / "b200_gate_test.cpp"
-        if so.exists() and src.exists() and (force or not REF_LINK_TEST.exists()
-                                             or REF_LINK_TEST.stat().st_mtime < max(so.stat().st_mtime, src.stat().st_mtime)):
-            subprocess.run(["make", "-C", str(HERE), "reflink"], check=True, capture_output=True)
+        host = HERE.parent / "iyokan_b200" / "host"
+        deps = [so, src, host / "libb200net.so", host / "iyokan_b200_main.cpp"]
+        if all(d.exists() for d in deps) and (force or not REF_LINK_TEST.exists() or not IYOKAN_B200.exists()
+                                              or min(REF_LINK_TEST.stat().st_mtime, IYOKAN_B200.stat().st_mtime)
+                                              < max(d.stat().st_mtime for d in deps)):
+            subprocess.run(["make", "-C", str(HERE), "-j4", "reflink"], check=True, capture_output=True)
 
 
 _lib = None

@@ -31,3 +31,51 @@ def test_binding_fails_loudly_without_a_gpu():
         pytest.skip("GPU present")
     r = _run(4, 1)
     assert r.returncode == 2 and "b200fhe_create" in r.stderr   # no silent CPU path behind the C ABI
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (O.IYOKAN_B200.exists() and O.have_iyokan_packet()), reason="oracle/_ref/iyokan-b200 not built")
+@pytest.mark.parametrize("blueprint,cycles", [("lookup.toml", 4), ("counter-2bit.toml", 3)])
+def test_iyokan_b200_binary_with_the_reference_loader(tmp_path, blueprint, cycles):
+    """`iyokan-b200 tfhe`: the reference's own blueprint / Yosys / MUX-memory loader and packet code (compiled from
+    its sources) in front of the B200 engine, against keys and packets made by the reference's iyokan-packet; the
+    decrypted result equals the plaintext run of the same blueprint and request."""
+    from pathlib import Path
+
+    import numpy as np
+
+    from iyokan_b200.cli import main
+    from iyokan_b200.packet import PlainPacket
+
+    bp = Path(__file__).resolve().parent / "fixtures" / blueprint
+    sk, ek = tmp_path / "sk", tmp_path / "ek"
+    O.iyokan_packet("genkey", "--type", "tfhepp", "--out", sk)
+    O.iyokan_packet("genevalkey", "--in", sk, "--out", ek)
+    if blueprint == "lookup.toml":
+        req = PlainPacket(rom={"rom": np.array([(w >> b) & 1 for w in (3, 12, 5, 10) for b in range(4)], np.uint8)},
+                          ram={"ram": np.zeros(16, np.uint8)},
+                          bits={"raddr": np.array([1, 0, 0, 1, 1, 1], np.uint8), "waddr": np.array([0, 0, 1, 0, 0, 1], np.uint8),
+                                "wren": np.array([1, 1, 0], np.uint8)})
+    else:
+        req = PlainPacket()
+    (tmp_path / "req.toml").write_text(req.to_toml())
+    O.iyokan_packet("toml2packet", "--in", tmp_path / "req.toml", "--out", tmp_path / "req")
+    O.iyokan_packet("enc", "--key", sk, "--in", tmp_path / "req", "--out", tmp_path / "req.enc")
+    r = subprocess.run([str(O.IYOKAN_B200), "tfhe", "--blueprint", str(bp), "--evalkey", str(ek), "-i", str(tmp_path / "req.enc"),
+                        "-o", str(tmp_path / "res.enc"), "-c", str(cycles)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "bootstraps per cycle" in r.stdout + r.stderr
+    O.iyokan_packet("dec", "--key", sk, "--in", tmp_path / "res.enc", "--out", tmp_path / "res")
+    try:
+        main(["plain", "--blueprint", str(bp), "-i", str(tmp_path / "req"), "-o", str(tmp_path / "res.plain"), "-c", str(cycles),
+              "--quiet"])
+    except SystemExit as e:
+        assert e.code == 0
+    got, want = PlainPacket.load(tmp_path / "res"), PlainPacket.load(tmp_path / "res.plain")
+    assert got.num_cycles == want.num_cycles == cycles
+    assert sorted(got.bits) == sorted(want.bits)
+    for name in want.bits:
+        assert np.array_equal(got.bits[name], want.bits[name]), name
+    for name in want.ram:
+        assert np.array_equal(got.ram[name], want.ram[name]), name
+    ek.unlink()

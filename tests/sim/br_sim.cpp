@@ -25,6 +25,13 @@ static BlockTw g_btw;
 static Block8Tw g_b8tw;
 static bool g_init = false;
 
+// Thread-order control: every phase function is claimed to be free of intra-phase cross-thread communication, so
+// the result must not depend on the order in which the simulator runs the threads (or warps) of a phase.  Mode 0 =
+// ascending, 1 = descending, 2 = a fixed permutation; tests run the kernels under all three and compare.
+static int g_order = 0;
+extern "C" void sim_set_thread_order(int mode) { g_order = mode; }
+static inline int ord(int i, int n) { return g_order == 0 ? i : g_order == 1 ? n - 1 - i : (i * 7 + 3) % n; }
+
 extern "C" void sim_init()
 {
     if (!g_init) {
@@ -212,29 +219,32 @@ static void sim_br3_cta(const BrJob* jobs, int njobs, int cta, const uint16_t* a
         for (int lane = 0; lane < 32; lane++)
             br_prologue<G>(sm, jobs[jobof(w >> 1)], arena, w >> 1, w & 1, lane, regs[w * 32 + lane].accr);
     for (int i = 0; i < n_iter; i++) {
-        for (int w = 0; w < W; w++) {
-            const int g = w >> 1, q = w & 1;
-            for (int lane = 0; lane < 32; lane++) {
+        for (int ww = 0; ww < W; ww++) {
+            const int w = ord(ww, W), g = w >> 1, q = w & 1;
+            for (int l = 0; l < 32; l++) {
+                const int lane = ord(l, 32);
                 Regs& r = regs[w * 32 + lane];
                 br_fwd3_a<G>(sm, i, g, q, lane, r.accr, r.x0, r.x1, r.x2);
             }
-            for (int lane = 0; lane < 32; lane++) {
+            for (int l = 0; l < 32; l++) {
+                const int lane = ord(l, 32);
                 Regs& r = regs[w * 32 + lane];
                 br_fwd3_b<G>(sm, g, q, lane, r.x0, r.x1, r.x2);
             }
-            for (int lane = 0; lane < 32; lane++) br_fwd3_c<G>(sm, g, q, lane);
+            for (int l = 0; l < 32; l++) br_fwd3_c<G>(sm, g, q, ord(l, 32));
         }
         const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
-        for (int tid = 0; tid < T; tid++) {
+        for (int t = 0; t < T; t++) {
+            const int tid = ord(t, T);
             uint32_t bk0[BK_COLS][ROWS];
             pw_load(bk_i, tid, bk0);
             br_pointwise<G>(sm, bk_i, tid, bk0);
         }
-        for (int w = 0; w < W; w++) {
-            const int g = w >> 1, q = w & 1;
-            for (int lane = 0; lane < 32; lane++) br_inv3_a<G>(sm, g, q, lane);
-            for (int lane = 0; lane < 32; lane++) br_inv3_b<G>(sm, g, q, lane, regs[w * 32 + lane].accr);
-            for (int lane = 0; lane < 32; lane++) br_inv3_c<G>(sm, g, q, lane, regs[w * 32 + lane].accr);
+        for (int ww = 0; ww < W; ww++) {
+            const int w = ord(ww, W), g = w >> 1, q = w & 1;
+            for (int l = 0; l < 32; l++) br_inv3_a<G>(sm, g, q, ord(l, 32));
+            for (int l = 0; l < 32; l++) br_inv3_b<G>(sm, g, q, ord(l, 32), regs[w * 32 + ord(l, 32)].accr);
+            for (int l = 0; l < 32; l++) br_inv3_c<G>(sm, g, q, ord(l, 32), regs[w * 32 + ord(l, 32)].accr);
         }
     }
     for (int w = 0; w < W; w++) {
@@ -405,8 +415,8 @@ static void sim_br4_cta(const BrJob* jobs, int job, const uint16_t* arena, const
     std::memcpy(sm.tw, &g_btw, sizeof(BlockTw));
     for (int tid = 0; tid < BR4_THREADS; tid++) br4_prologue(sm, jobs[job], arena, tid);
     auto each = [&](auto fn) {
-        for (int tid = 0; tid < BR4_THREADS; tid++) {
-            const int team = tid >> 6;
+        for (int k = 0; k < BR4_THREADS; k++) {
+            const int tid = ord(k, BR4_THREADS), team = tid >> 6;
             fn(team / GL, team % GL, tid & 63);
         }
     };
@@ -415,7 +425,8 @@ static void sim_br4_cta(const BrJob* jobs, int job, const uint16_t* arena, const
         each([&](int q, int d, int t) { br4_fwd_p1(sm, i, q, d, t); });
         each([&](int q, int d, int t) { br4_fwd_p2(sm, q, d, t); });
         each([&](int q, int d, int t) { br4_fwd_p3(sm, q, d, t); });
-        for (int tid = 0; tid < BR4_THREADS; tid++) {
+        for (int k = 0; k < BR4_THREADS; k++) {
+            const int tid = ord(k, BR4_THREADS);
             br4_pointwise_item(sm, tid);
             br4_pointwise_item(sm, tid + BR4_THREADS);
         }
@@ -532,8 +543,11 @@ static void sim_br6_cluster(const BrJob* jobs, int job, const uint16_t* arena, c
         for (int tid = 0; tid < BR6_THREADS; tid++) br6_prologue(sm[q], jobs[job], arena, q, tid);
     }
     auto each = [&](auto fn) {
-        for (int q = 0; q < 2; q++)
-            for (int tid = 0; tid < BR6_THREADS; tid++) fn(q, tid >> 7, tid & 127);
+        for (int qq = 0; qq < 2; qq++)
+            for (int k = 0; k < BR6_THREADS; k++) {
+                const int q = ord(qq, 2), tid = ord(k, BR6_THREADS);
+                fn(q, tid >> 7, tid & 127);
+            }
     };
     std::vector<uint64_t> pacc((size_t)2 * BR6_THREADS * LIMBS * 4);
     auto acc_of = [&](int q, int tid) -> uint64_t(&)[LIMBS][4] {
@@ -550,9 +564,9 @@ static void sim_br6_cluster(const BrJob* jobs, int job, const uint16_t* arena, c
             for (int d = 0; d < GL; d++)
                 std::memcpy(sm[q ^ 1].in_tile(q * GL + d), sm[q].in_tile(q * GL + d), (size_t)B8_WORDS * 4);
         for (int q = 0; q < 2; q++)
-            for (int tid = 0; tid < BR6_THREADS; tid++) br6_pw_local(sm[q], q, tid, acc_of(q, tid));
+            for (int k = 0; k < BR6_THREADS; k++) br6_pw_local(sm[q], q, ord(k, BR6_THREADS), acc_of(q, ord(k, BR6_THREADS)));
         for (int q = 0; q < 2; q++)
-            for (int tid = 0; tid < BR6_THREADS; tid++) br6_pw_finish(sm[q], q, tid, acc_of(q, tid));
+            for (int k = 0; k < BR6_THREADS; k++) br6_pw_finish(sm[q], q, ord(k, BR6_THREADS), acc_of(q, ord(k, BR6_THREADS)));
         each([&](int q, int d, int t) { br6_inv_pA(sm[q], d, t); });
         each([&](int q, int d, int t) { br6_inv_pB(sm[q], d, t); });
         each([&](int q, int d, int t) { br6_inv_pC(sm[q], d, t); });

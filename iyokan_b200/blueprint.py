@@ -11,7 +11,7 @@ and performs what the front end's constructor does before the DAG reaches the sc
 (TFHEppFrontend, src/iyokan_tfhepp.cpp:312-458): every sub-network is instantiated into ONE node space and
 every [connect] edge turns the consumer's INPUT wire into an alias of its producer.  MUX ROM / RAM builtins are
 generated (netlist.mux_rom / netlist.mux_ram: the circuits of iyokan.hpp:2538-2593, 2646-2762); CMUX-memory
-builtins (rom / ram with circuit bootstrapping) are out of scope and rejected.
+builtins (type "rom" / "ram") are functionally identical and are evaluated as MUX memories as well.
 """
 from __future__ import annotations
 
@@ -163,12 +163,16 @@ def read_blueprint(toml_path, mux_ram_json_dir=None):
     for bi in bp.get("builtin", []):
         name = bi["name"]
         sn = SubNet()
-        if bi["type"] == "mux-rom":
+        # CMUX memories (type "rom" / "ram": TRLWE-packed contents read with CMUX trees after circuit bootstrapping,
+        # src/iyokan_tfhepp.hpp:194-889) have the same ports and the same function as the MUX memories; this back-end
+        # evaluates them AS MUX memories (more gate bootstraps, no lvl02 kernels), using the per-bit TLWE form of the
+        # contents that `iyokan-packet enc` always writes next to the TRLWE form (romInTLWE / ramInTLWE).
+        if bi["type"] in ("mux-rom", "rom"):
             addr = [b._add(32) for _ in range(bi["in_addr_width"])]
             sn.inputs["addr"] = dict(enumerate(addr))
             outs = mux_rom(b, addr, bi["out_rdata_width"], name=name)
             sn.outputs["rdata"] = {i: b._add(34, o) for i, o in enumerate(outs)}
-        elif bi["type"] == "mux-ram":
+        elif bi["type"] in ("mux-ram", "ram"):
             a, w, r = bi["in_addr_width"], bi["in_wdata_width"], bi["out_rdata_width"]
             assert w == r
             pre = Path(mux_ram_json_dir) / f"mux-ram-{a}-{w}-{r}.min.json" if mux_ram_json_dir else None
@@ -183,7 +187,7 @@ def read_blueprint(toml_path, mux_ram_json_dir=None):
                 outs = mux_ram(b, addr, wren, wdata, name=name)
                 sn.outputs["rdata"] = {i: b._add(34, o) for i, o in enumerate(outs)}
         else:
-            raise ValueError(f"builtin type {bi['type']!r}: CMUX memory needs circuit bootstrapping, which this back-end does not implement (use the mux-rom / mux-ram blueprints)")
+            raise ValueError(f"unknown builtin type {bi['type']!r}")
         subs[name] = sn
     connect = dict(bp.get("connect", {}))
     togrnd = connect.pop("TOGND", [])

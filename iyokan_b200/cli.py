@@ -1,5 +1,5 @@
 """`python -m iyokan_b200 plain|tfhe ...`: the command line of `iyokan plain` / `iyokan tfhe` (src/main.cpp:12-277)
-for all-gate blueprints, on the plaintext host engine and on the B200 back-end.
+on the plaintext host engine and on the B200 back-end (CMUX memories are evaluated as MUX memories).
 
     python -m iyokan_b200 plain --blueprint B.toml -i req.plain -o res.plain [-c N] [--snapshot S]
     python -m iyokan_b200 tfhe  --blueprint B.toml --evalkey EK -i req.enc -o res.enc -c N [--snapshot S]

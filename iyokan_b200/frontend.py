@@ -1,7 +1,7 @@
 """Front end: the cycle protocol of `iyokan plain` / `iyokan tfhe` over a flat netlist, with snapshot / resume.
 
-Mirrors TFHEppFrontend / PlainFrontend (src/iyokan_tfhepp.cpp:116-573, src/iyokan_plain.cpp:115-) for all-gate
-blueprints:
+Mirrors TFHEppFrontend / PlainFrontend (src/iyokan_tfhepp.cpp:116-573, src/iyokan_plain.cpp:115-; SURVEY.md
+Appendix B); memories are gate-level MUX ROM / RAM (a blueprint's CMUX memories are built the same way):
   * request packet -> ROM contents at construction, RAM contents and `@`-port bit streams from the first cycle on
     (setInitialRAM / setCircularInputs, iyokan_tfhepp.cpp:274-296): bit b of port p at cycle c =
     stream[(width * c + b) mod size];

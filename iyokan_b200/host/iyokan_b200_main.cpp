@@ -170,8 +170,8 @@ int main(int argc, char** argv)
 
     // ---- the reference's loader: blueprint, netlists, builtin MUX memories ----
     const NetworkBlueprint bp{blueprintPath};
-    if (bp.needsCircuitKey())
-        error::die("blueprint uses CMUX memories (circuit bootstrapping): use the mux-rom / mux-ram builtins with this back-end");
+    if (bp.needsCircuitKey())  // type = "rom" / "ram": same ports, same function, evaluated here as MUX memories
+        spdlog::warn("blueprint declares CMUX memories: evaluating them as MUX memories (no circuit bootstrapping on this back-end)");
     std::map<std::string, std::shared_ptr<FlatNet>> name2net;
     for (const auto& file : bp.files()) name2net.emplace(file.name, readNetwork<FlatBuilder>(file));
     for (const auto& rom : bp.builtinROMs()) name2net.emplace(rom.name, makeROMWithMUX<FlatBuilder>(rom.inAddrWidth, rom.outRdataWidth));

@@ -1,6 +1,7 @@
 """`python -m iyokan_b200 plain ...`: blueprint loader, cycle protocol, packets and snapshot/resume on the
 plaintext back-end (no GPU).  Hand-written fixtures run everywhere; the reference's own test.rb cases
-(test/config-toml + test/in -> test/out) run where the reference tree is mounted."""
+(test/config-toml + test/in -> test/out) run where the reference tree is mounted: every blueprint of test.rb,
+those declared with CMUX memories included (evaluated as MUX memories)."""
 import json
 import subprocess
 import sys
@@ -91,9 +92,9 @@ def test_error_behaviour(tmp_path):
     assert run_cli("plain", "--blueprint", bp, "-i", tmp_path / "rst.in", "-o", tmp_path / "r", "-c", 1) == 1
     (tmp_path / "none.in").write_text("")
     assert run_cli("plain", "--blueprint", bp, "-i", tmp_path / "none.in", "-o", tmp_path / "r") == 1   # no cycle count
-    (tmp_path / "cmux.toml").write_text('[[builtin]]\ntype = "ram"\nname = "ram"\nin_addr_width = 8\n'
-                                        'in_wdata_width = 8\nout_rdata_width = 8\n')
-    assert run_cli("plain", "--blueprint", tmp_path / "cmux.toml", "-i", tmp_path / "none.in", "-o", tmp_path / "r",
+    (tmp_path / "odd.toml").write_text('[[builtin]]\ntype = "quantum-ram"\nname = "ram"\nin_addr_width = 8\n'
+                                       'in_wdata_width = 8\nout_rdata_width = 8\n')
+    assert run_cli("plain", "--blueprint", tmp_path / "odd.toml", "-i", tmp_path / "none.in", "-o", tmp_path / "r",
                    "-c", 1) == 1
     with pytest.raises(FrontendError):
         Frontend(B.read_blueprint(bp), "tfhe", None)   # encrypted mode never falls back to the CPU
@@ -156,6 +157,15 @@ TEST_RB = [  # (blueprint, request, golden result, cycles)
     ("mux-ram-addr8bit", "test06.in", "test06.out", 16), ("mux-ram-addr9bit", "test07.in", "test07.out", 16),
     ("mux-ram-8-16-16", "test08.in", "test08.out", 8), ("counter-4bit", "test13.in", "test13.out", 3),
     ("big-mult", "test21.in", "test21.out", 1),
+    # blueprints declared with CMUX memories (type = "rom" / "ram"): evaluated as MUX memories, same golden packets
+    ("cahp-diamond", "test00.in", "test00-diamond.out", 8), ("cahp-emerald", "test00.in", "test00-emerald.out", 6),
+    ("cahp-ruby", "test09.in", "test09-ruby.out", 7), ("cahp-pearl", "test09.in", "test09-pearl.out", 3),
+    ("cahp-diamond", "test01.in", "test01-diamond.out", 346), ("cahp-emerald", "test01.in", "test01-emerald.out", 261),
+    ("cahp-ruby", "test10.in", "test10-ruby.out", 362), ("cahp-pearl", "test10.in", "test10-pearl.out", 264),
+    ("cahp-ruby", "test14.in", "test14.out", 20), ("cahp-ruby-iyokanl1", "test09.in", "test09-ruby.out", 7),
+    ("ram-addr8bit", "test06.in", "test06.out", 16), ("ram-addr9bit", "test07.in", "test07.out", 16),
+    ("ram-8-16-16", "test08.in", "test08.out", 8), ("rom-7-32", "test12.in", "test12.out", 1), ("rom-4-8", "test15.in", "test15.out", 1),
+    ("dff-reset", "test23.in", "test23.out", 1),
 ]
 
 

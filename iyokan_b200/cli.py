@@ -8,7 +8,8 @@ on the plaintext host engine and on the B200 back-end (CMUX memories are evaluat
     python -m torch.distributed.run --nproc-per-node N -m iyokan_b200 tfhe ...   (N GPUs of one box, NCCL)
 
 Same option names as the reference; options that only tune its CPU scheduler (--cpu, --sched, --gpu, --num-gpu,
---show-combinational-progress, --dump-*) are accepted and ignored.  Requests may be given as binary packets
+--show-combinational-progress, --dump-time-csv-prefix, --dump-graph-*) are accepted and ignored; --dump-prefix
+writes the result packet after every cycle (encrypted in tfhe mode).  Requests may be given as binary packets
 (what `iyokan-packet toml2packet / enc` writes) or, in plain mode, directly as the TOML source.  Errors follow the
 reference: message on stderr, exit status 1 (src/error.hpp:21-47)."""
 from __future__ import annotations
@@ -52,7 +53,8 @@ def _common(sp):
     sp.add_argument("--quiet", action="store_true")
     sp.add_argument("--verbose", action="store_true")
     sp.add_argument("--stdout-csv", action="store_true")
-    for ignored in ("--cpu", "--sched", "--gpu", "--num-gpu", "--gpu_num", "--dump-prefix", "--dump-time-csv-prefix",
+    sp.add_argument("--dump-prefix")
+    for ignored in ("--cpu", "--sched", "--gpu", "--num-gpu", "--gpu_num", "--dump-time-csv-prefix",
                     "--dump-graph-json-prefix", "--dump-graph-dot-prefix", "--secret-key"):
         sp.add_argument(ignored, help=argparse.SUPPRESS)
     for ignored in ("--show-combinational-progress", "--enable-gpu", "--no-stdout-csv"):
@@ -119,7 +121,7 @@ def _run(args, mode):
         log(f"{mode} on {world} process(es): {fe.nl.n} nodes, {fe.eng.num_levels} levels, {fe.eng.bootstraps_per_cycle} bootstraps/cycle, "
             f"{fe.eng.num_dff} DFF; running {cycles} cycle(s) from cycle {fe.cycle}")
         t0 = time.time()
-        fe.run(cycles, skip_reset=args.skip_reset)
+        fe.run(cycles, skip_reset=args.skip_reset, dump_prefix=args.dump_prefix)
         log(f"done. ({int((time.time() - t0) * 1e6)} us)")
         res = fe.result()
         if rank == 0:

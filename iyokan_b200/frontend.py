@@ -140,7 +140,10 @@ class Frontend:
                 self._set(self.nl.mem[name], np.asarray(v))
 
     # ---- protocol ----
-    def run(self, cycles: int, skip_reset: bool = False):
+    def run(self, cycles: int, skip_reset: bool = False, dump_prefix: str | None = None):
+        """dump_prefix: write the result packet after every cycle to `<prefix>-<cycle>` (iyokan --dump-prefix,
+        src/iyokan_tfhepp.cpp:520-533; the reference decrypts the dumps with --secret-key, here they stay encrypted in
+        tfhe mode: key material never enters the back-end - run `iyokan-packet dec` on them)."""
         if cycles < 0:
             raise FrontendError("number of cycles must be >= 0")
         has_reset = "reset" in self.nl.in_ports
@@ -162,6 +165,8 @@ class Frontend:
                 self._set(nodes, stream[[(w * c + b) % len(stream) for b in range(w)]])
             self._eval()
             self.cycle += 1
+            if dump_prefix and self.rank == 0:
+                self.result().save(f"{dump_prefix}-{self.cycle}")
         if self.mode == "tfhe":
             self.ctx.sync()
 

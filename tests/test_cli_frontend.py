@@ -84,6 +84,17 @@ def test_snapshot_resume_equals_one_run(tmp_path):
     assert run_cli("plain", "--resume", req, "-o", tmp_path / "x", "-c", 1) == 1
 
 
+def test_dump_prefix_writes_one_packet_per_cycle(tmp_path):
+    # test.rb "cahp-diamond-dump-prefix-00" in miniature: --dump-prefix P leaves P-1 ... P-N behind
+    (tmp_path / "req.in").write_text("cycles = 4\n")
+    assert run_cli("plain", "--blueprint", FIX / "counter-2bit.toml", "-i", tmp_path / "req.in", "-o", tmp_path / "res",
+                   "--dump-prefix", tmp_path / "dump", "--quiet") == 0
+    for c, want in ((1, 0), (2, 1), (3, 2), (4, 3)):
+        p = PlainPacket.load(f"{tmp_path / 'dump'}-{c}")
+        assert p.num_cycles == c and word(p.bits["out"]) == want
+    assert (tmp_path / "res").read_bytes() == Path(f"{tmp_path / 'dump'}-4").read_bytes()
+
+
 def test_error_behaviour(tmp_path):
     bp = FIX / "counter-2bit.toml"
     (tmp_path / "bad.in").write_text('[[bits]]\nname = "nosuchport"\nsize = 1\nbytes = [1]\n')

@@ -63,6 +63,10 @@ def test_rom_ram_builtins_and_circular_inputs(tmp_path):
     assert ram == [rom_words[1], rom_words[2], 0, 0]
     assert word(res.bits["rdata"]) == ram[0]
     assert "rom" not in res.ram and res.num_cycles == 4
+    # declared with CMUX memories (type = "rom" / "ram") the design is built from the same MUX circuits
+    assert run_cli("plain", "--blueprint", FIX / "lookup-cmux.toml", "-i", tmp_path / "req", "-o", tmp_path / "res_cmux",
+                   "-c", 4, "--quiet") == 0
+    assert (tmp_path / "res_cmux").read_bytes() == (tmp_path / "res").read_bytes()
     # packet <-> TOML round trip (iyokan-packet packet2toml / toml2packet)
     assert run_cli("packet", "packet2toml", "--in", tmp_path / "res", "--out", tmp_path / "res.toml") == 0
     assert run_cli("packet", "toml2packet", "--in", tmp_path / "res.toml", "--out", tmp_path / "res2") == 0

@@ -69,3 +69,40 @@ def test_launch_plan_covers_every_frontier_size():
     assert plan_rotation(148 + 20) == [(4, 1, 148), (6, 1, 20)]
     assert plan_rotation(8192) == [(3, 6, 7992), (4, 1, 148), (6, 1, 52)]
     assert plan_rotation(0) == []
+
+
+def test_headers_are_plain_c(tmp_path):
+    # the drop-in boundary is a C ABI: both headers must compile as C99 (no C++-isms, no CUDA or torch types) and a C
+    # caller must link against the libraries
+    import shutil
+    import subprocess
+
+    from iyokan_b200 import build as B
+
+    B.build_cuda()
+    B.build_host()
+    cc = "/usr/bin/gcc" if shutil.which("/usr/bin/gcc") else "gcc"
+    src = tmp_path / "caller.c"
+    src.write_text('''
+#include "b200fhe.h"
+#include "b200net.h"
+#include <stdio.h>
+int main(void) {
+    b200fhe_ctx *ctx = 0;
+    int variant[4], g[4], jobs[4];
+    int n = b200fhe_plan_rotation(8192, variant, g, jobs, 4);
+    printf("%d segments, %.2f ms modelled\\n", n, b200fhe_plan_ms(8192));
+    if (b200fhe_create(&ctx, 0) != 0) { printf("no device: %s\\n", b200fhe_last_error()); return n == 3 ? 0 : 1; }
+    b200fhe_destroy(ctx);
+    return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    csrc, host = ROOT / "iyokan_b200" / "csrc", ROOT / "iyokan_b200" / "host"
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{ROOT / 'include'}", str(src), "-o", str(exe),
+                        f"-L{csrc}", "-lb200fhe", f"-L{host}", "-lb200net", f"-Wl,-rpath,{csrc}", f"-Wl,-rpath,{host}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "3 segments" in r.stdout

@@ -173,6 +173,8 @@ def read_blueprint(toml_path, mux_ram_json_dir=None):
             outs = mux_rom(b, addr, bi["out_rdata_width"], name=name)
             sn.outputs["rdata"] = {i: b._add(34, o) for i, o in enumerate(outs)}
         elif bi["type"] in ("mux-ram", "ram"):
+            if bi["type"] == "ram":
+                b.write_through.append(name)
             a, w, r = bi["in_addr_width"], bi["in_wdata_width"], bi["out_rdata_width"]
             assert w == r
             pre = Path(mux_ram_json_dir) / f"mux-ram-{a}-{w}-{r}.min.json" if mux_ram_json_dir else None

@@ -141,9 +141,11 @@ class Frontend:
 
     # ---- protocol ----
     def run(self, cycles: int, skip_reset: bool = False, dump_prefix: str | None = None):
-        """dump_prefix: write the result packet after every cycle to `<prefix>-<cycle>` (iyokan --dump-prefix,
-        src/iyokan_tfhepp.cpp:520-533; the reference decrypts the dumps with --secret-key, here they stay encrypted in
-        tfhe mode: key material never enters the back-end - run `iyokan-packet dec` on them)."""
+        """dump_prefix: before every cycle c the state reached so far is written as a result packet to `<prefix>-<c>`
+        (c = cycles executed: `-0` is the state after the reset pass; the final state is the -o packet), as
+        iyokan --dump-prefix does (src/iyokan_tfhepp.cpp:520-533).  The reference decrypts the dumps with
+        --secret-key; here they stay encrypted in tfhe mode - key material never enters the back-end - and
+        `iyokan-packet dec` opens them."""
         if cycles < 0:
             raise FrontendError("number of cycles must be >= 0")
         has_reset = "reset" in self.nl.in_ports
@@ -153,6 +155,8 @@ class Frontend:
         self.reset_done = True
         for _ in range(cycles):
             c = self.cycle
+            if dump_prefix and self.rank == 0:
+                self.result().save(f"{dump_prefix}-{c}")
             self._tick()
             if c == 0:
                 if has_reset:
@@ -165,15 +169,21 @@ class Frontend:
                 self._set(nodes, stream[[(w * c + b) % len(stream) for b in range(w)]])
             self._eval()
             self.cycle += 1
-            if dump_prefix and self.rank == 0:
-                self.result().save(f"{dump_prefix}-{self.cycle}")
         if self.mode == "tfhe":
             self.ctx.sync()
 
     def result(self):
         """Result packet: OUTPUT ports, RAM cells (ROM is not returned), numCycles."""
         out = {p: self._get(nodes) for p, nodes in self.nl.out_ports.items()}
-        ram = {m: self._get(nodes) for m, nodes in self.nl.mem.items() if self.nl.kind[nodes[0]] == DFF}
+        ram = {}
+        for m, nodes in self.nl.mem.items():
+            if self.nl.kind[nodes[0]] != DFF:
+                continue
+            if m in self.nl.write_through and self.cycle > 0:
+                # CMUX RAM semantics: the write of the last cycle is already part of the memory image; in the MUX
+                # formulation that value sits on the cells' D inputs until the next tick
+                nodes = [int(self.nl.in0[n]) for n in nodes]
+            ram[m] = self._get(nodes)
         if self.mode == "plain":
             return PlainPacket(ram=ram, bits=out, num_cycles=self.cycle)
         return TFHEPacket(ram_in_tlwe=ram, bits=out, num_cycles=self.cycle)
@@ -182,6 +192,7 @@ class Frontend:
     def snapshot(self, path):
         meta = {"magic": SNAPSHOT_MAGIC, "mode": self.mode, "cycle": self.cycle, "reset_done": self.reset_done,
                 "in_ports": self.nl.in_ports, "out_ports": self.nl.out_ports, "mem": self.nl.mem,
+                "write_through": self.nl.write_through,
                 "streams": sorted(self.streams), "rams": sorted(self.rams)}
         arrays = {"kind": self.nl.kind, "in0": self.nl.in0, "in1": self.nl.in1, "in2": self.nl.in2,
                   "state": self._get(self._all),
@@ -212,7 +223,8 @@ class Frontend:
             raise FrontendError(f"Invalid resume file: {path}")
         z = np.load(path)
         meta = json.loads(bytes(z["meta"]).decode())
-        nl = Netlist(z["kind"], z["in0"], z["in1"], z["in2"], meta["in_ports"], meta["out_ports"], meta["mem"])
+        nl = Netlist(z["kind"], z["in0"], z["in1"], z["in2"], meta["in_ports"], meta["out_ports"], meta["mem"],
+                     meta.get("write_through", []))
         fe = Frontend(nl, meta["mode"], ctx, rank, world, group)
         fe.cycle, fe.reset_done = int(meta["cycle"]), bool(meta["reset_done"])
         fe.streams = {k: z[f"stream__{k}"] for k in meta["streams"]}

@@ -306,7 +306,12 @@ int main(int argc, char** argv)
     }
     for (const auto& ram : bp.builtinRAMs()) {
         const size_t n = (size_t(1) << ram.inAddrWidth) * ram.outRdataWidth;
-        res.ramInTLWE.emplace(ram.name, get(memNodes(ram.name, "ram", "ramdata", n)));
+        auto nodes = memNodes(ram.name, "ram", "ramdata", n);
+        // A CMUX RAM is updated during the cycle (its image already holds the last cycle's write); the MUX RAM that
+        // stands in for it keeps that value on the cells' D inputs until the next tick: report those.
+        if (ram.type == blueprint::BuiltinRAM::TYPE::CMUX_MEMORY && numCycles > 0)
+            for (auto& v : nodes) v = (uint32_t)d.in0[v];
+        res.ramInTLWE.emplace(ram.name, get(nodes));
     }
     writeToArchive(outPath, res);
     b200net_destroy(net);

@@ -32,6 +32,7 @@ class NetBuilder:
         self.in_ports: dict[str, list[int]] = {}
         self.out_ports: dict[str, list[int]] = {}
         self.mem: dict[str, list[int]] = {}
+        self.write_through: list[str] = []
 
     def _add(self, kind, *ins):
         self.kind.append(kind)
@@ -76,7 +77,7 @@ class NetBuilder:
         ins = np.array(self.ins, dtype=np.int32).reshape(-1, 3)
         return Netlist(np.array(self.kind, np.uint8), ins[:, 0].copy(), ins[:, 1].copy(), ins[:, 2].copy(),
                        {k: list(v) for k, v in self.in_ports.items()}, {k: list(v) for k, v in self.out_ports.items()},
-                       {k: list(v) for k, v in self.mem.items()})
+                       {k: list(v) for k, v in self.mem.items()}, list(self.write_through))
 
 
 @dataclass
@@ -88,13 +89,18 @@ class Netlist:
     in_ports: dict = field(default_factory=dict)    # external input port -> INPUT node per bit
     out_ports: dict = field(default_factory=dict)   # external output port -> node per bit
     mem: dict = field(default_factory=dict)         # "ram"/"rom" name -> node per memory bit (DFF or INPUT)
+    # RAMs declared as CMUX memories in the blueprint: the reference updates them DURING the cycle (the result packet
+    # shows the last cycle's write), whereas a MUX RAM cell changes at the next tick; for these names the result is
+    # read from the cells' next-state inputs (see Frontend.result)
+    write_through: list = field(default_factory=list)
 
     @property
     def n(self):
         return int(self.kind.size)
 
     def save(self, path):
-        meta = json.dumps({"in_ports": self.in_ports, "out_ports": self.out_ports, "mem": self.mem})
+        meta = json.dumps({"in_ports": self.in_ports, "out_ports": self.out_ports, "mem": self.mem,
+                           "write_through": self.write_through})
         np.savez_compressed(path, kind=self.kind, in0=self.in0, in1=self.in1, in2=self.in2,
                             meta=np.frombuffer(meta.encode(), dtype=np.uint8))
 
@@ -102,7 +108,8 @@ class Netlist:
     def load(path) -> "Netlist":
         z = np.load(path)
         meta = json.loads(bytes(z["meta"]).decode())
-        return Netlist(z["kind"], z["in0"], z["in1"], z["in2"], meta["in_ports"], meta["out_ports"], meta["mem"])
+        return Netlist(z["kind"], z["in0"], z["in1"], z["in2"], meta["in_ports"], meta["out_ports"], meta["mem"],
+                       meta.get("write_through", []))
 
 
 # ---- generators (self-contained circuits for tests; structure follows the reference's descriptions) ----

@@ -21,6 +21,7 @@ LIB_PATH = HERE / "libtfhe_oracle.so"
 REF_DRIVER = HERE / "_ref" / "ref_driver"
 IYOKAN_PACKET = HERE / "_ref" / "iyokan-packet"   # the reference's own packet tool, built unmodified
 REF_LINK_TEST = HERE / "_ref" / "b200_gate_test"  # tests/ref_link/b200_gate_test.cpp: TFHEpp types over the C ABI
+IYOKAN_REF = HERE / "_ref" / "iyokan"             # the reference's own iyokan (plain + tfhe on CPU), built unmodified
 IYOKAN_B200 = HERE / "_ref" / "iyokan-b200"       # iyokan_b200/host/iyokan_b200_main.cpp: the reference's loader + our engine
 
 N0, N1, L, T = 636, 1024, 3, 7
@@ -60,6 +61,8 @@ def build(force: bool = False) -> None:
         if (force or not REF_DRIVER.exists() or not IYOKAN_PACKET.exists()
                 or REF_DRIVER.stat().st_mtime < (HERE / "ref_driver.cpp").stat().st_mtime):
             subprocess.run(["make", "-C", str(HERE), "-j8", "ref"], check=True, capture_output=True)
+        if force or not IYOKAN_REF.exists():
+            subprocess.run(["make", "-C", str(HERE), "-j4", "refbin"], check=True, capture_output=True)
         # reference-side binding test (TFHEpp types + the product's C ABI); needs the CUDA library built first
         so = HERE.parent / "iyokan_b200" / "csrc" / "libb200fhe.so"
         src = HERE.parent / "tests" / "ref_link" / "b200_gate_test.cpp"
@@ -226,6 +229,11 @@ def keyswitch(keys: Keys, u) -> np.ndarray:
 def num_bootstraps(ops) -> int:
     ops = np.asarray(ops, dtype=np.uint8)
     return int(((ops <= 7) | (ops >= 13)).sum() + 2 * (ops == 8).sum())
+
+
+def iyokan_ref(*args, timeout=1800) -> subprocess.CompletedProcess:
+    """Run the reference's own `iyokan` binary (oracle/_ref/iyokan)."""
+    return subprocess.run([str(IYOKAN_REF), *map(str, args)], capture_output=True, text=True, timeout=timeout)
 
 
 def have_ref() -> bool:

@@ -53,6 +53,15 @@ def plain_gate_vec(ops, a, b, c) -> np.ndarray:
     return out
 
 
+def _optional(cmd) -> None:
+    """Build step whose product only enables extra tests: a failure is reported, not fatal."""
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        import sys
+
+        print(f"oracle.build: optional step {' '.join(cmd[-2:])} failed:\n{r.stderr[-1500:]}", file=sys.stderr)
+
+
 def build(force: bool = False) -> None:
     """Compile the C restatement (and the reference driver when the reference tree exists)."""
     if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < (HERE / "tfhe_oracle.c").stat().st_mtime:
@@ -61,8 +70,8 @@ def build(force: bool = False) -> None:
         if (force or not REF_DRIVER.exists() or not IYOKAN_PACKET.exists()
                 or REF_DRIVER.stat().st_mtime < (HERE / "ref_driver.cpp").stat().st_mtime):
             subprocess.run(["make", "-C", str(HERE), "-j8", "ref"], check=True, capture_output=True)
-        if force or not IYOKAN_REF.exists():
-            subprocess.run(["make", "-C", str(HERE), "-j4", "refbin"], check=True, capture_output=True)
+        if force or not IYOKAN_REF.exists():  # optional: the differential tests skip without it
+            _optional(["make", "-C", str(HERE), "-j4", "refbin"])
         # reference-side binding test (TFHEpp types + the product's C ABI); needs the CUDA library built first
         so = HERE.parent / "iyokan_b200" / "csrc" / "libb200fhe.so"
         src = HERE.parent / "tests" / "ref_link" / "b200_gate_test.cpp"
@@ -71,7 +80,7 @@ def build(force: bool = False) -> None:
         if all(d.exists() for d in deps) and (force or not REF_LINK_TEST.exists() or not IYOKAN_B200.exists()
                                               or min(REF_LINK_TEST.stat().st_mtime, IYOKAN_B200.stat().st_mtime)
                                               < max(d.stat().st_mtime for d in deps)):
-            subprocess.run(["make", "-C", str(HERE), "-j4", "reflink"], check=True, capture_output=True)
+            _optional(["make", "-C", str(HERE), "-j4", "reflink"])
 
 
 _lib = None

@@ -63,8 +63,10 @@ def read_yosys(b: NetBuilder, path) -> SubNet:
         driver[con["Q" if t == "$_DFF_P_" else "Y"][0]] = n
     const = {}
 
-    def src(bit):
-        if isinstance(bit, str):  # constant driver "0" / "1" (iyokan.hpp:2170-2193)
+    def src(bit, port=False):
+        if isinstance(bit, str):  # constant driver "0" / "1": allowed on output ports only (iyokan.hpp:2170-2193)
+            if not port:
+                raise ValueError("Connection of cells to a constant driver is not implemented.")  # iyokan.hpp:2124
             if bit not in const:
                 const[bit] = b.gate("CONST1" if bit == "1" else "CONST0")
             return const[bit]
@@ -84,7 +86,7 @@ def read_yosys(b: NetBuilder, path) -> SubNet:
         if port["direction"] != "output":
             continue
         for i, bit in enumerate(port["bits"]):
-            sn.outputs.setdefault(pname, {})[i] = b._add(34, src(bit))  # OUTPUT wire
+            sn.outputs.setdefault(pname, {})[i] = b._add(34, src(bit, port=True))  # OUTPUT wire
     return sn
 
 

@@ -72,3 +72,20 @@ def build_host(force: bool = False) -> Path:
     if r.returncode != 0:
         raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
     return out
+
+
+def build_microbench(force: bool = False) -> list:
+    """Stand-alone micro-benchmarks (scripts/microbench/*.cu -> binaries next to the sources; run by scripts/gpu_round.sh)."""
+    outs = []
+    mb = ROOT / "scripts" / "microbench"
+    for src in sorted(mb.glob("*.cu")):
+        out = src.with_suffix("")
+        outs.append(out)
+        if not force and _newer(out, [src] + list(CSRC.glob("*.h"))):
+            continue
+        cmd = [_nvcc(), "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+               "--expt-relaxed-constexpr", "-o", str(out), str(src)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    return outs

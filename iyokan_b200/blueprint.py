@@ -70,6 +70,8 @@ def read_yosys(b: NetBuilder, path) -> SubNet:
             if bit not in const:
                 const[bit] = b.gate("CONST1" if bit == "1" else "CONST0")
             return const[bit]
+        if bit not in driver:
+            raise ValueError(f"Invalid JSON of network: signal {bit} has no driver")
         return driver[bit]
 
     for c, n in zip(cells, ids):
@@ -137,6 +139,8 @@ PORT_RE = re.compile(r"^(@?)([^/\[\]]+)(?:/([^\[\]]+))?(?:\[(\d+)(?::(\d+))?\])?
 
 def parse_ref(s):
     m = PORT_RE.match(s.strip())
+    if m is None:
+        raise ValueError(f"Invalid port string: {s}")   # NetworkBlueprint::parsePortString, iyokan.hpp:1697
     ext, a, bname, lo, hi = m.groups()
     lo = int(lo) if lo is not None else 0
     hi = int(hi) if hi is not None else lo
@@ -193,28 +197,38 @@ def read_blueprint(toml_path, mux_ram_json_dir=None):
         else:
             raise ValueError(f"unknown builtin type {bi['type']!r}")
         subs[name] = sn
+    def port(net, kind, name, bit):
+        """Node of net/name[bit]; the reference dies with these messages in TaskNetwork::get (iyokan.hpp:955-980)."""
+        if net not in subs:
+            raise ValueError(f"Invalid network name: {net}")
+        table = subs[net].inputs if kind == "input" else subs[net].outputs
+        if name not in table or bit not in table[name]:
+            raise ValueError(f"Invalid {kind} port: {net}/{name}[{bit}]")
+        return table[name][bit]
+
     connect = dict(bp.get("connect", {}))
     togrnd = connect.pop("TOGND", [])
     for dst, src in connect.items():
         if not isinstance(src, str) or not dst or not src or (dst[0] == "@" and src[0] == "@"):
             raise ValueError(f"Invalid connect: {dst} = {src}")
         d, s = parse_ref(dst), parse_ref(src)
-        assert len(d[2]) == len(s[2]), (dst, src)
+        if len(d[2]) != len(s[2]):
+            raise ValueError(f"Invalid connect: {dst} = {src}")
         for db, sb in zip(d[2], s[2]):
             if d[0] == "@":      # external output  "@out[i]" = "net/port[j]"
                 lst = b.out_ports.setdefault(d[1], [])
                 lst.extend([-1] * (db + 1 - len(lst)))
-                lst[db] = subs[s[0]].outputs[s[1]][sb]
+                lst[db] = port(s[0], "output", s[1], sb)
             elif s[0] == "@":    # external input   "net/port[i]" = "@in[j]"
                 lst = b.in_ports.setdefault(s[1], [])
                 lst.extend([-1] * (sb + 1 - len(lst)))
-                node = subs[d[0]].inputs[d[1]][db]
+                node = port(d[0], "input", d[1], db)
                 if lst[sb] == -1:
                     lst[sb] = node
                 else:            # one external bit feeding several inputs: alias the later ones
                     b.alias(node, lst[sb])
             else:                # internal edge: the consumer's INPUT wire becomes an alias of the producer
-                b.alias(subs[d[0]].inputs[d[1]][db], subs[s[0]].outputs[s[1]][sb])
+                b.alias(port(d[0], "input", d[1], db), port(s[0], "output", s[1], sb))
     # TOGND = ["@port[n:m]", ...]: bits that belong to an external port (they count for its width, hence for the
     # stride of its bit stream) but are connected to nothing (iyokan.hpp:1809-1825)
     for ref in togrnd:

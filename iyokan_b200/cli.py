@@ -131,7 +131,7 @@ def _run(args, mode):
         if rank == 0 and args.stdout_csv and mode == "plain":
             for name in sorted(res.bits):
                 print(f"{fe.cycle},{name},{sum(int(b) << i for i, b in enumerate(res.bits[name]))}")
-    except (FrontendError, PacketError, ValueError, OSError) as e:
+    except (FrontendError, PacketError, ValueError, KeyError, OSError) as e:
         die(e)
     finally:
         if world > 1:

@@ -210,3 +210,40 @@ def test_reference_test_rb_cases_plain(tmp_path, bp, fin, fout, cycles):
         assert np.array_equal(got.bits[name][:bits.size], bits), name
     for name, bits in want.ram.items():
         assert np.array_equal(got.ram[name][:bits.size], bits), name
+
+
+def test_blueprint_loader_rejects_what_the_reference_rejects(tmp_path):
+    """Error behaviour of the loader (NetworkBlueprint / YosysJSONReader die() cases, src/iyokan.hpp:1731-1895,2124)."""
+    import json
+
+    good = json.loads((FIX / "counter-2bit-yosys.json").read_text())
+
+    def design(mutate):
+        d = json.loads(json.dumps(good))
+        mutate(d["modules"]["Counter2"])
+        (tmp_path / "d.json").write_text(json.dumps(d))
+        (tmp_path / "d.toml").write_text('[[file]]\ntype = "yosys-json"\npath = "d.json"\nname = "core"\n[connect]\n'
+                                         '"core/reset" = "@reset"\n"@out[0:1]" = "core/io_out[0:1]"\n')
+        return tmp_path / "d.toml"
+
+    with pytest.raises(ValueError, match="constant driver"):      # a cell input tied to a constant
+        B.read_blueprint(design(lambda m: m["cells"]["inc0"]["connections"].update(A=["1"])))
+    with pytest.raises(ValueError, match="unsupported cell type"):  # e.g. a latch or an $_SDFF_ cell
+        B.read_blueprint(design(lambda m: m["cells"]["q0"].update(type="$_DLATCH_P_")))
+    with pytest.raises(ValueError, match="no driver"):              # a signal nobody drives
+        B.read_blueprint(design(lambda m: m["cells"]["inc1"]["connections"].update(B=[99])))
+    (tmp_path / "both.toml").write_text('[connect]\n"@a" = "@b"\n')
+    with pytest.raises(ValueError, match="Invalid connect"):
+        B.read_blueprint(tmp_path / "both.toml")
+    (tmp_path / "gnd.toml").write_text('[connect]\nTOGND = ["core/x[0:3]"]\n')
+    with pytest.raises(ValueError, match="TOGND"):
+        B.read_blueprint(tmp_path / "gnd.toml")
+    (tmp_path / "nonet.toml").write_text('[connect]\n"@out" = "ghost/io_out"\n')
+    with pytest.raises(ValueError, match="Invalid network name"):
+        B.read_blueprint(tmp_path / "nonet.toml")
+    with pytest.raises(ValueError, match="Invalid output port"):
+        B.read_blueprint(design(lambda m: m["ports"].pop("io_out")))
+    # and the command line turns every one of them into exit status 1 with a message, never a traceback
+    (tmp_path / "req.in").write_text("cycles = 1\n")
+    assert run_cli("plain", "--blueprint", tmp_path / "both.toml", "-i", tmp_path / "req.in", "-o", tmp_path / "r", "-c", 1) == 1
+    assert run_cli("plain", "--blueprint", tmp_path / "nonet.toml", "-i", tmp_path / "req.in", "-o", tmp_path / "r", "-c", 1) == 1

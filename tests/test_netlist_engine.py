@@ -84,3 +84,30 @@ def test_net_abi_exports():
     assert sorted(N.NET_EXPORTS) == names
     for n in names:
         assert hasattr(h, n)
+
+
+def test_cost_model_reproduces_the_measured_clock_cycles():
+    """scripts/model_netlist.py (launch-plan model + sharding policy, no GPU) against the clocks measured on 1, 2, 4 and 8
+    B200s and committed under profiles/: within 12 %, and the number of collectives per clock exactly."""
+    import importlib.util
+    import json
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    spec = importlib.util.spec_from_file_location("model_netlist", root / "scripts" / "model_netlist.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    checked = 0
+    for case in ("cahp-pearl-mux", "cahp-ruby-mux", "mux-ram-8-16-16"):
+        nl = N.Netlist.load(NL / f"{case}.npz")
+        for n in (1, 2, 4, 8):
+            log = root / "profiles" / f"r01_net_{case}_n{n}.log"
+            if not log.exists():
+                continue
+            meas = json.loads(log.read_text().strip().splitlines()[-1])
+            m = mod.model(nl, n)
+            assert abs(m["ms_per_cycle"] / 1e3 - meas["s_per_cycle"]) / meas["s_per_cycle"] < 0.12, (case, n, m, meas)
+            assert m["collectives"] == meas["collectives_per_cycle"], (case, n)
+            assert m["bootstraps_per_cycle"] == meas["bootstraps_per_cycle"]
+            checked += 1
+    assert checked >= 6

@@ -32,16 +32,16 @@ def run_cli(*argv):
 
 
 def test_counter_blueprint_yosys_reader_and_protocol(tmp_path):
-    nl = B.read_blueprint(FIX / "counter-2bit.toml")
+    nl = B.read_blueprint(FIX / "upcount2.toml")
     assert sorted(nl.in_ports) == ["reset"] and sorted(nl.out_ports) == ["one", "out"]
     (tmp_path / "req.in").write_text("cycles = 3\n")
     for cycles, want in ((1, 0), (2, 1), (3, 2), (6, 1)):
-        assert run_cli("plain", "--blueprint", FIX / "counter-2bit.toml", "-i", tmp_path / "req.in", "-o",
+        assert run_cli("plain", "--blueprint", FIX / "upcount2.toml", "-i", tmp_path / "req.in", "-o",
                        tmp_path / "res", "-c", cycles, "--quiet") == 0
         res = PlainPacket.load(tmp_path / "res")
         assert res.num_cycles == cycles and word(res.bits["out"]) == want and word(res.bits["one"]) == 1
     # cycles from the packet when -c is absent
-    assert run_cli("plain", "--blueprint", FIX / "counter-2bit.toml", "-i", tmp_path / "req.in", "-o", tmp_path / "res",
+    assert run_cli("plain", "--blueprint", FIX / "upcount2.toml", "-i", tmp_path / "req.in", "-o", tmp_path / "res",
                    "--quiet") == 0
     assert word(PlainPacket.load(tmp_path / "res").bits["out"]) == 2
 
@@ -85,7 +85,7 @@ def test_rom_ram_builtins_and_circular_inputs(tmp_path):
 
 
 def test_snapshot_resume_equals_one_run(tmp_path):
-    bp, req = FIX / "counter-2bit.toml", tmp_path / "req.in"
+    bp, req = FIX / "upcount2.toml", tmp_path / "req.in"
     req.write_text("cycles = 1\n")
     assert run_cli("plain", "--blueprint", bp, "-i", req, "-o", tmp_path / "a", "-c", 5, "--quiet") == 0
     assert run_cli("plain", "--blueprint", bp, "-i", req, "-o", tmp_path / "b1", "-c", 2, "--snapshot", tmp_path / "snap",
@@ -103,7 +103,7 @@ def test_dump_prefix_writes_one_packet_per_cycle(tmp_path):
     # test.rb "cahp-diamond-dump-prefix-00" in miniature: --dump-prefix P leaves P-0 ... P-(N-1) behind, P-c being the
     # state after c cycles (same numbering as the reference: tests/test_reference_binary.py compares them file by file)
     (tmp_path / "req.in").write_text("cycles = 4\n")
-    assert run_cli("plain", "--blueprint", FIX / "counter-2bit.toml", "-i", tmp_path / "req.in", "-o", tmp_path / "res",
+    assert run_cli("plain", "--blueprint", FIX / "upcount2.toml", "-i", tmp_path / "req.in", "-o", tmp_path / "res",
                    "--dump-prefix", tmp_path / "dump", "--quiet") == 0
     for c, want in ((1, 0), (2, 1), (3, 2)):
         p = PlainPacket.load(f"{tmp_path / 'dump'}-{c}")
@@ -113,7 +113,7 @@ def test_dump_prefix_writes_one_packet_per_cycle(tmp_path):
 
 
 def test_error_behaviour(tmp_path):
-    bp = FIX / "counter-2bit.toml"
+    bp = FIX / "upcount2.toml"
     (tmp_path / "bad.in").write_text('[[bits]]\nname = "nosuchport"\nsize = 1\nbytes = [1]\n')
     assert run_cli("plain", "--blueprint", bp, "-i", tmp_path / "bad.in", "-o", tmp_path / "r", "-c", 1) == 1
     (tmp_path / "rst.in").write_text('[[bits]]\nname = "reset"\nsize = 1\nbytes = [1]\n')
@@ -130,7 +130,7 @@ def test_error_behaviour(tmp_path):
 
 def test_module_entry_point(tmp_path):
     (tmp_path / "req.in").write_text("cycles = 2\n")
-    r = subprocess.run([sys.executable, "-m", "iyokan_b200", "plain", "--blueprint", str(FIX / "counter-2bit.toml"), "-i",
+    r = subprocess.run([sys.executable, "-m", "iyokan_b200", "plain", "--blueprint", str(FIX / "upcount2.toml"), "-i",
                         str(tmp_path / "req.in"), "-o", str(tmp_path / "res"), "--stdout-csv"], cwd=ROOT,
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
@@ -216,14 +216,14 @@ def test_blueprint_loader_rejects_what_the_reference_rejects(tmp_path):
     """Error behaviour of the loader (NetworkBlueprint / YosysJSONReader die() cases, src/iyokan.hpp:1731-1895,2124)."""
     import json
 
-    good = json.loads((FIX / "counter-2bit-yosys.json").read_text())
+    good = json.loads((FIX / "upcount2-netlist.json").read_text())
 
     def design(mutate):
         d = json.loads(json.dumps(good))
-        mutate(d["modules"]["Counter2"])
+        mutate(d["modules"]["UpCount2"])
         (tmp_path / "d.json").write_text(json.dumps(d))
         (tmp_path / "d.toml").write_text('[[file]]\ntype = "yosys-json"\npath = "d.json"\nname = "core"\n[connect]\n'
-                                         '"core/reset" = "@reset"\n"@out[0:1]" = "core/io_out[0:1]"\n')
+                                         '"core/reset" = "@reset"\n"@out[0:1]" = "core/io_q[0:1]"\n')
         return tmp_path / "d.toml"
 
     with pytest.raises(ValueError, match="constant driver"):      # a cell input tied to a constant
@@ -242,7 +242,7 @@ def test_blueprint_loader_rejects_what_the_reference_rejects(tmp_path):
     with pytest.raises(ValueError, match="Invalid network name"):
         B.read_blueprint(tmp_path / "nonet.toml")
     with pytest.raises(ValueError, match="Invalid output port"):
-        B.read_blueprint(design(lambda m: m["ports"].pop("io_out")))
+        B.read_blueprint(design(lambda m: m["ports"].pop("io_q")))
     # and the command line turns every one of them into exit status 1 with a message, never a traceback
     (tmp_path / "req.in").write_text("cycles = 1\n")
     assert run_cli("plain", "--blueprint", tmp_path / "both.toml", "-i", tmp_path / "req.in", "-o", tmp_path / "r", "-c", 1) == 1

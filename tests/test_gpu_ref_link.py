@@ -35,7 +35,7 @@ def test_binding_fails_loudly_without_a_gpu():
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not (O.IYOKAN_B200.exists() and O.have_iyokan_packet()), reason="oracle/_ref/iyokan-b200 not built")
-@pytest.mark.parametrize("blueprint,cycles", [("lookup.toml", 4), ("lookup-cmux.toml", 4), ("counter-2bit.toml", 3)])
+@pytest.mark.parametrize("blueprint,cycles", [("lookup.toml", 4), ("lookup-cmux.toml", 4), ("upcount2.toml", 3)])
 def test_iyokan_b200_binary_with_the_reference_loader(tmp_path, blueprint, cycles):
     """`iyokan-b200 tfhe`: the reference's own blueprint / Yosys / MUX-memory loader and packet code (compiled from
     its sources) in front of the B200 engine, against keys and packets made by the reference's iyokan-packet; the

@@ -39,7 +39,7 @@ def same_packet(a: PlainPacket, b: PlainPacket):
 
 
 @needs_ref
-@pytest.mark.parametrize("blueprint,cycles", [("counter-2bit.toml", 5), ("lookup.toml", 6), ("lookup-cmux.toml", 6)])
+@pytest.mark.parametrize("blueprint,cycles", [("upcount2.toml", 5), ("lookup.toml", 6), ("lookup-cmux.toml", 6)])
 def test_plain_mode_equals_the_reference_binary(tmp_path, blueprint, cycles):
     req = lookup_request() if blueprint.startswith("lookup") else PlainPacket()
     (tmp_path / "req.toml").write_text(req.to_toml())

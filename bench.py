@@ -37,12 +37,12 @@ BATCH = 8192
 WORKLOAD = ("batched HomNAND microbench: 8192 independent gate bootstraps per GPU, "
             "128-bit params (n=636, N=1024, l=3, Bgbit=6, t=7) [BASELINE.json configs[1]]")
 BK_BYTES_PER_ROTATION = 636 * 2 * 3 * 2 * 1024 * 8      # 62,521,344
-KS_BYTES_PER_SWITCH = 1024 * 7 * 3 * 637 * 2 * 3 // 4    # 6,849,024 expected rows touched
+KS_BYTES_PER_SWITCH = 1024 * 7 * 637 * 2 * 3 // 4        # 6,849,024: one of three rows per (i, j), 3/4 of them non-zero
 BYTES_PER_BOOTSTRAP = BK_BYTES_PER_ROTATION + KS_BYTES_PER_SWITCH + 3 * 1274   # 69,374,190
 BR_KERNEL_BYTES_PER_JOB = BK_BYTES_PER_ROTATION + 2 * 1274 + 4100               # key stream + TLWE in + lvl1 out
 KEY_SEED = 20261017
-KERNEL_NAMES = {(3, 6): "br3_kernel<6>", (3, 4): "br3_kernel<4>", (3, 2): "br3_kernel<2>", (4, 1): "br4_kernel", (5, 1): "br5_kernel", (6, 1): "br6_kernel",
-                (2, 1): "br2_kernel<1>", (2, 2): "br2_kernel<2>", (1, 4): "br_kernel<4>"}
+KERNEL_NAMES = {(7, 8): "br7_kernel<8>", (3, 6): "br3_kernel<6>", (3, 4): "br3_kernel<4>", (3, 2): "br3_kernel<2>",
+                (4, 1): "br4_kernel", (6, 1): "br6_kernel"}
 
 
 def measured_peak_hbm():

@@ -2,22 +2,24 @@
 //
 // Kernels (all hand-written CUDA, integer arithmetic, no tensor cores — the path is modular
 // integer math; see DESIGN.md for the roofline of each):
-//   br_kernel<G>     blind rotation of G jobs per CTA (br_phases.h)      — the hot kernel
+//   br7_kernel<8>    blind rotation, 8 jobs / 16 warps per CTA (br7_phases.h)   — the hot kernel
+//   br3_kernel<G>    blind rotation, G jobs / 2G warps per CTA, x3 interleave (br_phases.h)
+//   br4_kernel       one job per CTA, br6_kernel one job per 2-CTA cluster: latency shapes for narrow levels
 //   ks_kernel        sample-extracted lvl1 TLWE(s) -> lvl0 TLWE (ks_phases.h)
 //   unary_kernel     NOT / COPY / CONST and the DFF tick gather-copy
 //   bk_prep_kernel   raw TRGSW bootstrapping key -> NTT-domain 3-limb form (once per key)
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/b200fhe.h"
-#include "br2_phases.h"
 #include "br4_phases.h"
-#include "br5_phases.h"
 #include "br6_phases.h"
+#include "br7_phases.h"
 #include "br_phases.h"
 #include "gate_jobs.h"
 #include "ks_phases.h"
@@ -28,71 +30,8 @@ using namespace b200;
 // kernels
 // =====================================================================================
 
-// resident CTAs per SM the register allocator is asked to allow (shared memory permitting)
-constexpr int br_min_blocks(int G) { return G == 1 ? 4 : G == 2 ? 3 : G == 3 ? 2 : 1; }
-
-template <int G>
-__global__ void __launch_bounds__(64 * G, br_min_blocks(G))
-br_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ arena,
-          const uint32_t* __restrict__ bk_ntt, const tw_t* __restrict__ tw2f_g, const tw_t* __restrict__ tw2i_g,
-          uint32_t* __restrict__ ubuf, int n_iter)
-{
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    BrSmem<G> sm;
-    sm.carve(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = warp >> 1, q = warp & 1;
-
-    for (int k = tid; k < TW2_LEN; k += 64 * G) {
-        sm.tw2f[k] = tw2f_g[k];
-        sm.tw2i[k] = tw2i_g[k];
-    }
-    int job = blockIdx.x * G + g;
-    const bool valid = job < njobs;
-    if (!valid) job = njobs - 1;  // duplicate work, keeps every barrier uniform
-    const BrJob jb = jobs[job];
-
-    uint32_t accr[32];
-    br_prologue<G>(sm, jb, arena, g, q, lane, accr);
-    __syncthreads();
-
-    for (int i = 0; i < n_iter; i++) {
-        const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
-        uint32_t bk0[BK_COLS][ROWS];
-        {
-            uint32_t dreg[32];
-            br_rotate_diff<G>(sm, i, g, q, lane, accr, dreg);
-            __syncwarp();  // the accumulator copy shares the first tile with digit 0
-#pragma unroll 1
-            for (int d = 0; d < GL - 1; d++) {
-                br_fwd_a<G>(sm, g, q, lane, d, dreg);
-                __syncwarp();
-                br_fwd_b<G>(sm, g, q, lane, d);
-            }
-            br_fwd_a<G>(sm, g, q, lane, GL - 1, dreg);
-            __syncwarp();
-            pw_load(bk_i, tid, bk0);  // key words of phase M stay in flight during the last pass
-            br_fwd_b<G>(sm, g, q, lane, GL - 1);
-        }
-        __syncthreads();
-        br_pointwise<G>(sm, bk_i, tid, bk0);
-        __syncthreads();
-        {
-            uint32_t sum[32];
-#pragma unroll 1
-            for (int l = 0; l < LIMBS; l++) {
-                br_inv_a<G>(sm, g, q, lane, l);
-                __syncwarp();
-                br_inv_b<G>(sm, g, q, lane, l, sum);
-            }
-            br_acc_update<G>(sm, g, q, lane, sum, accr);
-        }
-        __syncwarp();
-    }
-    if (valid) br_epilogue<G>(sm, g, q, lane, ubuf + (size_t)job * U_STRIDE);
-}
-
-// interleaved variant: same decomposition as br_kernel, but the three transforms a warp owns run in
-// lock step (ct_stage3 / gs_stage3): 3x the ILP per warp and one twiddle fetch for three butterflies
+// 12-warp throughput shape: a warp owns one accumulator polynomial and runs its three transforms in lock step
+// (ct_stage3 / gs_stage3): 3x the ILP per warp and one twiddle fetch for three butterflies
 template <int G>
 __global__ void __launch_bounds__(64 * G, 1)
 br3_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ arena,
@@ -139,91 +78,67 @@ br3_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict
     if (valid) br_epilogue<G>(sm, g, q, lane, ubuf + (size_t)job * U_STRIDE);
 }
 
-// "one warp per transform" variant: 6 warps per job (br2_phases.h)
-constexpr int br2_min_blocks(int G) { return G == 1 ? 4 : G == 2 ? 2 : 1; }
-
 __device__ __forceinline__ void named_barrier_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int G>
-__device__ __forceinline__ void pw2_process(const Br2Smem<G>& sm, int item, const uint32_t (&bkv)[PW2_COLS][ROWS])
-{
-    int j, half;
-    pw2_item(item, j, half);
-    const int off = tile_of_j(j);
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-        uint32_t o[PW2_COLS];
-        pw2_compute<G>(sm, g, off, bkv, o);
-        __syncwarp();  // the partner lane (same position, other column half) has read its operands
-        pw2_store<G>(sm, g, half, off, o);
-    }
-}
-
-template <int G>
-__global__ void __launch_bounds__(192 * G, br2_min_blocks(G))
-br2_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ arena,
+// 16-warp throughput shape (br7_phases.h): eight jobs per CTA on XOR-swizzled tiles, two transforms of a
+// warp in lock step and the third alone so that 512 threads fit the register file (<= 128 each).
+// The CTA is cut into G/J barrier groups of J jobs; group k starts k/(G/J) of a step late (skew_cycles apart).
+template <int G, int J>
+__global__ void __launch_bounds__(64 * G, 1)
+br7_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ arena,
            const uint32_t* __restrict__ bk_ntt, const tw_t* __restrict__ tw2f_g, const tw_t* __restrict__ tw2i_g,
-           uint32_t* __restrict__ ubuf, int n_iter)
+           uint32_t* __restrict__ ubuf, int n_iter, int skew_cycles)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    constexpr int T = 192 * G;
-    Br2Smem<G> sm;
+    Br7Smem<G> sm;
     sm.carve(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = warp / BR2_WARPS_PER_JOB, r = warp % BR2_WARPS_PER_JOB, q = r / GL, d = r % GL;
-    const int barid = 1 + g * 2 + q;  // named barrier of the three warps that share polynomial q of job g
-
-    for (int k = tid; k < TW2_LEN; k += T) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = warp >> 1, q = warp & 1;
+    const int group = g / J, g0 = group * J, tig = tid - 64 * g0;
+    for (int k = tid; k < TW2_LEN; k += 64 * G) {
         sm.tw2f[k] = tw2f_g[k];
         sm.tw2i[k] = tw2i_g[k];
     }
     int job = blockIdx.x * G + g;
     const bool valid = job < njobs;
-    if (!valid) job = njobs - 1;
+    if (!valid) job = njobs - 1;  // duplicate work, keeps every barrier uniform
     const BrJob jb = jobs[job];
-    br2_prologue<G>(sm, jb, arena, g, q, d, lane);
+    uint32_t accr[32];
+    br7_prologue<G>(sm, jb, arena, g, q, lane, accr);
     __syncthreads();
-
+    if (J < G && group > 0 && skew_cycles > 0) {
+        const long long t0 = clock64(), wait = (long long)group * skew_cycles;
+        while (clock64() - t0 < wait) {}
+    }
     for (int i = 0; i < n_iter; i++) {
         const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
-        uint32_t bk0[PW2_COLS][ROWS], bk1[PW2_COLS][ROWS];
-        br2_fwd_a<G>(sm, i, g, q, d, lane);
+        uint32_t bk0[BK_COLS][ROWS];
+        br7_fwd12_a<G>(sm, i, g, q, lane, accr);
         __syncwarp();
+        br7_fwd12_c<G>(sm, g, q, lane);
         {
-            int j, half;
-            pw2_item(tid, j, half);
-            pw2_load(bk_i, j, half, bk0);  // key words of phase M in flight during pass 2
+            uint32_t x0[32];
+            br7_fwd0_a<G>(sm, i, g, q, lane, accr, x0);
+            __syncwarp();  // last read of the accumulator copy that shares tile 3q with digit 0
+            br7_fwd0_b<G>(sm, g, q, lane, x0);
         }
-        br2_fwd_b<G>(sm, g, q, d, lane);
-        __syncthreads();
-        for (int item = tid; item < PW2_ITEMS; item += 2 * T) {
-            const int item1 = item + T, item2 = item + 2 * T;
-            int j, half;
-            if (item1 < PW2_ITEMS) {
-                pw2_item(item1, j, half);
-                pw2_load(bk_i, j, half, bk1);
-            }
-            pw2_process<G>(sm, item, bk0);
-            if (item1 < PW2_ITEMS) {
-                if (item2 < PW2_ITEMS) {
-                    pw2_item(item2, j, half);
-                    pw2_load(bk_i, j, half, bk0);
-                }
-                pw2_process<G>(sm, item1, bk1);
-            }
-        }
-        __syncthreads();
-        br2_inv_a<G>(sm, g, q, d, lane);
         __syncwarp();
-        br2_inv_b<G>(sm, g, q, d, lane);
-        named_barrier_sync(barid, 96);
-        br2_combine<G>(sm, g, q, d, lane);
-        named_barrier_sync(barid, 96);
+        br7_fwd0_c<G>(sm, g, q, lane);
+        pw_load(bk_i, tig, bk0);  // key words of the pointwise stage in flight across the barrier
+        if (J == G) __syncthreads(); else named_barrier_sync(1 + group, 64 * J);
+        br7_pointwise<G, J>(sm, bk_i, g0, tig, bk0);
+        if (J == G) __syncthreads(); else named_barrier_sync(1 + group, 64 * J);
+        br7_inv01_a<G>(sm, g, q, lane);
+        __syncwarp();
+        br7_inv01_b<G>(sm, g, q, lane, accr);
+        br7_inv2_a<G>(sm, g, q, lane);
+        __syncwarp();
+        br7_inv2_b<G>(sm, g, q, lane, accr);
+        __syncwarp();
     }
-    if (valid) br2_epilogue<G>(sm, g, q, d, lane, ubuf + (size_t)job * U_STRIDE);
+    if (valid) br7_epilogue<G>(sm, g, q, lane, ubuf + (size_t)job * U_STRIDE);
 }
 
 
@@ -309,7 +224,7 @@ br4_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict
 }
 
 
-// ---- cluster shape: one job per 2-CTA cluster (br5_phases.h) ----
+// ---- cluster helpers ----
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
     uint32_t r;
@@ -327,88 +242,6 @@ __device__ __forceinline__ T* map_to_cta(T* p, uint32_t rank)  // generic addres
     asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((uint64_t)p), "r"(rank));
     return reinterpret_cast<T*>(out);
 }
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BR5_THREADS, 1)
-br5_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ arena,
-           const uint32_t* __restrict__ bk_ntt, const BlockTw* __restrict__ tw_g, uint32_t* __restrict__ ubuf, int n_iter)
-{
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    Br5Smem sm;
-    sm.carve(smem_raw);
-    const int tid = threadIdx.x, d = tid >> 6, t = tid & 63;
-    const int q = (int)cluster_ctarank();
-    const int job = blockIdx.x >> 1;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(tw_g);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(sm.tw);
-        for (int k = tid; k < (int)(sizeof(BlockTw) / 4); k += BR5_THREADS) dst[k] = src[k];
-    }
-    if (tid == 0) mbar_init(sm.mbar, 1);
-    const BrJob jb = jobs[job];
-    br5_prologue(sm, jb, arena, q, tid);
-    __syncthreads();
-    const uint32_t* key0 = bk_ntt + (size_t)q * BR5_KEY_WORDS;  // columns 3q..3q+2 of step 0
-    auto stage = [&](int i) {
-        constexpr uint32_t BYTES = BR5_KEY_WORDS * 4;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(sm.mbar)), "r"(BYTES) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         smem_u32(sm.keyb)),
-                     "l"(key0 + (size_t)i * BR4_KEY_WORDS), "r"(BYTES), "r"(smem_u32(sm.mbar))
-                     : "memory");
-    };
-    // second mbarrier: counts the bytes of the three digit tiles the peer copies into this CTA per step
-    uint64_t* mbar_dig = sm.mbar + 1;
-    constexpr uint32_t TILE_BYTES = BT_WORDS * 4;
-    if (tid == 0) mbar_init(mbar_dig, 1);
-    __syncthreads();
-    const uint32_t my_tile = smem_u32(sm.in_tile(q * GL + d));   // source of this team's copy
-    uint32_t peer_tile, peer_bar;                                // same offsets inside the peer CTA
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_tile) : "r"(my_tile), "r"((uint32_t)(q ^ 1)));
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_bar) : "r"(smem_u32(mbar_dig)), "r"((uint32_t)(q ^ 1)));
-    if (tid == 0 && n_iter > 0) stage(0);
-    cluster_arrive();  // both CTAs have initialised their barriers before anyone copies into the other
-    cluster_wait();
-    cluster_arrive_relaxed();  // phase (B) of "step -1": nothing of the peer's is being read yet
-
-    for (int i = 0; i < n_iter; i++) {
-        if (tid == 0)  // this step's three incoming tiles
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar_dig)),
-                         "r"(GL * TILE_BYTES)
-                         : "memory");
-        br5_fwd_p1(sm, i, q, d, t);
-        named_barrier_sync(1 + d, TEAM_THREADS);
-        br5_fwd_p2(sm, q, d, t);
-        named_barrier_sync(1 + d, TEAM_THREADS);
-        br5_fwd_p3(sm, q, d, t);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my tile writes -> visible to the copy engine
-        cluster_wait();    // (B) the peer's pointwise stage of the previous step no longer reads my copies
-        named_barrier_sync(1 + d, TEAM_THREADS);
-        if (t == 0)
-            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             peer_tile),
-                         "r"(my_tile), "r"(TILE_BYTES), "r"(peer_bar)
-                         : "memory");
-        mbar_wait(sm.mbar, (uint32_t)(i & 1));
-        uint64_t pacc[BR5_PW_PER_THREAD][4];
-        named_barrier_sync(7, BR5_THREADS);  // the local teams' tiles are complete (CTA-wide)
-        br5_pw_local(sm, q, tid, pacc);
-        mbar_wait(mbar_dig, (uint32_t)(i & 1));  // the peer's three tiles have landed
-        br5_pw_finish(sm, q, tid, pacc);
-        cluster_arrive_relaxed();  // (B) for the next step
-        __syncthreads();
-        if (tid == 0 && i + 1 < n_iter) stage(i + 1);
-        br5_inv_pA(sm, d, t);
-        named_barrier_sync(1 + d, TEAM_THREADS);
-        br5_inv_pB(sm, d, t);
-        named_barrier_sync(1 + d, TEAM_THREADS);
-        br5_inv_pC(sm, d, t);
-        __syncthreads();
-    }
-    cluster_wait();  // pairs with the last arrive: neither CTA exits while the other may still copy into it
-    br5_epilogue(sm, q, tid, ubuf + (size_t)job * U_STRIDE);
-}
-
 
 // ---- fine-grained cluster shape: one job per 2-CTA cluster, 3 teams of 128 threads per CTA (br6_phases.h) ----
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BR6_THREADS, 1)
@@ -434,9 +267,9 @@ br6_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict
     const BrJob jb = jobs[job];
     br6_prologue(sm, jb, arena, q, tid);
     __syncthreads();
-    const uint32_t* key0 = bk_ntt + (size_t)q * BR5_KEY_WORDS;  // columns 3q..3q+2 of step 0
+    const uint32_t* key0 = bk_ntt + (size_t)q * BR6_KEY_WORDS;  // columns 3q..3q+2 of step 0
     auto stage = [&](int i) {
-        constexpr uint32_t BYTES = BR5_KEY_WORDS * 4;
+        constexpr uint32_t BYTES = BR6_KEY_WORDS * 4;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(sm.mbar)), "r"(BYTES) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -638,16 +471,20 @@ static int fail(const std::string& msg)
                         std::to_string(__LINE__) + ")");                                           \
     } while (0)
 
+constexpr int BR_MAX_SEGMENTS = 5;  // launches one frontier's blind rotations are cut into, at most
+
 struct b200fhe_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    int G = 4;
-    int variant = 1;  // 1: warp per accumulator polynomial (br_kernel), 2: warp per transform (br2_kernel)
+    int G = 8;
+    int variant = 7;  // pinned shape when autotune is off (b200fhe_set_kernel_variant / _jobs_per_cta)
     bool autotune = true;  // pick (variant, G) per batch size unless the caller pinned them
+    int br7_group = 8;     // jobs per barrier group of br7_kernel (8 = CTA-wide pointwise stage, 4 or 2 = skewed groups)
+    int br7_skew = 0;      // start delay between consecutive groups, SM cycles
     NttTables* tab = nullptr;
     tw_t* d_tw2f = nullptr;
     tw_t* d_tw2i = nullptr;
-    BlockTw* d_blocktw = nullptr;   // team-NTT twiddles (br4_kernel, br5_kernel)
+    BlockTw* d_blocktw = nullptr;   // team-NTT twiddles (br4_kernel)
     Block8Tw* d_block8tw = nullptr; // 128-thread team NTT (br6_kernel)
     uint32_t* d_bk_ntt = nullptr;   // [636][6][6][1024]
     uint16_t* d_ksk = nullptr;      // [1024][7][3][640]
@@ -666,8 +503,8 @@ struct b200fhe_ctx {
     cudaEvent_t ev_staged = nullptr, ev_t[3] = {nullptr, nullptr, nullptr};
     bool staged_pending = false, timed = false;
     // per-segment timing of the most recent launch plan (see plan_rotation)
-    cudaEvent_t ev_seg[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    int seg_n = 0, seg_variant[4] = {0, 0, 0, 0}, seg_G[4] = {0, 0, 0, 0}, seg_count[4] = {0, 0, 0, 0};
+    cudaEvent_t ev_seg[BR_MAX_SEGMENTS + 1] = {};
+    int seg_n = 0, seg_variant[BR_MAX_SEGMENTS] = {}, seg_G[BR_MAX_SEGMENTS] = {}, seg_count[BR_MAX_SEGMENTS] = {};
     uint64_t launches = 0;
 };
 
@@ -677,47 +514,78 @@ static int set_dev(b200fhe_ctx* c)
     return 0;
 }
 
-template <int G>
-static int br_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
-{
-    static bool attr_set[64] = {};
-    if (!attr_set[c->device]) {
-        CK(cudaFuncSetAttribute(br_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BrSmem<G>::BYTES));
-        attr_set[c->device] = true;
-    }
-    const int grid = (njobs + G - 1) / G;
-    br_kernel<G><<<grid, 64 * G, BrSmem<G>::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_tw2f,
-                                                                 c->d_tw2i, ubuf, N0);
-    CK(cudaGetLastError());
-    c->launches++;
-    return 0;
-}
-template <int G>
-static int br2_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
-{
-    static bool attr_set[64] = {};
-    if (!attr_set[c->device]) {
-        CK(cudaFuncSetAttribute(br2_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br2Smem<G>::BYTES));
-        attr_set[c->device] = true;
-    }
-    const int grid = (njobs + G - 1) / G;
-    br2_kernel<G><<<grid, 192 * G, Br2Smem<G>::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_tw2f,
-                                                                    c->d_tw2i, ubuf, N0);
-    CK(cudaGetLastError());
-    c->launches++;
-    return 0;
-}
-
-// Launch plan from the measured latency tables (profiles/r01_latency_table*.json, B200, ms per wave):
-//   variant 6 (one job per 2-SM cluster)  74 jobs per wave,  2.09 ms  -> lowest latency
-//   variant 4 (one job per SM)           148 jobs per wave,  3.02 ms  -> 49.0 k rotations/s
-//   variant 3, 4 jobs per CTA            592 jobs per wave, 10.25 ms  -> 57.8 k/s
-//   variant 3, 6 jobs per CTA            888 jobs per wave, 14.68 ms  -> 60.5 k/s
-// A frontier is cut into at most four segments (full waves of the throughput shapes, then the latency
-// shapes for the tail) so that wave quantisation never costs more than one 3 ms wave; narrow dependency
-// levels (< 445 jobs) run entirely on the latency shapes.
-constexpr int BR_MAX_SEGMENTS = 4;
+// ---- launch plan ------------------------------------------------------------------------------------
+// A frontier of n rotation jobs is cut into launches of the shapes below so that the modelled time is
+// minimal: whole waves of the throughput shape, the tail on the latency shapes.  The table holds, per
+// shape, the jobs one wave of 148 SMs takes and the duration of a wave.  The defaults were measured on a
+// B200 at 1965 MHz (profiles/r02_latency_table.json); b200fhe_calibrate() re-measures them on the device
+// at hand (one short wave per shape), so a differently clocked or power-capped part plans with its own
+// numbers.  The plan is an unbounded-knapsack DP over "one more wave of shape s" (cheap: 5 shapes).
+constexpr int N_SHAPES = 5;
+struct BrShape { int variant, G, wave_jobs; double wave_ms; };
 struct BrSegment { int variant, G, count; };
+struct PlanTable {
+    BrShape shape[N_SHAPES] = {
+        {7, 8, 1184, 16.6},  // 16-warp throughput shape
+        {3, 6, 888, 14.68},  // 12-warp throughput shape (kept for the ablation; normally dominated by 7)
+        {3, 4, 592, 10.25},
+        {4, 1, 148, 3.02},   // one job per SM
+        {6, 1, 74, 2.06},    // one job per 2-SM cluster: lowest latency
+    };
+    double launch_ms = 0.01;  // per extra launch: breaks ties in favour of fewer segments
+    bool calibrated = false;
+    // DP cache: best[m] = (ms, shape of the last wave) for m jobs, m < DP_MAX
+    static constexpr int DP_MAX = 4 * 1184 + 1;
+    double best_ms[DP_MAX];
+    int8_t best_shape[DP_MAX];
+    bool dp_valid = false;
+    void build()
+    {
+        best_ms[0] = 0.0;
+        best_shape[0] = -1;
+        for (int m = 1; m < DP_MAX; m++) {
+            double bm = 1e30;
+            int bs = 0;
+            for (int k = 0; k < N_SHAPES; k++) {
+                const BrShape& sh = shape[k];
+                const int rest = m > sh.wave_jobs ? m - sh.wave_jobs : 0;
+                // a new launch is needed whenever the shape changes; approximating by "per wave of a shape other
+                // than the previous one" keeps the DP one-dimensional
+                const double t = sh.wave_ms + best_ms[rest] + ((rest > 0 && best_shape[rest] != k) ? launch_ms : 0.0);
+                if (t < bm - 1e-12) bm = t, bs = k;
+            }
+            best_ms[m] = bm;
+            best_shape[m] = (int8_t)bs;
+        }
+        dp_valid = true;
+    }
+    // counts[k] = jobs assigned to shape k; returns modelled ms
+    double solve(int n, int (&counts)[N_SHAPES])
+    {
+        if (!dp_valid) build();
+        for (int& c : counts) c = 0;
+        double ms = 0.0;
+        // far above the DP range the best-throughput shape takes whole waves
+        int top = 0;
+        for (int k = 1; k < N_SHAPES; k++)
+            if (shape[k].wave_jobs / shape[k].wave_ms > shape[top].wave_jobs / shape[top].wave_ms) top = k;
+        while (n >= DP_MAX) {
+            counts[top] += shape[top].wave_jobs;
+            n -= shape[top].wave_jobs;
+            ms += shape[top].wave_ms;
+        }
+        ms += best_ms[n];
+        while (n > 0) {
+            const int k = best_shape[n];
+            const int take = n < shape[k].wave_jobs ? n : shape[k].wave_jobs;
+            counts[k] += take;
+            n -= take;
+        }
+        return ms;
+    }
+};
+static PlanTable g_plan;  // process-wide: the planning entry points of the ABI take no context
+
 static int plan_rotation(const b200fhe_ctx* c, int njobs, BrSegment (&seg)[BR_MAX_SEGMENTS], double* model_ms = nullptr)
 {
     if (!c->autotune) {
@@ -725,41 +593,12 @@ static int plan_rotation(const b200fhe_ctx* c, int njobs, BrSegment (&seg)[BR_MA
         if (model_ms) *model_ms = 0.0;
         return 1;
     }
-    constexpr double T5 = 2.09, T4 = 3.02, T34 = 10.25, T36 = 14.68;
-    constexpr int W5 = 74, W4 = 148, W34 = 592, W36 = 888;
-    auto waves = [](int count, int per_wave) { return (count + per_wave - 1) / per_wave; };
-    // tail on the latency shapes: full one-job-per-SM waves, the last partial wave on clusters if it fits
-    auto tail_ms = [&](int rest) {
-        const int r = rest % W4;
-        return (rest / W4) * T4 + (r == 0 ? 0.0 : (r <= W5 ? T5 : T4)) + 0.01 * ((rest >= W4) + (r > 0));
-    };
-    const int K = waves(njobs, W36);
-    double best = 1e30;
-    int b6 = 0, b4 = 0;
-    for (int k6 = K > 2 ? K - 2 : 0; k6 <= K; k6++)
-        for (int k4 = 0; k4 <= 3; k4++) {
-            const int c6 = k6 * W36 < njobs ? k6 * W36 : njobs;
-            const int c4 = k4 * W34 < njobs - c6 ? k4 * W34 : njobs - c6;
-            const int rest = njobs - c6 - c4;
-            const double ms = waves(c6, W36) * T36 + waves(c4, W34) * T34 + tail_ms(rest) +
-                              0.01 * ((c6 > 0) + (c4 > 0));  // launch overhead breaks ties
-            if (ms < best) best = ms, b6 = k6, b4 = k4;
-        }
-    if (model_ms) *model_ms = best;
-    int n = 0, left = njobs;
-    auto push = [&](int variant, int G, int count) {
-        if (count > 0) seg[n++] = BrSegment{variant, G, count};
-        left -= count;
-    };
-    push(3, 6, b6 * W36 < left ? b6 * W36 : left);
-    push(3, 4, b4 * W34 < left ? b4 * W34 : left);
-    const int r = left % W4;
-    if (r > 0 && r <= W5) {
-        push(4, 1, left - r);
-        push(6, 1, r);
-    } else {
-        push(4, 1, left);
-    }
+    int counts[N_SHAPES];
+    const double ms = g_plan.solve(njobs, counts);
+    if (model_ms) *model_ms = ms;
+    int n = 0;
+    for (int k = 0; k < N_SHAPES; k++)  // table order = widest shape first: full waves first, the tail last
+        if (counts[k] > 0) seg[n++] = BrSegment{g_plan.shape[k].variant, g_plan.shape[k].G, counts[k]};
     return n;
 }
 
@@ -779,6 +618,22 @@ static int br3_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
     return 0;
 }
 
+template <int G, int J>
+static int br7_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+{
+    static bool attr_set[64] = {};
+    if (!attr_set[c->device]) {
+        CK(cudaFuncSetAttribute(br7_kernel<G, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br7Smem<G>::BYTES));
+        attr_set[c->device] = true;
+    }
+    const int grid = (njobs + G - 1) / G;
+    br7_kernel<G, J><<<grid, 64 * G, Br7Smem<G>::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_tw2f,
+                                                                     c->d_tw2i, ubuf, N0, c->br7_skew);
+    CK(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
 static int br4_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
 {
     static bool attr_set[64] = {};
@@ -787,19 +642,6 @@ static int br4_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
         attr_set[c->device] = true;
     }
     br4_kernel<<<njobs, BR4_THREADS, Br4Smem::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_blocktw, ubuf, N0);
-    CK(cudaGetLastError());
-    c->launches++;
-    return 0;
-}
-
-static int br5_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
-{
-    static bool attr_set[64] = {};
-    if (!attr_set[c->device]) {
-        CK(cudaFuncSetAttribute(br5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br5Smem::BYTES));
-        attr_set[c->device] = true;
-    }
-    br5_kernel<<<2 * njobs, BR5_THREADS, Br5Smem::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_blocktw, ubuf, N0);
     CK(cudaGetLastError());
     c->launches++;
     return 0;
@@ -821,8 +663,14 @@ static int br6_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
 static int br_dispatch_one(b200fhe_ctx* c, int variant, int G, int njobs, const uint16_t* arena, uint32_t* ubuf,
                            const BrJob* d_jobs)
 {
+    if (variant == 7) {
+        switch (c->br7_group) {
+        case 2: return br7_launch<8, 2>(c, njobs, arena, ubuf, d_jobs);
+        case 4: return br7_launch<8, 4>(c, njobs, arena, ubuf, d_jobs);
+        default: return br7_launch<8, 8>(c, njobs, arena, ubuf, d_jobs);
+        }
+    }
     if (variant == 6) return br6_launch(c, njobs, arena, ubuf, d_jobs);
-    if (variant == 5) return br5_launch(c, njobs, arena, ubuf, d_jobs);
     if (variant == 4) return br4_launch(c, njobs, arena, ubuf, d_jobs);
     if (variant == 3) {
         switch (G) {
@@ -832,23 +680,7 @@ static int br_dispatch_one(b200fhe_ctx* c, int variant, int G, int njobs, const 
         default: return fail("variant 3 supports 2, 4 or 6 jobs per CTA");
         }
     }
-    if (variant == 2) {
-        switch (G) {
-        case 1: return br2_launch<1>(c, njobs, arena, ubuf, d_jobs);
-        case 2: return br2_launch<2>(c, njobs, arena, ubuf, d_jobs);
-        case 3: return br2_launch<3>(c, njobs, arena, ubuf, d_jobs);
-        case 4: return br2_launch<4>(c, njobs, arena, ubuf, d_jobs);
-        default: return fail("variant 2 supports 1, 2, 3 or 4 jobs per CTA");
-        }
-    }
-    switch (G) {
-    case 1: return br_launch<1>(c, njobs, arena, ubuf, d_jobs);
-    case 2: return br_launch<2>(c, njobs, arena, ubuf, d_jobs);
-    case 3: return br_launch<3>(c, njobs, arena, ubuf, d_jobs);
-    case 4: return br_launch<4>(c, njobs, arena, ubuf, d_jobs);
-    case 6: return br_launch<6>(c, njobs, arena, ubuf, d_jobs);
-    default: return fail("jobs per CTA must be 1, 2, 3, 4 or 6");
-    }
+    return fail("kernel variant must be 3, 4, 6 or 7");
 }
 
 // rotation job k writes ubuf[k]: segments are contiguous ranges of the job list
@@ -864,7 +696,7 @@ static int br_dispatch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_
             return 1;
         CK(cudaEventRecord(c->ev_seg[k + 1], c->stream));
         c->seg_variant[k] = seg[k].variant;
-        c->seg_G[k] = seg[k].variant >= 4 ? 1 : seg[k].G;
+        c->seg_G[k] = (seg[k].variant == 4 || seg[k].variant == 6) ? 1 : seg[k].G;
         c->seg_count[k] = seg[k].count;
         first += seg[k].count;
     }
@@ -938,6 +770,8 @@ int b200fhe_create(b200fhe_ctx** out, int device)
     CK(cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming));
     for (auto& e : c->ev_t) CK(cudaEventCreate(&e));
     for (auto& e : c->ev_seg) CK(cudaEventCreate(&e));
+    if (const char* e = getenv("B200FHE_BR7_GROUP")) c->br7_group = atoi(e);   // experiment knobs (profiles/r02_br7_groups.md)
+    if (const char* e = getenv("B200FHE_BR7_SKEW")) c->br7_skew = atoi(e);
     c->tab = new NttTables();
     ntt_tables_init(*c->tab);
     // every transfer goes through the context's non-blocking stream: the legacy default stream is not
@@ -998,11 +832,11 @@ int b200fhe_set_jobs_per_cta(b200fhe_ctx* c, int g)
     if (!c) return fail("null context");
     if (g == 0) {  // back to the batch-size heuristic
         c->autotune = true;
-        c->G = 4;
-        c->variant = 1;
+        c->G = 8;
+        c->variant = 7;
         return 0;
     }
-    if (g != 1 && g != 2 && g != 3 && g != 4 && g != 6) return fail("jobs per CTA must be 1, 2, 3, 4 or 6");
+    if (g != 2 && g != 4 && g != 6 && g != 8) return fail("jobs per CTA must be 2, 4, 6 (variant 3) or 8 (variant 7)");
     c->G = g;
     c->autotune = false;
     return 0;
@@ -1011,7 +845,8 @@ int b200fhe_set_jobs_per_cta(b200fhe_ctx* c, int g)
 int b200fhe_set_kernel_variant(b200fhe_ctx* c, int variant)
 {
     if (!c) return fail("null context");
-    if (variant < 1 || variant > 6) return fail("kernel variant must be 1..6");
+    if (variant == 0) return b200fhe_set_jobs_per_cta(c, 0);
+    if (variant != 3 && variant != 4 && variant != 6 && variant != 7) return fail("kernel variant must be 0 (auto), 3, 4, 6 or 7");
     c->variant = variant;
     c->autotune = false;
     return 0;
@@ -1224,7 +1059,7 @@ int b200fhe_plan_rotation(int njobs, int* variant, int* jobs_per_cta, int* jobs,
     const int n = nseg < max_segments ? nseg : max_segments;
     for (int k = 0; k < n; k++) {
         if (variant) variant[k] = seg[k].variant;
-        if (jobs_per_cta) jobs_per_cta[k] = seg[k].variant >= 4 ? 1 : seg[k].G;
+        if (jobs_per_cta) jobs_per_cta[k] = (seg[k].variant == 4 || seg[k].variant == 6) ? 1 : seg[k].G;
         if (jobs) jobs[k] = seg[k].count;
     }
     return n;

@@ -1,22 +1,22 @@
 // Blind rotation, fine-grained cluster shape (br6_kernel): ONE rotation job per 2-CTA cluster,
 // 384 threads per CTA = 3 teams of 128 threads x 8 points (ntt_block8.h).
 //
-// Same arithmetic, reference functions and cluster protocol as br5_phases.h (TFHEpp
-// gatebootstrapping.hpp:19-71, detwfa.hpp:36-49, trgsw.hpp:62-131, trlwe.hpp:213-223; digit tiles
-// copied to the peer CTA by bulk-async DSMEM copies, per-polynomial key halves staged by TMA), with
-// twice the threads per transform: 12 warps per SM instead of 6 and a per-thread dependency chain
-// half as long.  It exists for the latency-bound levels of processor netlists, where a clock cycle
+// Reference functions: TFHEpp gatebootstrapping.hpp:19-71, detwfa.hpp:36-49, trgsw.hpp:62-131,
+// trlwe.hpp:213-223.  CTA q of the cluster owns accumulator polynomial q: it transforms the three digits
+// of its polynomial, copies each finished digit tile to the peer CTA with a bulk-async DSMEM copy, stages
+// its half of the step's NTT-domain key (73,728 B) by TMA, and inverts the three limbs of its polynomial.  It exists for the latency-bound levels of processor netlists, where a clock cycle
 // is the SUM of single-rotation times.
 #pragma once
-#include "br5_phases.h"
+#include "br4_phases.h"
 #include "ntt_block8.h"
 
 namespace b200 {
 
 constexpr int BR6_THREADS = GL * TEAM8_THREADS;              // 384
+constexpr int BR6_KEY_WORDS = LIMBS * ROWS * N1;             // 18,432 words = 73,728 B: the key columns of one polynomial
 
 struct Br6Smem {
-    static constexpr size_t BYTES = (size_t)BR5_KEY_WORDS * 4 + (size_t)(ROWS + LIMBS) * B8_WORDS * 4 + (size_t)N1 * 4 +
+    static constexpr size_t BYTES = (size_t)BR6_KEY_WORDS * 4 + (size_t)(ROWS + LIMBS) * B8_WORDS * 4 + (size_t)N1 * 4 +
                                     sizeof(Block8Tw) + (size_t)SLOT_STRIDE * 2 + 16;
     uint32_t* keyb;   // [LIMBS][ROWS][1024] key columns of this CTA's polynomial
     uint32_t* din;    // [ROWS][B8_WORDS]: rows 3q..3q+2 computed here, the other three copied in by the peer
@@ -29,7 +29,7 @@ struct Br6Smem {
     {
         uint8_t* p = reinterpret_cast<uint8_t*>(base);
         keyb = reinterpret_cast<uint32_t*>(p);
-        p += (size_t)BR5_KEY_WORDS * 4;
+        p += (size_t)BR6_KEY_WORDS * 4;
         din = reinterpret_cast<uint32_t*>(p);
         p += (size_t)ROWS * B8_WORDS * 4;
         dout = reinterpret_cast<uint32_t*>(p);
@@ -87,7 +87,7 @@ B200_HD void br6_fwd_p2(const Br6Smem& sm, int q, int d, int t) { blk8_fwd_p2(sm
 B200_HD void br6_fwd_p3(const Br6Smem& sm, int q, int d, int t) { blk8_fwd_p3(sm.in_tile(q * GL + d), sm.tw->q3f, t); }
 B200_HD void br6_fwd_p4(const Br6Smem& sm, int q, int d, int t) { blk8_fwd_p4(sm.in_tile(q * GL + d), sm.tw->q4f, t); }
 
-// Pointwise stage, split around the arrival of the peer's tiles like br5_pw_local / br5_pw_finish.
+// Pointwise stage, split around the arrival of the peer's tiles (local rows first, the peer's rows once they have landed).
 // A thread (tid < 256) owns quad m = tid of NTT positions for ALL three limb columns of the CTA's
 // polynomial, so each digit quad is read once instead of three times: the stage is bound by
 // shared-memory wavefronts (key 576 + digits 216 per step), not by the multiplies, and eight busy

@@ -16,13 +16,12 @@
 // streams the NTT-domain bootstrapping key once per CTA and reuses it for all G jobs) turns
 // the three limb results back (phase I).  Only two __syncthreads per CMUX step.
 //
-// Step sequence executed by the kernel (and, identically, by the CPU simulator):
-//   pw_load(first position)            key words for phase M requested a whole phase early
-//   br_rotate_diff  ; syncwarp         rotated read of the accumulator copy in the warp's first tile
-//   3 x { br_fwd_a ; syncwarp ; br_fwd_b }
+// Step sequence of br3_kernel (and, identically, of the CPU simulator):
+//   br_fwd3_a ; syncwarp ; br_fwd3_b ; syncwarp ; br_fwd3_c      rotated difference, 3 digits, forward NTT x3
+//   pw_load(first position)            key words for phase M requested before the barrier
 //   syncthreads ; br_pointwise ; syncthreads
-//   3 x { br_inv_a ; syncwarp ; br_inv_b }
-//   br_acc_update ; syncwarp
+//   br_inv3_a ; syncwarp ; br_inv3_b ; syncwarp ; br_inv3_c      inverse NTT x3, lift, recombine, accumulate
+// br7_phases.h holds the 16-warp variant of the same protocol (the shape the launch plan prefers).
 //
 // Every function here is free of intra-phase cross-thread communication: threads talk only
 // through shared memory between phases, so a sequential CPU loop over (phase, thread) is an
@@ -108,51 +107,8 @@ B200_HD void br_prologue(const BrSmem<G>& sm, const BrJob& job, const uint16_t* 
     }
 }
 
-// ---- phase F: (X^abar - 1) * acc, decomposition, forward NTT ----------------------------
-// F0: rotated difference into registers (utils.hpp:130-144)
-template <int G>
-B200_HD void br_rotate_diff(const BrSmem<G>& sm, int i, int g, int q, int lane, const uint32_t (&accr)[32],
-                            uint32_t (&dreg)[32])
-{
-    const uint32_t abar = sm.abar[g * SLOT_STRIDE + i];
-    const uint32_t* acc = sm.acc(g, q);
-    const uint32_t base = ((uint32_t)lane - abar) & (2u * N1 - 1);
-    B200_UNROLL
-    for (int a = 0; a < 32; a++) {
-        const uint32_t m = (base + 32u * a) & (2u * N1 - 1);
-        const uint32_t v = acc[m & (N1 - 1)];
-        const uint32_t neg = 0u - ((m >> NBIT) & 1u);  // all ones when the wrap flips the sign
-        dreg[a] = ((v ^ neg) - neg) - accr[a];
-    }
-}
-
-// Fa(d): digit d of the decomposition (trgsw.hpp:62-78) -> forward pass 1 -> column store
-template <int G>
-B200_HD void br_fwd_a(const BrSmem<G>& sm, int g, int q, int lane, int d, const uint32_t (&dreg)[32])
-{
-    uint32_t x[32];
-    const int sh = 32 - (d + 1) * BGBIT;
-    B200_UNROLL
-    for (int a = 0; a < 32; a++) {
-        const uint32_t v = dreg[a] + (DEC_OFFSET + DEC_ROUND);
-        x[a] = ((v >> sh) & ((1u << BGBIT) - 1)) + (P - (1u << (BGBIT - 1)));  // digit + p, in [p-32, p+31]
-    }
-    fwd_pass1(x);
-    tile_store_col(sm.tile(g, q * GL + d), x, lane);
-}
-// Fb(d): row load -> forward pass 2 -> row store (values < 4p)
-template <int G>
-B200_HD void br_fwd_b(const BrSmem<G>& sm, int g, int q, int lane, int d)
-{
-    uint32_t x[32];
-    uint32_t* t = sm.tile(g, q * GL + d);
-    tile_load_row(t, x, lane);
-    fwd_pass2(x, sm.tw2f, lane);
-    tile_store_row(t, x, lane);
-}
-
-// ---- interleaved variant (br3_kernel): the three digit / limb transforms of a polynomial run in
-// lock step inside the owning warp (see ct_stage3 in ntt_warp.h).  Same tiles, same barriers.
+// ---- phase F: (X^abar - 1) * acc (utils.hpp:130-144), decomposition (trgsw.hpp:62-78), forward NTT.
+// The three digit / limb transforms of a polynomial run in lock step inside the owning warp (ct_stage3 in ntt_warp.h).
 // F3a: rotated difference -> three digits -> pass 1 x3; returns the three register sets so the
 // caller can __syncwarp (the accumulator copy shares tile 3q) before F3b stores them.
 template <int G>
@@ -287,43 +243,6 @@ B200_HD void br_pointwise(const BrSmem<G>& sm, const uint32_t* bk_i, int tid, ui
             if (j2 < N1) pw_load(bk_i, j2, bk0);
             pw_compute<G>(sm, j1, bk1);
         }
-    }
-}
-
-// ---- phase I: inverse NTT of the three limbs, exact recombination, accumulate ------------
-// Ia(l): row load -> inverse pass 1 -> row store
-template <int G>
-B200_HD void br_inv_a(const BrSmem<G>& sm, int g, int q, int lane, int l)
-{
-    uint32_t x[32];
-    uint32_t* t = sm.tile(g, q * LIMBS + l);
-    tile_load_row(t, x, lane);
-    inv_pass1(x, sm.tw2i, lane);
-    tile_store_row(t, x, lane);
-}
-// Ib(l): column load -> inverse pass 2 -> centred lift -> sum += v << (11*l)
-template <int G>
-B200_HD void br_inv_b(const BrSmem<G>& sm, int g, int q, int lane, int l, uint32_t (&sum)[32])
-{
-    uint32_t x[32];
-    tile_load_col(sm.tile(g, q * LIMBS + l), x, lane);
-    inv_pass2(x);
-    B200_UNROLL
-    for (int a = 0; a < 32; a++) {
-        const uint32_t v = (uint32_t)centered_lift(x[a]);
-        sum[a] = (l == 0) ? v : sum[a] + (v << (LIMB_BITS * l));
-    }
-}
-// Ic: acc += external product; refresh the shared copy used by the next rotated read
-template <int G>
-B200_HD void br_acc_update(const BrSmem<G>& sm, int g, int q, int lane, const uint32_t (&sum)[32],
-                           uint32_t (&accr)[32])
-{
-    uint32_t* acc = sm.acc(g, q);
-    B200_UNROLL
-    for (int a = 0; a < 32; a++) {
-        accr[a] += sum[a];
-        acc[32 * a + lane] = accr[a];
     }
 }
 

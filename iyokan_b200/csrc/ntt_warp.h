@@ -271,6 +271,116 @@ B200_HD void inv_pass2_x3(B200_X3)
     gs_stage3<0, 1>(x0, x1, x2, [](int g) { return twi_u(1 + g); });
 }
 
+// ---- two transforms interleaved in one lane (br7_kernel: 16 warps per SM need <= 128 registers,
+// so a warp runs two of its three transforms in lock step and the third one alone) -------------
+template <int LS, int FIX, class TwFn>
+B200_HD void ct_stage2(uint32_t (&x0)[32], uint32_t (&x1)[32], TwFn tw)
+{
+    constexpr int half = 16 >> LS;
+    B200_UNROLL
+    for (int g = 0; g < (1 << LS); g++) {
+        const tw_t w = tw(g);
+        B200_UNROLL
+        for (int k = 0; k < half; k++) {
+            const int i0 = g * 2 * half + k, i1 = i0 + half;
+            const uint32_t X0 = apply_fix<FIX>(x0[i0]), X1 = apply_fix<FIX>(x1[i0]);
+            const uint32_t T0 = shoup_mul(x0[i1], w), T1 = shoup_mul(x1[i1], w);
+            x0[i0] = X0 + T0;
+            x0[i1] = X0 - T0 + P2;
+            x1[i0] = X1 + T1;
+            x1[i1] = X1 - T1 + P2;
+        }
+    }
+}
+template <int LS, int FIX, class TwFn>
+B200_HD void gs_stage2(uint32_t (&x0)[32], uint32_t (&x1)[32], TwFn tw)
+{
+    constexpr int half = 16 >> LS;
+    B200_UNROLL
+    for (int g = 0; g < (1 << LS); g++) {
+        const tw_t w = tw(g);
+        B200_UNROLL
+        for (int k = 0; k < half; k++) {
+            const int i0 = g * 2 * half + k, i1 = i0 + half;
+            const uint32_t U0 = x0[i0], V0 = x0[i1], U1 = x1[i0], V1 = x1[i1];
+            x0[i0] = apply_fix<FIX>(U0 + V0);
+            x1[i0] = apply_fix<FIX>(U1 + V1);
+            x0[i1] = shoup_mul(U0 - V0 + P4, w);
+            x1[i1] = shoup_mul(U1 - V1 + P4, w);
+        }
+    }
+}
+#define B200_X2 uint32_t (&x0)[32], uint32_t (&x1)[32]
+B200_HD void fwd_pass1_x2(B200_X2)
+{
+    ct_stage2<0, 0>(x0, x1, [](int g) { return twf_u(1 + g); });
+    ct_stage2<1, 0>(x0, x1, [](int g) { return twf_u(2 + g); });
+    ct_stage2<2, 0>(x0, x1, [](int g) { return twf_u(4 + g); });
+    ct_stage2<3, 1>(x0, x1, [](int g) { return twf_u(8 + g); });
+    ct_stage2<4, 0>(x0, x1, [](int g) { return twf_u(16 + g); });
+}
+B200_HD void fwd_pass2_x2(B200_X2, const tw_t* tw2, int lane)
+{
+    ct_stage2<0, 1>(x0, x1, [=](int g) { return tw2[(0 + g) * 32 + lane]; });
+    ct_stage2<1, 0>(x0, x1, [=](int g) { return tw2[(1 + g) * 32 + lane]; });
+    ct_stage2<2, 1>(x0, x1, [=](int g) { return tw2[(3 + g) * 32 + lane]; });
+    ct_stage2<3, 0>(x0, x1, [=](int g) { return tw2[(7 + g) * 32 + lane]; });
+    ct_stage2<4, 2>(x0, x1, [=](int g) { return tw2[(15 + g) * 32 + lane]; });
+}
+B200_HD void inv_pass1_x2(B200_X2, const tw_t* tw2, int lane)
+{
+    gs_stage2<4, 1>(x0, x1, [=](int g) { return tw2[(15 + g) * 32 + lane]; });
+    gs_stage2<3, 1>(x0, x1, [=](int g) { return tw2[(7 + g) * 32 + lane]; });
+    gs_stage2<2, 1>(x0, x1, [=](int g) { return tw2[(3 + g) * 32 + lane]; });
+    gs_stage2<1, 1>(x0, x1, [=](int g) { return tw2[(1 + g) * 32 + lane]; });
+    gs_stage2<0, 1>(x0, x1, [=](int g) { return tw2[(0 + g) * 32 + lane]; });
+}
+B200_HD void inv_pass2_x2(B200_X2)
+{
+    gs_stage2<4, 1>(x0, x1, [](int g) { return twi_u(16 + g); });
+    gs_stage2<3, 1>(x0, x1, [](int g) { return twi_u(8 + g); });
+    gs_stage2<2, 1>(x0, x1, [](int g) { return twi_u(4 + g); });
+    gs_stage2<1, 1>(x0, x1, [](int g) { return twi_u(2 + g); });
+    gs_stage2<0, 1>(x0, x1, [](int g) { return twi_u(1 + g); });
+}
+
+// ---- XOR-swizzled tile (br7_kernel): 32 x 32 words with NO row padding.  Element (a, b) lives at
+// word a*32 + (b ^ ((a & 7) << 2)): the 16-byte chunk index is XORed with the low row bits, so the
+// row-wise 128-bit accesses of 8 consecutive rows hit 8 different bank groups, while the column-wise
+// 32-bit accesses of a warp stay a permutation of one row (conflict free either way).
+constexpr int STILE_WORDS = 1024;
+B200_HD int stile_of_j(int j) { return j ^ (((j >> 5) & 7) << 2); }
+B200_HD void stile_store_col(uint32_t* tile, const uint32_t (&x)[32], int lane)
+{
+    B200_UNROLL
+    for (int a = 0; a < 32; a++) tile[a * 32 + (lane ^ ((a & 7) << 2))] = x[a];
+}
+B200_HD void stile_load_col(const uint32_t* tile, uint32_t (&x)[32], int lane)
+{
+    B200_UNROLL
+    for (int a = 0; a < 32; a++) x[a] = tile[a * 32 + (lane ^ ((a & 7) << 2))];
+}
+B200_HD void stile_store_row(uint32_t* tile, const uint32_t (&x)[32], int lane)
+{
+    u32x4* row = reinterpret_cast<u32x4*>(tile + lane * 32);
+    const int s = lane & 7;
+    B200_UNROLL
+    for (int k = 0; k < 8; k++) row[k ^ s] = u32x4{x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]};
+}
+B200_HD void stile_load_row(const uint32_t* tile, uint32_t (&x)[32], int lane)
+{
+    const u32x4* row = reinterpret_cast<const u32x4*>(tile + lane * 32);
+    const int s = lane & 7;
+    B200_UNROLL
+    for (int k = 0; k < 8; k++) {
+        const u32x4 v = row[k ^ s];
+        x[4 * k] = v.x;
+        x[4 * k + 1] = v.y;
+        x[4 * k + 2] = v.z;
+        x[4 * k + 3] = v.w;
+    }
+}
+
 // ---- tile access -----------------------------------------------------------------------
 // column access: register index = a, lane = b  (32-bit, conflict free)
 B200_HD void tile_store_col(uint32_t* tile, const uint32_t (&x)[32], int lane)

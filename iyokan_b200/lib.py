@@ -132,8 +132,8 @@ class PinnedBuffer:
 def plan_rotation(njobs: int):
     """Launch plan of the batch-size heuristic for `njobs` blind rotations: [(variant, jobs_per_cta, jobs)]."""
     lib = load()
-    v, g, n = (np.zeros(4, np.int32) for _ in range(3))
-    k = lib.b200fhe_plan_rotation(int(njobs), _ptr(v), _ptr(g), _ptr(n), 4)
+    v, g, n = (np.zeros(8, np.int32) for _ in range(3))
+    k = lib.b200fhe_plan_rotation(int(njobs), _ptr(v), _ptr(g), _ptr(n), 8)
     return [(int(v[i]), int(g[i]), int(n[i])) for i in range(k)]
 
 
@@ -254,9 +254,9 @@ class Context:
 
     def last_batch_segments(self):
         """Launch plan of the most recent gate_batch: list of dicts (variant, jobs_per_cta, jobs, ms)."""
-        v, g, n = (np.zeros(4, np.int32) for _ in range(3))
-        ms = np.zeros(4, np.float32)
-        k = self._lib.b200fhe_last_batch_segments(self._h, _ptr(v), _ptr(g), _ptr(n), _ptr(ms), 4)
+        v, g, n = (np.zeros(8, np.int32) for _ in range(3))
+        ms = np.zeros(8, np.float32)
+        k = self._lib.b200fhe_last_batch_segments(self._h, _ptr(v), _ptr(g), _ptr(n), _ptr(ms), 8)
         if k < 0:
             raise B200FheError(self._lib.b200fhe_last_error().decode())
         return [{"variant": int(v[i]), "jobs_per_cta": int(g[i]), "jobs": int(n[i]), "ms": float(ms[i])} for i in range(k)]

@@ -15,11 +15,12 @@ ctx.upload(ids[:N], a); ctx.upload(ids[N:2 * N], b)
 ops = np.full(N, OPS["NAND"], np.uint8)
 table = {}
 import itertools
-sel = os.environ.get('VARIANTS', '6:1,5:1,4:1,2:1,3:4,3:6')
+sel = os.environ.get('VARIANTS', '6:1,4:1,3:4,3:6,7:8')
 sizes = [int(x) for x in os.environ.get('SIZES', '1,74,148,296,444,592,888,1184,1776,2368').split(',')]
 for variant, g in (tuple(int(y) for y in x.split(':')) for x in sel.split(',')):
     ctx.set_kernel_variant(variant)
-    ctx.set_jobs_per_cta(g)
+    if g > 1:
+        ctx.set_jobs_per_cta(g)
     row = {}
     for nb in sizes:
         for rep in range(2):

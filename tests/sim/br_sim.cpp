@@ -10,10 +10,9 @@
 #include <cstring>
 #include <vector>
 
-#include "../../iyokan_b200/csrc/br2_phases.h"
 #include "../../iyokan_b200/csrc/br4_phases.h"
-#include "../../iyokan_b200/csrc/br5_phases.h"
 #include "../../iyokan_b200/csrc/br6_phases.h"
+#include "../../iyokan_b200/csrc/br7_phases.h"
 #include "../../iyokan_b200/csrc/br_phases.h"
 #include "../../iyokan_b200/csrc/gate_jobs.h"
 #include "../../iyokan_b200/csrc/ks_phases.h"
@@ -123,79 +122,6 @@ extern "C" void sim_bk_prepare(const uint32_t* bk_raw, uint32_t* bk_ntt, int n_i
     }
 }
 
-template <int G>
-static void sim_br_cta(const BrJob* jobs, int njobs, int cta, const uint16_t* arena, const uint32_t* bk_ntt,
-                       uint32_t* ubuf, int n_iter)
-{
-    constexpr int T = 64 * G, W = 2 * G;
-    std::vector<uint8_t> smem(BrSmem<G>::BYTES + 16);
-    BrSmem<G> sm;
-    sm.carve(smem.data());
-    std::memcpy(sm.tw2f, g_tab.tw2f, sizeof(g_tab.tw2f));
-    std::memcpy(sm.tw2i, g_tab.tw2i, sizeof(g_tab.tw2i));
-    struct Regs {
-        uint32_t accr[32], dreg[32], sum[32];
-    };
-    std::vector<Regs> regs(T);
-    auto jobof = [&](int g) {
-        int j = cta * G + g;
-        return j < njobs ? j : njobs - 1;
-    };
-    for (int w = 0; w < W; w++)
-        for (int lane = 0; lane < 32; lane++)
-            br_prologue<G>(sm, jobs[jobof(w >> 1)], arena, w >> 1, w & 1, lane, regs[w * 32 + lane].accr);
-    for (int i = 0; i < n_iter; i++) {
-        for (int w = 0; w < W; w++) {
-            const int g = w >> 1, q = w & 1;
-            for (int lane = 0; lane < 32; lane++)
-                br_rotate_diff<G>(sm, i, g, q, lane, regs[w * 32 + lane].accr, regs[w * 32 + lane].dreg);
-            for (int d = 0; d < GL; d++) {
-                for (int lane = 0; lane < 32; lane++) br_fwd_a<G>(sm, g, q, lane, d, regs[w * 32 + lane].dreg);
-                for (int lane = 0; lane < 32; lane++) br_fwd_b<G>(sm, g, q, lane, d);
-            }
-        }
-        const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
-        for (int tid = 0; tid < T; tid++) {
-            uint32_t bk0[BK_COLS][ROWS];
-            pw_load(bk_i, tid, bk0);
-            br_pointwise<G>(sm, bk_i, tid, bk0);
-        }
-        for (int w = 0; w < W; w++) {
-            const int g = w >> 1, q = w & 1;
-            for (int l = 0; l < LIMBS; l++) {
-                for (int lane = 0; lane < 32; lane++) br_inv_a<G>(sm, g, q, lane, l);
-                for (int lane = 0; lane < 32; lane++) br_inv_b<G>(sm, g, q, lane, l, regs[w * 32 + lane].sum);
-            }
-            for (int lane = 0; lane < 32; lane++)
-                br_acc_update<G>(sm, g, q, lane, regs[w * 32 + lane].sum, regs[w * 32 + lane].accr);
-        }
-    }
-    for (int w = 0; w < W; w++) {
-        const int g = w >> 1, q = w & 1;
-        if (cta * G + g >= njobs) continue;
-        for (int lane = 0; lane < 32; lane++)
-            br_epilogue<G>(sm, g, q, lane, ubuf + (size_t)(cta * G + g) * U_STRIDE);
-    }
-}
-
-// jobs: packed BrJob array (16 bytes each); arena: uint16 [slots][640]; ubuf: uint32 [njobs][1028]
-extern "C" void sim_blind_rotate(int G, const void* jobs_raw, int njobs, const uint16_t* arena,
-                                 const uint32_t* bk_ntt, uint32_t* ubuf, int n_iter)
-{
-    sim_init();
-    const BrJob* jobs = reinterpret_cast<const BrJob*>(jobs_raw);
-    const int ncta = (njobs + G - 1) / G;
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int cta = 0; cta < ncta; cta++) {
-        if (G == 1) sim_br_cta<1>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
-        else if (G == 2) sim_br_cta<2>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
-        else if (G == 3) sim_br_cta<3>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
-        else if (G == 6) sim_br_cta<6>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
-        else if (G == 4) sim_br_cta<4>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
-        else std::abort();
-    }
-}
-
 // ---- variant 3: interleaved transforms (br3_kernel) ----
 template <int G>
 static void sim_br3_cta(const BrJob* jobs, int njobs, int cta, const uint16_t* arena, const uint32_t* bk_ntt,
@@ -270,92 +196,82 @@ extern "C" void sim_blind_rotate3(int G, const void* jobs_raw, int njobs, const 
     }
 }
 
-// ---- variant 2: one warp per transform (br2_kernel) ----
-template <int G>
-static void sim_br2_cta(const BrJob* jobs, int njobs, int cta, const uint16_t* arena, const uint32_t* bk_ntt,
+// ---- variant 7: 16-warp throughput shape on swizzled tiles (br7_kernel) ----
+template <int G, int J>
+static void sim_br7_cta(const BrJob* jobs, int njobs, int cta, const uint16_t* arena, const uint32_t* bk_ntt,
                         uint32_t* ubuf, int n_iter)
 {
-    constexpr int T = 192 * G, W = 6 * G;
-    std::vector<uint8_t> smem(Br2Smem<G>::BYTES + 16);
-    Br2Smem<G> sm;
+    constexpr int T = 64 * G, W = 2 * G;
+    std::vector<uint8_t> smem(Br7Smem<G>::BYTES + 16);
+    Br7Smem<G> sm;
     sm.carve(smem.data());
     std::memcpy(sm.tw2f, g_tab.tw2f, sizeof(g_tab.tw2f));
     std::memcpy(sm.tw2i, g_tab.tw2i, sizeof(g_tab.tw2i));
+    struct Regs {
+        uint32_t accr[32], x0[32];
+    };
+    std::vector<Regs> regs(T);
     auto jobof = [&](int g) {
         int j = cta * G + g;
         return j < njobs ? j : njobs - 1;
     };
-    auto ids = [](int w, int& g, int& q, int& d) {
-        g = w / 6;
-        q = (w % 6) / 3;
-        d = (w % 6) % 3;
-    };
-    int g, q, d;
-    for (int w = 0; w < W; w++) {
-        ids(w, g, q, d);
-        for (int lane = 0; lane < 32; lane++) br2_prologue<G>(sm, jobs[jobof(g)], arena, g, q, d, lane);
-    }
+    for (int w = 0; w < W; w++)
+        for (int lane = 0; lane < 32; lane++)
+            br7_prologue<G>(sm, jobs[jobof(w >> 1)], arena, w >> 1, w & 1, lane, regs[w * 32 + lane].accr);
     for (int i = 0; i < n_iter; i++) {
-        for (int w = 0; w < W; w++) {
-            ids(w, g, q, d);
-            for (int lane = 0; lane < 32; lane++) br2_fwd_a<G>(sm, i, g, q, d, lane);
-        }
-        for (int w = 0; w < W; w++) {  // all rotated reads happen before any tile is overwritten? no:
-            ids(w, g, q, d);           // fwd_a only writes the warp's own tile, acc is read-only here
-            for (int lane = 0; lane < 32; lane++) br2_fwd_b<G>(sm, g, q, d, lane);
+        for (int ww = 0; ww < W; ww++) {
+            const int w = ord(ww, W), g = w >> 1, q = w & 1;
+            for (int l = 0; l < 32; l++) br7_fwd12_a<G>(sm, i, g, q, ord(l, 32), regs[w * 32 + ord(l, 32)].accr);
+            for (int l = 0; l < 32; l++) br7_fwd12_c<G>(sm, g, q, ord(l, 32));
+            for (int l = 0; l < 32; l++) {
+                Regs& r = regs[w * 32 + ord(l, 32)];
+                br7_fwd0_a<G>(sm, i, g, q, ord(l, 32), r.accr, r.x0);
+            }
+            for (int l = 0; l < 32; l++) br7_fwd0_b<G>(sm, g, q, ord(l, 32), regs[w * 32 + ord(l, 32)].x0);
+            for (int l = 0; l < 32; l++) br7_fwd0_c<G>(sm, g, q, ord(l, 32));
         }
         const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
-        // pointwise: per warp, per item round, per job: all lanes compute, then all lanes store
-        for (int w = 0; w < W; w++)
-            for (int item0 = w * 32; item0 < PW2_ITEMS; item0 += T)
-                for (int gg = 0; gg < G; gg++) {
-                    uint32_t o[32][PW2_COLS];
-                    for (int lane = 0; lane < 32; lane++) {
-                        int j, half;
-                        pw2_item(item0 + lane, j, half);
-                        uint32_t bkv[PW2_COLS][ROWS];
-                        pw2_load(bk_i, j, half, bkv);
-                        pw2_compute<G>(sm, gg, tile_of_j(j), bkv, o[lane]);
-                    }
-                    for (int lane = 0; lane < 32; lane++) {
-                        int j, half;
-                        pw2_item(item0 + lane, j, half);
-                        pw2_store<G>(sm, gg, half, tile_of_j(j), o[lane]);
-                    }
-                }
-        for (int w = 0; w < W; w++) {
-            ids(w, g, q, d);
-            for (int lane = 0; lane < 32; lane++) br2_inv_a<G>(sm, g, q, d, lane);
-            for (int lane = 0; lane < 32; lane++) br2_inv_b<G>(sm, g, q, d, lane);
+        for (int t = 0; t < T; t++) {  // barrier groups of J jobs, each with its own pointwise stage
+            const int tid = ord(t, T), g0 = (tid / (64 * J)) * J, tig = tid - 64 * g0;
+            uint32_t bk0[BK_COLS][ROWS];
+            pw_load(bk_i, tig, bk0);
+            br7_pointwise<G, J>(sm, bk_i, g0, tig, bk0);
         }
-        for (int w = 0; w < W; w++) {  // after the named barrier
-            ids(w, g, q, d);
-            for (int lane = 0; lane < 32; lane++) br2_combine<G>(sm, g, q, d, lane);
+        for (int ww = 0; ww < W; ww++) {
+            const int w = ord(ww, W), g = w >> 1, q = w & 1;
+            for (int l = 0; l < 32; l++) br7_inv01_a<G>(sm, g, q, ord(l, 32));
+            // I01b and I2a share a phase in the kernel (no __syncwarp between them): they touch different tiles
+            for (int l = 0; l < 32; l++) {
+                br7_inv01_b<G>(sm, g, q, ord(l, 32), regs[w * 32 + ord(l, 32)].accr);
+                br7_inv2_a<G>(sm, g, q, ord(l, 32));
+            }
+            for (int l = 0; l < 32; l++) br7_inv2_b<G>(sm, g, q, ord(l, 32), regs[w * 32 + ord(l, 32)].accr);
         }
     }
     for (int w = 0; w < W; w++) {
-        ids(w, g, q, d);
+        const int g = w >> 1, q = w & 1;
         if (cta * G + g >= njobs) continue;
-        for (int lane = 0; lane < 32; lane++) br2_epilogue<G>(sm, g, q, d, lane, ubuf + (size_t)(cta * G + g) * U_STRIDE);
+        for (int lane = 0; lane < 32; lane++)
+            br7_epilogue<G>(sm, g, q, lane, ubuf + (size_t)(cta * G + g) * U_STRIDE);
     }
 }
 
-extern "C" void sim_blind_rotate2(int G, const void* jobs_raw, int njobs, const uint16_t* arena,
+extern "C" void sim_blind_rotate7(int G, const void* jobs_raw, int njobs, const uint16_t* arena,
                                   const uint32_t* bk_ntt, uint32_t* ubuf, int n_iter)
 {
     sim_init();
     const BrJob* jobs = reinterpret_cast<const BrJob*>(jobs_raw);
-    const int ncta = (njobs + G - 1) / G;
+    const int Gj = G > 8 ? 8 : G;
+    const int ncta = (njobs + Gj - 1) / Gj;
 #pragma omp parallel for schedule(dynamic, 1)
     for (int cta = 0; cta < ncta; cta++) {
-        if (G == 1) sim_br2_cta<1>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
-        else if (G == 2) sim_br2_cta<2>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
-        else if (G == 3) sim_br2_cta<3>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
-        else if (G == 4) sim_br2_cta<4>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
+        if (G == 2) sim_br7_cta<2, 2>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
+        else if (G == 8) sim_br7_cta<8, 8>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
+        else if (G == 84) sim_br7_cta<8, 4>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);  // 8 jobs, groups of 4
+        else if (G == 82) sim_br7_cta<8, 2>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);  // 8 jobs, groups of 2
         else std::abort();
     }
 }
-
 
 // ---- variant 4: one job per CTA, 6 teams of 64 threads (br4_kernel) ----
 // team transform on its own: natural order in, NTT positions out (must equal the warp transform bit for bit)
@@ -447,59 +363,6 @@ extern "C" void sim_blind_rotate4(const void* jobs_raw, int njobs, const uint16_
 }
 
 
-// ---- variant 5: one job per 2-CTA cluster (br5_kernel); both CTAs advance phase by phase ----
-static void sim_br5_cluster(const BrJob* jobs, int job, const uint16_t* arena, const uint32_t* bk_ntt, uint32_t* ubuf,
-                            int n_iter)
-{
-    std::vector<uint8_t> smem[2] = {std::vector<uint8_t>(Br5Smem::BYTES + 128), std::vector<uint8_t>(Br5Smem::BYTES + 128)};
-    Br5Smem sm[2];
-    for (int q = 0; q < 2; q++) {
-        sm[q].carve(reinterpret_cast<void*>(((uintptr_t)smem[q].data() + 127) & ~(uintptr_t)127));
-        std::memcpy(sm[q].tw, &g_btw, sizeof(BlockTw));
-        for (int tid = 0; tid < BR5_THREADS; tid++) br5_prologue(sm[q], jobs[job], arena, q, tid);
-    }
-    auto each = [&](auto fn) {
-        for (int q = 0; q < 2; q++)
-            for (int tid = 0; tid < BR5_THREADS; tid++) fn(q, tid >> 6, tid & 63);
-    };
-    for (int i = 0; i < n_iter; i++) {
-        for (int q = 0; q < 2; q++)  // the bulk-async copy of this CTA's key columns
-            std::memcpy(sm[q].keyb, bk_ntt + (size_t)i * BR4_KEY_WORDS + (size_t)q * BR5_KEY_WORDS, (size_t)BR5_KEY_WORDS * 4);
-        each([&](int q, int d, int t) { br5_fwd_p1(sm[q], i, q, d, t); });
-        each([&](int q, int d, int t) { br5_fwd_p2(sm[q], q, d, t); });
-        each([&](int q, int d, int t) { br5_fwd_p3(sm[q], q, d, t); });
-        for (int q = 0; q < 2; q++)  // the tile copies into the peer (cp.async.bulk shared::cta -> shared::cluster)
-            for (int d = 0; d < GL; d++)
-                std::memcpy(sm[q ^ 1].in_tile(q * GL + d), sm[q].in_tile(q * GL + d), (size_t)BT_WORDS * 4);
-        {
-            std::vector<uint64_t> pacc((size_t)2 * BR5_THREADS * BR5_PW_PER_THREAD * 4);
-            auto acc_of = [&](int q, int tid) -> uint64_t(&)[BR5_PW_PER_THREAD][4] {
-                return *reinterpret_cast<uint64_t(*)[BR5_PW_PER_THREAD][4]>(
-                    pacc.data() + ((size_t)q * BR5_THREADS + tid) * BR5_PW_PER_THREAD * 4);
-            };
-            for (int q = 0; q < 2; q++)
-                for (int tid = 0; tid < BR5_THREADS; tid++) br5_pw_local(sm[q], q, tid, acc_of(q, tid));
-            for (int q = 0; q < 2; q++)
-                for (int tid = 0; tid < BR5_THREADS; tid++) br5_pw_finish(sm[q], q, tid, acc_of(q, tid));
-        }
-        each([&](int q, int d, int t) { br5_inv_pA(sm[q], d, t); });
-        each([&](int q, int d, int t) { br5_inv_pB(sm[q], d, t); });
-        each([&](int q, int d, int t) { br5_inv_pC(sm[q], d, t); });
-    }
-    for (int q = 0; q < 2; q++)
-        for (int tid = 0; tid < BR5_THREADS; tid++) br5_epilogue(sm[q], q, tid, ubuf + (size_t)job * U_STRIDE);
-}
-
-extern "C" void sim_blind_rotate5(const void* jobs_raw, int njobs, const uint16_t* arena, const uint32_t* bk_ntt,
-                                  uint32_t* ubuf, int n_iter)
-{
-    sim_init();
-    const BrJob* jobs = reinterpret_cast<const BrJob*>(jobs_raw);
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int job = 0; job < njobs; job++) sim_br5_cluster(jobs, job, arena, bk_ntt, ubuf, n_iter);
-}
-
-
 // ---- variant 6: cluster shape with 128-thread x 8-point teams (br6_kernel) ----
 extern "C" void sim_block8_forward(const uint32_t* in, uint32_t* out)
 {
@@ -555,7 +418,7 @@ static void sim_br6_cluster(const BrJob* jobs, int job, const uint16_t* arena, c
     };
     for (int i = 0; i < n_iter; i++) {
         for (int q = 0; q < 2; q++)
-            std::memcpy(sm[q].keyb, bk_ntt + (size_t)i * BR4_KEY_WORDS + (size_t)q * BR5_KEY_WORDS, (size_t)BR5_KEY_WORDS * 4);
+            std::memcpy(sm[q].keyb, bk_ntt + (size_t)i * BR4_KEY_WORDS + (size_t)q * BR6_KEY_WORDS, (size_t)BR6_KEY_WORDS * 4);
         each([&](int q, int d, int t) { br6_fwd_p1(sm[q], i, q, d, t); });
         each([&](int q, int d, int t) { br6_fwd_p2(sm[q], q, d, t); });
         each([&](int q, int d, int t) { br6_fwd_p3(sm[q], q, d, t); });
@@ -683,7 +546,8 @@ extern "C" int sim_gate_batch(int G, const uint8_t* opcode, const uint32_t* in0,
     }
     if (cnt.nbr) {
         std::vector<uint32_t> ubuf(cnt.nbr * (size_t)U_STRIDE);
-        sim_blind_rotate(G, br.data(), (int)cnt.nbr, arena, bk_ntt, ubuf.data(), N0);
+        if (G == 8) sim_blind_rotate7(G, br.data(), (int)cnt.nbr, arena, bk_ntt, ubuf.data(), N0);
+        else sim_blind_rotate3(G, br.data(), (int)cnt.nbr, arena, bk_ntt, ubuf.data(), N0);
         sim_keyswitch(ks.data(), (int)cnt.nks, ubuf.data(), ksk_dev, arena);
     }
     return 0;

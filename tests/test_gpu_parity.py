@@ -26,29 +26,24 @@ def test_bk_ntt_matches_cpu_simulator(gpu_ctx, bk_ntt_sim):
         assert np.array_equal(gpu_ctx.test_read_bk_ntt(first, 4), bk_ntt_sim[first:first + 4])
 
 
-@pytest.mark.parametrize("G", [1, 2, 3, 4, 6])
-def test_blind_rotate_bit_exact(gpu_ctx, keys, golden, G):
-    gpu_ctx.set_jobs_per_cta(G)
-    c = golden["br_in"][:3]  # 3 jobs: ragged for G = 2 and 4
-    assert np.array_equal(gpu_ctx.test_bootstrap_lvl1(c), O.bootstrap_to_lvl1(keys, c))
-    gpu_ctx.set_jobs_per_cta(0)
-
-
-@pytest.mark.parametrize("G", [1, 2, 3, 4])
-def test_blind_rotate_variant2_bit_exact(gpu_ctx, keys, golden, G):
-    gpu_ctx.set_kernel_variant(2)
-    gpu_ctx.set_jobs_per_cta(G)
+def test_blind_rotate_variant7_bit_exact(gpu_ctx, keys, golden):
+    # 16-warp throughput shape: 8 jobs per CTA on swizzled tiles
+    gpu_ctx.set_kernel_variant(7)
+    gpu_ctx.set_jobs_per_cta(8)
     try:
-        c = golden["br_in"][:3]
+        c = golden["br_in"][:3]  # ragged: 3 of 8 jobs of the CTA are real
         assert np.array_equal(gpu_ctx.test_bootstrap_lvl1(c), O.bootstrap_to_lvl1(keys, c))
         edge = np.zeros((2, 637), np.uint16)
         edge[0, :8] = [0xFFFF, 0xFFF0, 0, 15, 0x8000, 0x7FF0, 0x8010, 0x0010]
         edge[0, 636] = 0x001F
         edge[1, 636] = 0xFFFF
         assert np.array_equal(gpu_ctx.test_bootstrap_lvl1(edge), O.bootstrap_to_lvl1(keys, edge))
+        many = np.tile(golden["br_in"][:4], (300, 1))   # 1200 jobs: 150 CTAs, more than one wave
+        got = gpu_ctx.test_bootstrap_lvl1(many)
+        want = O.bootstrap_to_lvl1(keys, golden["br_in"][:4])
+        assert np.array_equal(got, np.tile(want, (300, 1)))
     finally:
-        gpu_ctx.set_kernel_variant(1)
-        gpu_ctx.set_jobs_per_cta(0)
+        gpu_ctx.set_kernel_variant(0)
 
 
 @pytest.mark.parametrize("G", [2, 4, 6])
@@ -59,8 +54,7 @@ def test_blind_rotate_variant3_bit_exact(gpu_ctx, keys, golden, G):
         c = golden["br_in"][:3]
         assert np.array_equal(gpu_ctx.test_bootstrap_lvl1(c), O.bootstrap_to_lvl1(keys, c))
     finally:
-        gpu_ctx.set_kernel_variant(1)
-        gpu_ctx.set_jobs_per_cta(0)
+        gpu_ctx.set_kernel_variant(0)
 
 
 def test_blind_rotate_variant4_bit_exact(gpu_ctx, keys, golden):
@@ -82,14 +76,13 @@ def test_blind_rotate_variant4_bit_exact(gpu_ctx, keys, golden):
         want = O.bootstrap_to_lvl1(keys, golden["br_in"][:4])
         assert np.array_equal(got, np.tile(want, (80, 1)))
     finally:
-        gpu_ctx.set_kernel_variant(1)
-        gpu_ctx.set_jobs_per_cta(0)
+        gpu_ctx.set_kernel_variant(0)
 
 
-@pytest.mark.parametrize("variant", [5, 6])
+@pytest.mark.parametrize("variant", [6])
 def test_blind_rotate_cluster_shapes_bit_exact(gpu_ctx, keys, golden, variant):
-    # cluster shapes: one job per 2-CTA cluster, digit tiles exchanged through distributed shared memory
-    # (5: 64-thread x 16-point teams, 6: 128-thread x 8-point teams)
+    # cluster shape: one job per 2-CTA cluster, digit tiles exchanged through distributed shared memory
+    # (128-thread x 8-point teams)
     gpu_ctx.set_kernel_variant(variant)
     try:
         c = golden["br_in"][:5]
@@ -106,8 +99,7 @@ def test_blind_rotate_cluster_shapes_bit_exact(gpu_ctx, keys, golden, variant):
         want = O.bootstrap_to_lvl1(keys, golden["br_in"][:4])
         assert np.array_equal(got, np.tile(want, (50, 1)))
     finally:
-        gpu_ctx.set_kernel_variant(1)
-        gpu_ctx.set_jobs_per_cta(0)
+        gpu_ctx.set_kernel_variant(0)
 
 
 def test_blind_rotate_edge_inputs(gpu_ctx, keys):

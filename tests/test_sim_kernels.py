@@ -64,47 +64,6 @@ def test_bk_limbs_recombine(sim, keys, bk_ntt_sim):
     assert np.array_equal((x0 + (x1 << 11) + (x2 << 22)) % 2**32, raw % 2**32)
 
 
-@pytest.mark.parametrize("G", [1, 2, 3, 4, 6])
-def test_blind_rotate_bit_exact(sim, keys, bk_ntt_sim, G):
-    rng = np.random.default_rng(10 + G)
-    n = 3  # not a multiple of G for G = 2, 4: exercises the ragged last CTA
-    pa, pb = rng.integers(0, 2, n, dtype=np.uint8), rng.integers(0, 2, n, dtype=np.uint8)
-    ca, cb = O.encrypt_bits(1, keys, pa), O.encrypt_bits(2, keys, pb)
-    arena = np.zeros((2 * n, 640), np.uint16)
-    arena[:n, :637], arena[n:, :637] = ca, cb
-    jobs = np.zeros(n, BRJOB)
-    for g in range(n):
-        jobs[g]["in"] = (g, n + g, 0)
-        jobs[g]["sgn"] = (2, 2, 0)          # XOR: 2a + 2b + 2mu
-        jobs[g]["off"] = 2 << 13
-    ubuf = np.zeros((n, 1028), np.uint32)
-    sim.sim_blind_rotate(G, p(jobs), n, p(arena), p(bk_ntt_sim), p(ubuf), 636)
-    c = (2 * ca.astype(np.int32) + 2 * cb.astype(np.int32)).astype(np.uint16)
-    c[:, 636] += np.uint16(2 << 13)
-    assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
-
-
-@pytest.mark.parametrize("G", [1, 2, 3, 4])
-def test_blind_rotate_variant2_bit_exact(sim, keys, bk_ntt_sim, G):
-    # "one warp per transform" kernel (br2_phases.h): same result, different work decomposition
-    rng = np.random.default_rng(20 + G)
-    n = 3
-    pa, pb = rng.integers(0, 2, n, dtype=np.uint8), rng.integers(0, 2, n, dtype=np.uint8)
-    ca, cb = O.encrypt_bits(3, keys, pa), O.encrypt_bits(4, keys, pb)
-    arena = np.zeros((2 * n, 640), np.uint16)
-    arena[:n, :637], arena[n:, :637] = ca, cb
-    jobs = np.zeros(n, BRJOB)
-    for g in range(n):
-        jobs[g]["in"] = (g, n + g, 0)
-        jobs[g]["sgn"] = (-1, 1, 0)          # ANDNY: -a + b - mu
-        jobs[g]["off"] = (-(1 << 13)) & 0xFFFF
-    ubuf = np.zeros((n, 1028), np.uint32)
-    sim.sim_blind_rotate2(G, p(jobs), n, p(arena), p(bk_ntt_sim), p(ubuf), 636)
-    c = (-ca.astype(np.int32) + cb.astype(np.int32)).astype(np.uint16)
-    c[:, 636] -= np.uint16(1 << 13)
-    assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
-
-
 @pytest.mark.parametrize("G", [2, 4])
 def test_blind_rotate_variant3_bit_exact(sim, keys, bk_ntt_sim, G):
     # interleaved transforms (ct_stage3 / gs_stage3): same result as the other two decompositions
@@ -123,6 +82,27 @@ def test_blind_rotate_variant3_bit_exact(sim, keys, bk_ntt_sim, G):
     sim.sim_blind_rotate3(G, p(jobs), n, p(arena), p(bk_ntt_sim), p(ubuf), 636)
     c = (ca.astype(np.int32) + cb.astype(np.int32)).astype(np.uint16)
     c[:, 636] += np.uint16(1 << 13)
+    assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
+
+
+@pytest.mark.parametrize("G", [2, 8, 84, 82])   # 84 / 82: eight jobs per CTA in barrier groups of 4 / 2
+def test_blind_rotate_variant7_bit_exact(sim, keys, bk_ntt_sim, G):
+    # 16-warp throughput shape (br7_phases.h): swizzled tiles, x2 + x1 interleave, digit 0 / limb 2 last
+    rng = np.random.default_rng(70 + G)
+    n = 9 if G > 8 else 3  # ragged last CTA
+    pa, pb = rng.integers(0, 2, n, dtype=np.uint8), rng.integers(0, 2, n, dtype=np.uint8)
+    ca, cb = O.encrypt_bits(17, keys, pa), O.encrypt_bits(18, keys, pb)
+    arena = np.zeros((2 * n, 640), np.uint16)
+    arena[:n, :637], arena[n:, :637] = ca, cb
+    jobs = np.zeros(n, BRJOB)
+    for g in range(n):
+        jobs[g]["in"] = (g, n + g, 0)
+        jobs[g]["sgn"] = (2, 2, 0)          # XOR: 2a + 2b + 2mu
+        jobs[g]["off"] = 2 << 13
+    ubuf = np.zeros((n, 1028), np.uint32)
+    sim.sim_blind_rotate7(G, p(jobs), n, p(arena), p(bk_ntt_sim), p(ubuf), 636)
+    c = (2 * ca.astype(np.int32) + 2 * cb.astype(np.int32)).astype(np.uint16)
+    c[:, 636] += np.uint16(2 << 13)
     assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
 
 
@@ -169,26 +149,6 @@ def test_blind_rotate_variant4_bit_exact(sim, keys, bk_ntt_sim):
     assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
 
 
-def test_blind_rotate_variant5_bit_exact(sim, keys, bk_ntt_sim):
-    # cluster shape (br5_phases.h): two CTAs per job, digit tiles pushed to the peer, per-polynomial key halves
-    rng = np.random.default_rng(55)
-    n = 3
-    pa, pb = rng.integers(0, 2, n, dtype=np.uint8), rng.integers(0, 2, n, dtype=np.uint8)
-    ca, cb = O.encrypt_bits(9, keys, pa), O.encrypt_bits(10, keys, pb)
-    arena = np.zeros((2 * n, 640), np.uint16)
-    arena[:n, :637], arena[n:, :637] = ca, cb
-    jobs = np.zeros(n, BRJOB)
-    for g in range(n):
-        jobs[g]["in"] = (g, n + g, 0)
-        jobs[g]["sgn"] = (-1, -1, 0)         # NAND: -a - b + mu
-        jobs[g]["off"] = 1 << 13
-    ubuf = np.zeros((n, 1028), np.uint32)
-    sim.sim_blind_rotate5(p(jobs), n, p(arena), p(bk_ntt_sim), p(ubuf), 636)
-    c = (-ca.astype(np.int32) - cb.astype(np.int32)).astype(np.uint16)
-    c[:, 636] += np.uint16(1 << 13)
-    assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
-
-
 def test_blind_rotate_variant6_bit_exact(sim, keys, bk_ntt_sim):
     # fine-grained cluster shape (br6_phases.h): 128-thread x 8-point teams
     rng = np.random.default_rng(66)
@@ -213,7 +173,7 @@ def test_phases_are_thread_order_independent(sim, keys, bk_ntt_sim):
     """The simulator's claim (and the kernels' barrier placement) rests on every phase function being free of
     intra-phase cross-thread communication.  If that holds, running the threads and warps of each phase in
     descending or permuted order must not change a single bit; a read-after-write or write-after-read hazard inside
-    a phase (i.e. a missing barrier) would.  Checked for the three production shapes on 40 CMUX steps."""
+    a phase (i.e. a missing barrier) would.  Checked for the four production shapes on 40 CMUX steps."""
     rng = np.random.default_rng(99)
     n, steps = 2, 40
     ca, cb = O.encrypt_bits(15, keys, rng.integers(0, 2, n, dtype=np.uint8)), O.encrypt_bits(16, keys, rng.integers(0, 2, n, dtype=np.uint8))
@@ -225,6 +185,7 @@ def test_phases_are_thread_order_independent(sim, keys, bk_ntt_sim):
         jobs[g]["sgn"] = (-1, -1, 0)
         jobs[g]["off"] = 1 << 13
     runs = {"br3": lambda u: sim.sim_blind_rotate3(2, p(jobs), n, p(arena), p(bk_ntt_sim), p(u), steps),
+            "br7": lambda u: sim.sim_blind_rotate7(2, p(jobs), n, p(arena), p(bk_ntt_sim), p(u), steps),
             "br4": lambda u: sim.sim_blind_rotate4(p(jobs), n, p(arena), p(bk_ntt_sim), p(u), steps),
             "br6": lambda u: sim.sim_blind_rotate6(p(jobs), n, p(arena), p(bk_ntt_sim), p(u), steps)}
     try:
@@ -257,7 +218,7 @@ def test_blind_rotate_abar_edges(sim, keys, bk_ntt_sim):
         jobs[g]["in"] = (g, 0, 0)
         jobs[g]["sgn"] = (1, 0, 0)
     ubuf = np.zeros((2, 1028), np.uint32)
-    sim.sim_blind_rotate(2, p(jobs), 2, p(arena), p(bk_ntt_sim), p(ubuf), 636)
+    sim.sim_blind_rotate7(2, p(jobs), 2, p(arena), p(bk_ntt_sim), p(ubuf), 636)
     assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
 
 

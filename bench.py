@@ -188,6 +188,77 @@ def run_reference(args, rank: int, world: int):
     print(json.dumps(line), flush=True)
 
 
+def BN_binary_available(tools) -> bool:
+    return tools.O.IYOKAN_B200.exists() and os.environ.get("B200FHE_NETLIST_HOST", "") != "python"
+
+
+def netlist_legs(args, ctx, stream, rank, world, barrier):
+    """north_star's workload through the product path (see bench_netlist.py); every rank takes part."""
+    import torch
+    import torch.distributed as dist
+
+    import bench_netlist as BN
+    from iyokan_b200.packet import read_eval_key
+
+    names = [x for x in args.netlist_cases.split(",") if x] or (["cahp-pearl-mux", "mux-ram-8-16-16"] if world == 1 else ["cahp-pearl-mux"])
+    box = [tempfile.mkdtemp(prefix="b200fhe_net_") if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    work = Path(box[0])
+    lines = []
+    try:
+        tools = BN.RefTools(work)
+        if not tools.have_packet:
+            if rank == 0:
+                print("bench.py: oracle/_ref/iyokan-packet is not built; netlist leg skipped", file=sys.stderr)
+            return []
+        assets = work / "test"
+        if rank == 0:
+            BN._assets(assets)
+            tools.genkeys()
+        barrier()
+        use_binary = BN_binary_available(tools)
+        if not use_binary:
+            bk, ksk = read_eval_key(tools.ek)
+            ctx.load_keys(bk, ksk)
+
+        def allreduce_max(x):
+            if world == 1:
+                return float(x)
+            t = torch.tensor([x], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        def stream_events(fn):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            ev0.record(stream)
+            fn()
+            ev1.record(stream)
+            barrier()
+            ms = ev0.elapsed_time(ev1)
+            if world > 1:
+                t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms
+
+        for name in names:
+            if use_binary:
+                line = BN.run_case_binary(name, tools, assets, rank, int(os.environ.get("LOCAL_RANK", "0")), world,
+                                          args.netlist_cycles, barrier, allreduce_max, cpu=not args.no_cpu_baseline)
+            else:
+                line = BN.run_case(name, tools, assets, ctx, rank, world, args.netlist_cycles, barrier, stream_events,
+                                   cpu=not args.no_cpu_baseline)
+            if line is not None:
+                lines.append(line)
+    finally:
+        barrier()
+        if rank == 0:
+            shutil.rmtree(work, ignore_errors=True)
+    return lines
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -198,6 +269,9 @@ def main():
     ap.add_argument("--jobs-per-cta", type=int, default=0)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-netlist", action="store_true", help="skip the netlist leg (CAHP processor / mux-ram)")
+    ap.add_argument("--netlist-cycles", type=int, default=10)
+    ap.add_argument("--netlist-cases", default="", help="comma list; default: cahp-pearl-mux (+ mux-ram-8-16-16 at N=1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -314,6 +388,10 @@ def main():
     else:
         all_ok = bits_ok and exact_ok and e2e_ok
 
+    net_lines = []
+    if not args.no_netlist and not args.variant and not args.jobs_per_cta and n == BATCH:
+        net_lines = netlist_legs(args, ctx, stream, rank, world, barrier)
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         value = world * n * args.steps / (ms_total / 1e3)
@@ -355,6 +433,21 @@ def main():
                          "gate_model_frac": (value / world) * BYTES_PER_BOOTSTRAP / (peak * 1e9)},
             "outputs_ok": all_ok,
         }
+        # honest bound of the dominant kernel: the int32 multiply pipe (DRAM is idle: keys sit in L2).  Pipe cycles per
+        # CMUX step and job from the SASS of br7_kernel<8,8> (per thread and step: 2100 IMAD x 2 + 1056 IMAD.HI x 4 +
+        # 584 IMAD.WIDE x 4 + 180 IMAD.IADD/SHL x 2 cycles = 11,120 per warp; 16 warps on 4 schedulers, 8 jobs per SM)
+        sm_hz = 1e6 * ((clocks or {}).get("sm_mhz") or 1965.0)
+        pipe_cycles_per_rotation = 636 * 11120 * 4 / 8
+        alu_peak = 148 * sm_hz / pipe_cycles_per_rotation
+        line["roofline"]["alu"] = {"bound": "int32 multiply pipe (fmaheavy), 148 SMs at the sampled SM clock",
+                                   "pipe_cycles_per_rotation": pipe_cycles_per_rotation, "peak": alu_peak,
+                                   "achieved": dom["jobs"] / (dom["ms"] / 1e3), "unit": "rotations/s",
+                                   "frac": dom["jobs"] / (dom["ms"] / 1e3) / alu_peak}
+        if net_lines:
+            line["netlist"] = net_lines[0]
+            if len(net_lines) > 1:
+                line["netlist_more"] = net_lines[1:]
+            line["outputs_ok"] = bool(all_ok and all(x["outputs_ok"] for x in net_lines))
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             sample = min(n, max(cores * 512, 256))  # ~10 s of host work: the whole batch on a 16-core box

@@ -62,17 +62,16 @@ typedef struct b200fhe_ctx b200fhe_ctx;
 int b200fhe_create(b200fhe_ctx **out, int device);
 void b200fhe_destroy(b200fhe_ctx *ctx);
 const char *b200fhe_last_error(void);
-/* tuning knob: rotation jobs per CTA (1, 2, 3, 4 or 6); 0 = default: chosen per batch size (and kernel
- * variant with it).  Pinning either knob switches the heuristic off. */
+/* tuning knob: rotation jobs per CTA (2, 4, 6 for variant 3; 8 for variant 7); 0 = default: chosen per batch
+ * size (and kernel variant with it).  Pinning either knob switches the heuristic off. */
 int b200fhe_set_jobs_per_cta(b200fhe_ctx *ctx, int g);
-/* tuning knob: blind-rotation kernel variant. 1 = one warp per accumulator polynomial (2 warps per
- * job), 2 = one warp per transform (6 warps per job: lower latency per dependency level),
- * 3 = as 1 with the three transforms of a warp interleaved (more ILP per warp),
+/* tuning knob: blind-rotation kernel shape; 0 = back to the launch plan.
+ * 7 = eight jobs / 16 warps per CTA on swizzled tiles (the throughput shape the plan prefers),
+ * 3 = G jobs / 2G warps per CTA, the three transforms of a warp interleaved (12 warps at G = 6),
  * 4 = one job per CTA, 12 warps (6 teams of 64 threads), key staged into shared memory by bulk-async
  *     copies: low latency for one dependency level (jobs-per-CTA is ignored),
- * 5 = one job per 2-CTA thread-block cluster (one accumulator polynomial per SM, digit tiles exchanged
- *     by bulk-async copies through distributed shared memory), 6 teams x 64 threads x 16 points,
- * 6 = as 5 with 128-thread x 8-point teams (12 warps per SM): lowest latency, for <= 74 jobs */
+ * 6 = one job per 2-CTA thread-block cluster (one accumulator polynomial per SM, digit tiles exchanged by
+ *     bulk-async copies through distributed shared memory), 128-thread x 8-point teams: lowest latency, <= 74 jobs */
 int b200fhe_set_kernel_variant(b200fhe_ctx *ctx, int variant);
 
 /* keys: raw bootstrapping key + key-switching key in the reference's memory layout.
@@ -100,6 +99,39 @@ int b200fhe_dff_tick(b200fhe_ctx *ctx, const uint32_t *src, const uint32_t *dst,
 int b200fhe_sync(b200fhe_ctx *ctx);
 int b200fhe_query(b200fhe_ctx *ctx); /* 0 = idle, 1 = busy, <0 = error */
 
+/* programs: a static schedule recorded once, replayed as ONE CUDA graph ------------------------------ */
+/* A netlist is the same every clock cycle, so its host (include/b200net.h) records the frontiers of a clock
+ * once - b200fhe_program_batch per step, b200fhe_program_exchange where a step was sharded over ranks,
+ * b200fhe_program_tick for the DFF update - and finalises: the job lists are uploaded once and all launches
+ * are captured into one CUDA graph.  b200fhe_program_launch then costs one cudaGraphLaunch per clock.
+ * This replaces the reference's per-gate scheduling turn: Worker::update pops ONE ready node, starts it and
+ * polls it (src/iyokan.hpp:851-874, run loop src/iyokan_tfhepp.cpp:28-47); cuFHE adds three PCIe copies and
+ * a cudaStreamQuery per gate (src/iyokan_cufhe.hpp:217-241).  Arguments as b200fhe_gate_batch / _dff_tick. */
+typedef struct b200fhe_program b200fhe_program;
+int b200fhe_program_create(b200fhe_ctx *ctx, b200fhe_program **out);
+void b200fhe_program_destroy(b200fhe_program *prog);
+int b200fhe_program_batch(b200fhe_program *prog, const uint8_t *opcode, const uint32_t *in0, const uint32_t *in1,
+                          const uint32_t *in2, const uint32_t *out, size_t n);
+int b200fhe_program_tick(b200fhe_program *prog, const uint32_t *src, const uint32_t *dst, size_t n);
+int b200fhe_program_exchange(b200fhe_program *prog, size_t first_slot, size_t slots_per_rank);
+int b200fhe_program_finalize(b200fhe_program *prog);
+int b200fhe_program_launch(b200fhe_program *prog); /* asynchronous on the context's stream */
+/* any pointer may be NULL.  is_graph = 0 when the capture was refused and the program replays launch by launch */
+int b200fhe_program_info(const b200fhe_program *prog, uint64_t *rotations, uint64_t *launches_per_replay,
+                         uint64_t *exchanges, uint64_t *exchanged_slots, int *is_graph, double *model_ms);
+
+/* multi-GPU exchange: one process per GPU, identical arena layout on every rank ------------------------ */
+/* Replaces cufhe::SetGPUNum + round-robin streams through host memory (cuFHE include/cufhe_gpu.cuh:164-169,
+ * src/iyokan_cufhe.cpp:533).  Rank 0 creates a 128-byte id (ncclUniqueId) and hands it to the other ranks
+ * by any host channel; every rank then calls b200fhe_comm_init.  b200fhe_exchange is ONE in-place all-gather
+ * over NVLink (NCCL, bound at run time with dlopen): rank r contributes slots
+ * [first_slot + r*slots_per_rank, first_slot + (r+1)*slots_per_rank), afterwards every rank holds all of them. */
+int b200fhe_comm_unique_id(uint8_t *id128);
+int b200fhe_comm_init(b200fhe_ctx *ctx, int rank, int world, const uint8_t *id128);
+int b200fhe_comm_rank(const b200fhe_ctx *ctx);
+int b200fhe_comm_world(const b200fhe_ctx *ctx);
+int b200fhe_exchange(b200fhe_ctx *ctx, size_t first_slot, size_t slots_per_rank);
+
 /* End-to-end convenience with HOST operands: uploads, evaluates, downloads (synchronous).
  * in*_host / out_host are [n][637] uint16; needs an arena of at least 4*n slots. */
 int b200fhe_gates_host(b200fhe_ctx *ctx, const uint8_t *opcode, const uint16_t *in0_host,
@@ -115,7 +147,7 @@ uint64_t b200fhe_launch_count(const b200fhe_ctx *ctx);
 /* device time (ms, CUDA events on the context's stream) spent in the blind-rotation kernel /
  * key-switch kernel by the most recent b200fhe_gate_batch; valid after b200fhe_sync */
 int b200fhe_last_batch_ms(b200fhe_ctx *ctx, float *blind_rotate_ms, float *keyswitch_ms);
-/* the launch plan of that batch: a frontier is cut into at most four blind-rotation launches (full
+/* the launch plan of that batch: a frontier is cut into at most five blind-rotation launches (full
  * waves of the throughput kernels, the tail on the latency kernels).  Fills up to max_segments entries
  * (kernel variant, jobs per CTA, rotation jobs, device ms) and returns the number of segments, -1 on error. */
 int b200fhe_last_batch_segments(b200fhe_ctx *ctx, int *variant, int *jobs_per_cta, int *jobs, float *ms,

@@ -69,6 +69,24 @@ int b200net_run(b200net *net);                                /* every level, wh
 /* multi-GPU building block: evaluate only rank's contiguous share of one level */
 int b200net_run_level_shard(b200net *net, size_t level, int rank, int world_size);
 
+/* ---- static schedule + compiled replay (the path the front ends use) ----------------------------------- */
+#define B200NET_PACK 1u /* pull gates with slack forward into under-full steps when the launch-plan model gains */
+/* Schedules one clock cycle for `world` ranks (steps = frontiers; each replicated on every rank or sharded with
+ * one all-gather), assigns arena slots, and compiles rank `rank`'s share into two b200fhe programs (clock, tick),
+ * each ONE CUDA graph.  ctx must have keys loaded and, for world > 1, b200fhe_comm_init done.
+ * Afterwards b200net_run / b200net_tick replay the graphs; set / get / restore work as after b200net_bind. */
+int b200net_bind_rank(b200net *net, b200fhe_ctx *ctx, int rank, int world, unsigned flags);
+/* the schedule alone (no GPU): what b200net_bind_rank would run */
+int b200net_schedule(b200net *net, int world, unsigned flags);
+size_t b200net_num_steps(const b200net *net);
+size_t b200net_step_jobs(const b200net *net, size_t step, int *sharded); /* rotation jobs of a step, all ranks */
+/* the gates `rank` evaluates in a step (replicated ones + its share); returns the count, fills up to cap node ids */
+size_t b200net_step_gates(const b200net *net, size_t step, int rank, uint32_t *nodes, size_t cap);
+/* the all-gather that follows a step: slots [first + r*per_rank, first + (r+1)*per_rank) come from rank r; per_rank = 0: none */
+int b200net_step_exchange(const b200net *net, size_t step, uint32_t *first_slot, size_t *slots_per_rank);
+int b200net_schedule_info(const b200net *net, size_t *steps, size_t *collectives, size_t *exchanged_slots,
+                          double *model_ms, int *packed);
+
 #ifdef __cplusplus
 }
 #endif

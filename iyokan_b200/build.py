@@ -35,7 +35,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     srcs = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.h")) + [ROOT / "include" / "b200fhe.h"]
     if not force and _newer(out, srcs):
         return out
-    cmd = [_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(out), str(CSRC / "b200fhe.cu")]
+    cmd = [_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(out), str(CSRC / "b200fhe.cu"), "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)

@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <dlfcn.h>
 #include <string>
 #include <vector>
 
@@ -506,12 +508,51 @@ struct b200fhe_ctx {
     cudaEvent_t ev_seg[BR_MAX_SEGMENTS + 1] = {};
     int seg_n = 0, seg_variant[BR_MAX_SEGMENTS] = {}, seg_G[BR_MAX_SEGMENTS] = {}, seg_count[BR_MAX_SEGMENTS] = {};
     uint64_t launches = 0;
+    // multi-GPU exchange (one process per GPU): NCCL communicator, created by b200fhe_comm_init
+    void* comm = nullptr;
+    int rank = 0, world = 1;
 };
 
 static int set_dev(b200fhe_ctx* c)
 {
     CK(cudaSetDevice(c->device));
     return 0;
+}
+
+// NCCL, bound at run time (see the exchange section below)
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load()
+{
+    if (g_nccl.lib) return 0;
+    const char* names[] = {getenv("B200FHE_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names)
+        if (n && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!h) return fail(std::string("cannot load NCCL (libnccl.so.2): ") + dlerror());
+    NcclApi a;
+    a.lib = h;
+    a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(h, "ncclAllGather"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    if (!a.GetUniqueId || !a.CommInitRank || !a.AllGather || !a.CommDestroy) return fail("libnccl lacks the expected symbols");
+    g_nccl = a;
+    return 0;
+}
+static int nccl_fail(const char* what, int rc)
+{
+    return fail(std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "NCCL error") + " (" +
+                std::to_string(rc) + ")");
 }
 
 // ---- launch plan ------------------------------------------------------------------------------------
@@ -526,8 +567,8 @@ struct BrShape { int variant, G, wave_jobs; double wave_ms; };
 struct BrSegment { int variant, G, count; };
 struct PlanTable {
     BrShape shape[N_SHAPES] = {
-        {7, 8, 1184, 16.6},  // 16-warp throughput shape
-        {3, 6, 888, 14.68},  // 12-warp throughput shape (kept for the ablation; normally dominated by 7)
+        {7, 8, 1184, 18.98}, // 16-warp throughput shape: 62.4 k rotations/s
+        {3, 6, 888, 14.70},  // 12-warp throughput shape: 60.4 k/s, fills the gap between one and two 16-warp waves
         {3, 4, 592, 10.25},
         {4, 1, 148, 3.02},   // one job per SM
         {6, 1, 74, 2.06},    // one job per 2-SM cluster: lowest latency
@@ -605,11 +646,6 @@ static int plan_rotation(const b200fhe_ctx* c, int njobs, BrSegment (&seg)[BR_MA
 template <int G>
 static int br3_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
 {
-    static bool attr_set[64] = {};
-    if (!attr_set[c->device]) {
-        CK(cudaFuncSetAttribute(br3_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BrSmem<G>::BYTES));
-        attr_set[c->device] = true;
-    }
     const int grid = (njobs + G - 1) / G;
     br3_kernel<G><<<grid, 64 * G, BrSmem<G>::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_tw2f,
                                                                   c->d_tw2i, ubuf, N0);
@@ -621,11 +657,6 @@ static int br3_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
 template <int G, int J>
 static int br7_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
 {
-    static bool attr_set[64] = {};
-    if (!attr_set[c->device]) {
-        CK(cudaFuncSetAttribute(br7_kernel<G, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br7Smem<G>::BYTES));
-        attr_set[c->device] = true;
-    }
     const int grid = (njobs + G - 1) / G;
     br7_kernel<G, J><<<grid, 64 * G, Br7Smem<G>::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_tw2f,
                                                                      c->d_tw2i, ubuf, N0, c->br7_skew);
@@ -636,11 +667,6 @@ static int br7_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
 
 static int br4_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
 {
-    static bool attr_set[64] = {};
-    if (!attr_set[c->device]) {
-        CK(cudaFuncSetAttribute(br4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br4Smem::BYTES));
-        attr_set[c->device] = true;
-    }
     br4_kernel<<<njobs, BR4_THREADS, Br4Smem::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_blocktw, ubuf, N0);
     CK(cudaGetLastError());
     c->launches++;
@@ -649,14 +675,23 @@ static int br4_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
 
 static int br6_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
 {
-    static bool attr_set[64] = {};
-    if (!attr_set[c->device]) {
-        CK(cudaFuncSetAttribute(br6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br6Smem::BYTES));
-        attr_set[c->device] = true;
-    }
     br6_kernel<<<2 * njobs, BR6_THREADS, Br6Smem::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_block8tw, ubuf, N0);
     CK(cudaGetLastError());
     c->launches++;
+    return 0;
+}
+
+// dynamic shared memory opt-in of every blind-rotation shape, once per device (never inside a graph capture)
+static int set_kernel_attrs()
+{
+    CK(cudaFuncSetAttribute(br3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BrSmem<2>::BYTES));
+    CK(cudaFuncSetAttribute(br3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BrSmem<4>::BYTES));
+    CK(cudaFuncSetAttribute(br3_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BrSmem<6>::BYTES));
+    CK(cudaFuncSetAttribute(br7_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br7Smem<8>::BYTES));
+    CK(cudaFuncSetAttribute(br7_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br7Smem<8>::BYTES));
+    CK(cudaFuncSetAttribute(br7_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br7Smem<8>::BYTES));
+    CK(cudaFuncSetAttribute(br4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br4Smem::BYTES));
+    CK(cudaFuncSetAttribute(br6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br6Smem::BYTES));
     return 0;
 }
 
@@ -684,17 +719,18 @@ static int br_dispatch_one(b200fhe_ctx* c, int variant, int G, int njobs, const 
 }
 
 // rotation job k writes ubuf[k]: segments are contiguous ranges of the job list
-static int br_dispatch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+static int br_dispatch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs,
+                       bool timing = true)
 {
     BrSegment seg[BR_MAX_SEGMENTS];
     const int nseg = plan_rotation(c, njobs, seg);
     int first = 0;
-    CK(cudaEventRecord(c->ev_seg[0], c->stream));
+    if (timing) CK(cudaEventRecord(c->ev_seg[0], c->stream));
     for (int k = 0; k < nseg; k++) {
         if (br_dispatch_one(c, seg[k].variant, seg[k].G, seg[k].count, arena, ubuf + (size_t)first * U_STRIDE,
                             d_jobs + first))
             return 1;
-        CK(cudaEventRecord(c->ev_seg[k + 1], c->stream));
+        if (timing) CK(cudaEventRecord(c->ev_seg[k + 1], c->stream));
         c->seg_variant[k] = seg[k].variant;
         c->seg_G[k] = (seg[k].variant == 4 || seg[k].variant == 6) ? 1 : seg[k].G;
         c->seg_count[k] = seg[k].count;
@@ -764,6 +800,7 @@ int b200fhe_create(b200fhe_ctx** out, int device)
     if (prop.major != 10)
         return fail(std::string("b200fhe is built for sm_100a only; device is sm_") + std::to_string(prop.major) +
                     std::to_string(prop.minor));
+    if (set_kernel_attrs()) return 1;
     b200fhe_ctx* c = new b200fhe_ctx();
     c->device = device;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -819,6 +856,7 @@ void b200fhe_destroy(b200fhe_ctx* c)
     cudaFree(c->d_ubuf);
     cudaFree(c->d_unstage);
     cudaFree(c->d_kspart);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     cudaEventDestroy(c->ev_staged);
     for (auto& e : c->ev_t) cudaEventDestroy(e);
     for (auto& e : c->ev_seg) cudaEventDestroy(e);
@@ -1132,6 +1170,290 @@ int b200fhe_host_free(void* ptr)
     CK(cudaFreeHost(ptr));
     return 0;
 }
+
+}  // extern "C"
+
+// ---- multi-GPU exchange --------------------------------------------------------------------------------
+// The netlist engine shards a dependency level over the ranks (one process per GPU, replicated arena layout)
+// and replicates the level's outputs with ONE in-place all-gather over NVLink.  NCCL is bound at run time
+// (dlopen of libnccl.so.2, the library torch.distributed already has in the process, or the system one), so
+// single-GPU users of this library need no NCCL at all.  Reference hook this replaces: cufhe::SetGPUNum +
+// round-robin streams through host memory (cuFHE include/cufhe_gpu.cuh:164-169, src/iyokan_cufhe.cpp:533).
+static int exchange_issue(b200fhe_ctx* c, size_t first_slot, size_t slots_per_rank)
+{
+    if (c->world == 1 || slots_per_rank == 0) return 0;
+    if (!c->comm) return fail("no communicator: call b200fhe_comm_init first");
+    if (first_slot + slots_per_rank * (size_t)c->world > c->n_slots) return fail("exchange range exceeds the arena");
+    uint8_t* base = reinterpret_cast<uint8_t*>(c->d_arena) + first_slot * (size_t)SLOT_STRIDE * 2;
+    const size_t bytes = slots_per_rank * (size_t)SLOT_STRIDE * 2;
+    const int rc = g_nccl.AllGather(base + (size_t)c->rank * bytes, base, bytes, /*ncclUint8*/ 1, c->comm, c->stream);
+    if (rc) return nccl_fail("ncclAllGather", rc);
+    return 0;
+}
+
+// ---- programs: a static schedule recorded once and replayed as one CUDA graph ---------------------------
+// The netlist is the same every clock cycle, so the host builds the job lists of every dependency level
+// ONCE, uploads them once, and captures all launches of a clock (unary ops, blind rotations, key switches,
+// exchanges, the DFF tick) into one CUDA graph; a clock cycle is then a single cudaGraphLaunch.
+struct ProgStep {
+    int kind = 0;  // 0 = gate batch, 1 = tick (parallel copy), 2 = exchange
+    size_t br_off = 0, nbr = 0, ks_off = 0, nks = 0, un_off = 0, nun = 0;
+    size_t first_slot = 0, slots_per_rank = 0;
+};
+struct b200fhe_program {
+    b200fhe_ctx* c = nullptr;
+    std::vector<BrJob> h_br;
+    std::vector<KsJob> h_ks;
+    std::vector<UnaryJob> h_un;
+    std::vector<ProgStep> steps;
+    BrJob* d_br = nullptr;
+    KsJob* d_ks = nullptr;
+    UnaryJob* d_un = nullptr;
+    uint32_t* d_ubuf = nullptr;
+    uint32_t* d_unstage = nullptr;
+    size_t max_nbr = 0, max_nun = 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool finalized = false;
+    uint64_t launches_per_replay = 0, rotations = 0, exchanges = 0, exchanged_slots = 0;
+    double model_ms = 0.0;
+};
+
+static int program_issue(b200fhe_program* p)
+{
+    b200fhe_ctx* c = p->c;
+    uint32_t* aw = reinterpret_cast<uint32_t*>(c->d_arena);
+    for (const ProgStep& st : p->steps) {
+        if (st.kind == 2) {
+            if (exchange_issue(c, st.first_slot, st.slots_per_rank)) return 1;
+            continue;
+        }
+        if (st.nun) {  // gather, then scatter: every source is read before any destination is written
+            unary_gather_kernel<<<(unsigned)st.nun, KS_THREADS, 0, c->stream>>>(p->d_un + st.un_off, aw, p->d_unstage);
+            unary_scatter_kernel<<<(unsigned)st.nun, KS_THREADS, 0, c->stream>>>(p->d_un + st.un_off, p->d_unstage, aw);
+            CK(cudaGetLastError());
+            c->launches += 2;
+        }
+        if (st.nbr) {
+            if (br_dispatch(c, (int)st.nbr, c->d_arena, p->d_ubuf, p->d_br + st.br_off, false)) return 1;
+            if (ks_dispatch(c, st.nks, p->d_ks + st.ks_off, p->d_ubuf, c->d_arena)) return 1;
+        }
+    }
+    return 0;
+}
+
+extern "C" {
+
+int b200fhe_comm_unique_id(uint8_t* id128)
+{
+    if (!id128) return fail("null argument");
+    if (nccl_load()) return 1;
+    NcclId id;
+    const int rc = g_nccl.GetUniqueId(&id);
+    if (rc) return nccl_fail("ncclGetUniqueId", rc);
+    std::memcpy(id128, id.internal, 128);
+    return 0;
+}
+
+int b200fhe_comm_init(b200fhe_ctx* c, int rank, int world, const uint8_t* id128)
+{
+    if (!c) return fail("null context");
+    if (world < 1 || rank < 0 || rank >= world) return fail("bad rank / world size");
+    if (c->comm) {
+        g_nccl.CommDestroy(c->comm);
+        c->comm = nullptr;
+    }
+    c->rank = rank;
+    c->world = world;
+    if (world == 1) return 0;
+    if (!id128) return fail("null unique id");
+    if (set_dev(c) || nccl_load()) return 1;
+    NcclId id;
+    std::memcpy(id.internal, id128, 128);
+    const int rc = g_nccl.CommInitRank(&c->comm, world, id, rank);
+    if (rc) return nccl_fail("ncclCommInitRank", rc);
+    return 0;
+}
+
+int b200fhe_comm_rank(const b200fhe_ctx* c) { return c ? c->rank : 0; }
+int b200fhe_comm_world(const b200fhe_ctx* c) { return c ? c->world : 1; }
+
+int b200fhe_exchange(b200fhe_ctx* c, size_t first_slot, size_t slots_per_rank)
+{
+    if (!c) return fail("null context");
+    if (!c->d_arena) return fail("no arena allocated");
+    if (set_dev(c)) return 1;
+    return exchange_issue(c, first_slot, slots_per_rank);
+}
+
+int b200fhe_program_create(b200fhe_ctx* c, b200fhe_program** out)
+{
+    if (!c || !out) return fail("null argument");
+    *out = new b200fhe_program();
+    (*out)->c = c;
+    return 0;
+}
+
+void b200fhe_program_destroy(b200fhe_program* p)
+{
+    if (!p) return;
+    if (p->c) {
+        cudaSetDevice(p->c->device);
+        cudaStreamSynchronize(p->c->stream);
+    }
+    if (p->exec) cudaGraphExecDestroy(p->exec);
+    if (p->graph) cudaGraphDestroy(p->graph);
+    cudaFree(p->d_br);
+    cudaFree(p->d_ks);
+    cudaFree(p->d_un);
+    cudaFree(p->d_ubuf);
+    cudaFree(p->d_unstage);
+    delete p;
+}
+
+int b200fhe_program_batch(b200fhe_program* p, const uint8_t* opcode, const uint32_t* in0, const uint32_t* in1,
+                          const uint32_t* in2, const uint32_t* out, size_t n)
+{
+    if (!p) return fail("null program");
+    if (p->finalized) return fail("program already finalized");
+    if (n == 0) return 0;
+    if (!opcode || !out) return fail("null argument");
+    if (!p->c->d_arena) return fail("no arena allocated");
+    std::vector<BrJob> br(2 * n);
+    std::vector<KsJob> ks(n);
+    std::vector<UnaryJob> un(n);
+    BatchCounts cnt;
+    if (const char* err = build_gate_jobs(opcode, in0, in1, in2, out, n, p->c->n_slots, br.data(), ks.data(), un.data(), cnt))
+        return fail(err);
+    ProgStep st;
+    st.kind = 0;
+    st.br_off = p->h_br.size();
+    st.nbr = cnt.nbr;
+    st.ks_off = p->h_ks.size();
+    st.nks = cnt.nks;
+    st.un_off = p->h_un.size();
+    st.nun = cnt.nun;
+    p->h_br.insert(p->h_br.end(), br.begin(), br.begin() + cnt.nbr);
+    p->h_ks.insert(p->h_ks.end(), ks.begin(), ks.begin() + cnt.nks);
+    p->h_un.insert(p->h_un.end(), un.begin(), un.begin() + cnt.nun);
+    p->max_nbr = std::max(p->max_nbr, cnt.nbr);
+    p->max_nun = std::max(p->max_nun, cnt.nun);
+    p->rotations += cnt.nbr;
+    if (cnt.nbr) p->model_ms += b200fhe_plan_ms((int)cnt.nbr);
+    p->steps.push_back(st);
+    return 0;
+}
+
+int b200fhe_program_tick(b200fhe_program* p, const uint32_t* src, const uint32_t* dst, size_t n)
+{
+    if (!p) return fail("null program");
+    if (p->finalized) return fail("program already finalized");
+    if (n == 0) return 0;
+    if (!src || !dst) return fail("null argument");
+    if (!p->c->d_arena) return fail("no arena allocated");
+    if (check_slots(p->c, src, n) || check_slots(p->c, dst, n)) return 1;
+    ProgStep st;
+    st.kind = 1;
+    st.un_off = p->h_un.size();
+    st.nun = n;
+    for (size_t i = 0; i < n; i++) p->h_un.push_back(UnaryJob{src[i], dst[i], (uint32_t)OP_COPY});
+    p->max_nun = std::max(p->max_nun, n);
+    p->steps.push_back(st);
+    return 0;
+}
+
+int b200fhe_program_exchange(b200fhe_program* p, size_t first_slot, size_t slots_per_rank)
+{
+    if (!p) return fail("null program");
+    if (p->finalized) return fail("program already finalized");
+    if (slots_per_rank == 0 || p->c->world == 1) return 0;
+    if (first_slot + slots_per_rank * (size_t)p->c->world > p->c->n_slots) return fail("exchange range exceeds the arena");
+    ProgStep st;
+    st.kind = 2;
+    st.first_slot = first_slot;
+    st.slots_per_rank = slots_per_rank;
+    p->exchanges++;
+    p->exchanged_slots += slots_per_rank * (size_t)p->c->world;
+    p->steps.push_back(st);
+    return 0;
+}
+
+int b200fhe_program_finalize(b200fhe_program* p)
+{
+    if (!p) return fail("null program");
+    if (p->finalized) return 0;
+    b200fhe_ctx* c = p->c;
+    if (!c->keys && p->rotations) return fail("keys not loaded");
+    if (set_dev(c)) return 1;
+    auto up = [&](auto** d, const auto& h) -> int {
+        if (h.empty()) return 0;
+        CK(cudaMalloc(d, h.size() * sizeof(h[0])));
+        CK(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(h[0]), cudaMemcpyHostToDevice, c->stream));
+        return 0;
+    };
+    if (up(&p->d_br, p->h_br) || up(&p->d_ks, p->h_ks) || up(&p->d_un, p->h_un)) return 1;
+    if (p->max_nbr) CK(cudaMalloc(&p->d_ubuf, p->max_nbr * (size_t)U_STRIDE * 4));
+    if (p->max_nun) CK(cudaMalloc(&p->d_unstage, p->max_nun * (size_t)KS_THREADS * 4));
+    CK(cudaStreamSynchronize(c->stream));
+    p->finalized = true;
+    // capture one replay; if the capture is refused (driver / NCCL build without graph support) the program
+    // still runs, launch by launch, from the resident job lists
+    const uint64_t l0 = c->launches;
+    const char* no_graph = getenv("B200FHE_NO_GRAPH");
+    bool captured = false;
+    if (!(no_graph && no_graph[0] == '1') && !p->steps.empty()) {
+        if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int rc = program_issue(p);
+            cudaGraph_t g = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            if (rc == 0 && e == cudaSuccess && g && cudaGraphInstantiate(&p->exec, g, 0) == cudaSuccess) {
+                p->graph = g;
+                captured = true;
+            } else {
+                if (g) cudaGraphDestroy(g);
+                p->exec = nullptr;
+                cudaGetLastError();  // clear the sticky capture error
+            }
+        }
+        p->launches_per_replay = c->launches - l0;
+        c->launches = l0;
+    }
+    if (!captured) {  // count the launches of one eager replay without running it twice: issue once now
+        p->launches_per_replay = 0;
+    }
+    return 0;
+}
+
+int b200fhe_program_launch(b200fhe_program* p)
+{
+    if (!p) return fail("null program");
+    if (!p->finalized && b200fhe_program_finalize(p)) return 1;
+    b200fhe_ctx* c = p->c;
+    if (set_dev(c)) return 1;
+    if (p->exec) {
+        CK(cudaGraphLaunch(p->exec, c->stream));
+        c->launches += p->launches_per_replay;
+        return 0;
+    }
+    return program_issue(p);
+}
+
+int b200fhe_program_info(const b200fhe_program* p, uint64_t* rotations, uint64_t* launches_per_replay, uint64_t* exchanges,
+                         uint64_t* exchanged_slots, int* is_graph, double* model_ms)
+{
+    if (!p) return fail("null program");
+    if (rotations) *rotations = p->rotations;
+    if (launches_per_replay) *launches_per_replay = p->launches_per_replay;
+    if (exchanges) *exchanges = p->exchanges;
+    if (exchanged_slots) *exchanged_slots = p->exchanged_slots;
+    if (is_graph) *is_graph = p->exec ? 1 : 0;
+    if (model_ms) *model_ms = p->model_ms;
+    return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ---- test hooks -------------------------------------------------------------------------
 

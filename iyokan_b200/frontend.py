@@ -36,8 +36,8 @@ class FrontendError(ValueError):
 class Frontend:
     def __init__(self, nl: Netlist, mode: str, ctx=None, rank: int = 0, world: int = 1, group=None):
         """rank / world / group: one process per GPU under torch.distributed (`torchrun -m iyokan_b200 tfhe ...`):
-        every rank holds the whole state, each dependency level is split between the ranks when that pays and its
-        outputs are all-gathered (iyokan_b200/shard.py); rank 0 writes the result."""
+        every rank holds the whole state, a step of the static schedule is split between the ranks when that pays and
+        its outputs are all-gathered (b200net_bind_rank; iyokan_b200/shard.py); rank 0 writes the result."""
         if mode not in ("plain", "tfhe"):
             raise FrontendError("mode must be 'plain' or 'tfhe'")
         if mode == "tfhe" and ctx is None:
@@ -51,15 +51,18 @@ class Frontend:
         self.rams: dict = {}
         self._all = np.arange(nl.n, dtype=np.uint32)
         self.be = self.runner = None
-        if world > 1:
-            from .shard import GpuBackend, PlainBackend, ShardedRunner
+        if world > 1 and mode == "plain":
+            from .shard import PlainBackend, ScheduledRunner
 
-            self.be = PlainBackend(nl, self.eng, world) if mode == "plain" else GpuBackend(nl, self.eng, ctx, world)
-            self.runner = ShardedRunner(nl, self.eng, self.be, rank, world, group=group, min_shard_width=None)
+            self.be = PlainBackend(nl, self.eng, world)
+            self.runner = ScheduledRunner(nl, self.eng, self.be, rank, world, group=group)
         elif mode == "plain":
             self.v = np.zeros(nl.n, np.uint8)
-        else:
-            self.eng.bind(ctx, 1)
+        else:  # one CUDA graph per clock; for world > 1 the all-gathers of the sharded steps are inside it
+            from .shard import setup_comm
+
+            setup_comm(ctx, rank, world, group)
+            self.eng.bind_rank(ctx, rank, world)
         if mode == "tfhe":
             dffs = np.nonzero(nl.kind == DFF)[0]
             if dffs.size:  # DFF initial value: trivial 0 (iyokan_tfhepp.hpp:23-27)
@@ -128,9 +131,13 @@ class Frontend:
                 raise FrontendError("@reset cannot be set by the request (iyokan_tfhepp.cpp:284-285)")
             if name not in self.nl.in_ports:
                 raise FrontendError(f"request drives unknown input port @{name}")
-        for name in list(rams) + list(roms):
-            if name not in self.nl.mem:
-                raise FrontendError(f"request initialises unknown memory {name!r}")
+        for kind, mems in (("RAM", rams), ("ROM", roms)):
+            for name, v in mems.items():
+                if name not in self.nl.mem:
+                    raise FrontendError(f"request initialises unknown memory {name!r}")
+                if len(v) != len(self.nl.mem[name]):  # iyokan_tfhepp.cpp:242-259 ("wrong length of RAM")
+                    raise FrontendError(f"Invalid request packet: wrong length of {kind} {name!r} "
+                                        f"({len(v)} bits given, the memory holds {len(self.nl.mem[name])})")
         self.streams = {k: np.asarray(v) for k, v in bits.items()}
         self.rams = {k: np.asarray(v) for k, v in rams.items() if self.nl.kind[self.nl.mem[k][0]] == DFF}
         for name, v in roms.items():

@@ -74,6 +74,20 @@ struct b200net {
     };
     std::vector<Batch> batches;
     std::vector<uint32_t> tick_src, tick_dst;
+    // ---- compiled schedule (b200net_bind_rank): steps instead of ASAP levels, one CUDA graph per clock ----
+    struct Step {
+        std::vector<uint32_t> rep;   // gates every rank evaluates (no exchange)
+        std::vector<uint32_t> shd;   // gates split over the ranks, outputs all-gathered after the step
+        std::vector<size_t> cut;     // shd[cut[r] .. cut[r+1]) belongs to rank r (world + 1 entries)
+        size_t chunk = 0;            // slots per rank of the sharded region
+        uint32_t base_rep = 0, base_shd = 0;
+        size_t jobs_rep = 0, jobs_shd = 0;
+    };
+    std::vector<Step> steps;
+    bool compiled = false, packed = false;
+    int rank = 0;
+    double model_ms = 0.0;
+    b200fhe_program *run_prog = nullptr, *tick_prog = nullptr;
 
     uint32_t resolve(uint32_t node) const
     {
@@ -158,7 +172,13 @@ int b200net_create(b200net** out, size_t n, const uint8_t* kind, const int32_t* 
     return 0;
 }
 
-void b200net_destroy(b200net* net) { delete net; }
+void b200net_destroy(b200net* net)
+{
+    if (!net) return;
+    b200fhe_program_destroy(net->run_prog);
+    b200fhe_program_destroy(net->tick_prog);
+    delete net;
+}
 size_t b200net_num_nodes(const b200net* net) { return net->n; }
 size_t b200net_num_levels(const b200net* net) { return net->levels.size(); }
 size_t b200net_level_width(const b200net* net, size_t l) { return l < net->levels.size() ? net->levels[l].size() : 0; }
@@ -250,6 +270,7 @@ int b200net_bind(b200net* net, b200fhe_ctx* ctx, int world)
     if (!net || !ctx) return fail("null argument");
     if (b200net_layout(net, world)) return 1;
     net->ctx = ctx;
+    net->compiled = false;
     if (b200fhe_arena_alloc(ctx, std::max<size_t>(net->n_slots, 1))) return fail(b200fhe_last_error());
     return 0;
 }
@@ -296,6 +317,11 @@ int b200net_get(b200net* net, const uint32_t* nodes, uint16_t* tlwe, size_t n)
 int b200net_tick(b200net* net)
 {
     if (!net || !net->ctx) return fail("netlist is not bound to a context");
+    if (net->compiled) {
+        if (net->tick_src.empty()) return 0;
+        if (b200fhe_program_launch(net->tick_prog)) return fail(b200fhe_last_error());
+        return 0;
+    }
     if (b200fhe_dff_tick(net->ctx, net->tick_src.data(), net->tick_dst.data(), net->tick_src.size()))
         return fail(b200fhe_last_error());
     return 0;
@@ -304,6 +330,7 @@ int b200net_tick(b200net* net)
 int b200net_run_level_shard(b200net* net, size_t level, int rank, int world)
 {
     if (!net || !net->ctx) return fail("netlist is not bound to a context");
+    if (net->compiled) return fail("netlist was compiled with b200net_bind_rank: use b200net_run");
     if (level >= net->batches.size()) return fail("level out of range");
     // world may be 1 (whole level, used for levels too narrow to shard) or the bound world size
     if ((world != net->world && world != 1) || rank < 0 || rank >= world) return fail("rank/world mismatch with bind");
@@ -320,8 +347,306 @@ int b200net_run_level_shard(b200net* net, size_t level, int rank, int world)
 int b200net_run(b200net* net)
 {
     if (!net || !net->ctx) return fail("netlist is not bound to a context");
+    if (net->compiled) {
+        if (b200fhe_program_launch(net->run_prog)) return fail(b200fhe_last_error());
+        return 0;
+    }
     for (size_t l = 0; l < net->batches.size(); l++)
         if (b200net_run_level_shard(net, l, 0, 1)) return 1;
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- static scheduling ---------------------------------------------------------------------------------
+// The reference orders ready nodes by HEFT upward rank (graph::doRankuSort, src/iyokan.cpp:4-98) and lets
+// N workers pop them one at a time.  Here the whole clock cycle is scheduled once: a sequence of STEPS,
+// each one frontier of independent gates.  With packing off a step is an ASAP dependency level.  With
+// packing on, gates that have slack (ALAP level later than ASAP level) are pulled forward into steps whose
+// mandatory gates leave SMs idle, as long as the launch-plan model (b200fhe_plan_ms) says the step gets
+// cheaper per job than the throughput shape would later charge for them; the schedule with the lower
+// modelled clock time is kept.  On `world` ranks a step is either replicated (every rank evaluates all of
+// it, no exchange) or sharded (contiguous shares balanced by rotation count, outputs all-gathered).
+namespace {
+
+struct Scheduler {
+    const b200net& net;
+    int world;
+    double exch_ms;
+    std::vector<int32_t> alap;
+    std::vector<uint8_t> jobs;
+    Scheduler(const b200net& n, int w, double x) : net(n), world(w), exch_ms(x) {}
+
+    // cost (ms) of one step with `total` rotation jobs: replicated, or sharded over the ranks
+    double step_cost(size_t total, bool* shard) const
+    {
+        const double rep = b200fhe_plan_ms((int)total);
+        if (world == 1 || total == 0) {
+            if (shard) *shard = false;
+            return rep;
+        }
+        const double shd = b200fhe_plan_ms((int)((total + world - 1) / world)) + exch_ms;
+        if (shard) *shard = shd < rep;
+        return shd < rep ? shd : rep;
+    }
+
+    void compute_alap()
+    {
+        const size_t n = net.n;
+        const int32_t D = (int32_t)net.levels.size();
+        alap.assign(n, D);
+        jobs.assign(n, 0);
+        for (size_t i = 0; i < n; i++) jobs[i] = (uint8_t)bootstraps(net.kind[i]);
+        // reverse ASAP order: users of a gate are on strictly later levels
+        for (int32_t l = D - 1; l >= 0; l--)
+            for (uint32_t g : net.levels[l]) {
+                const int ar = arity(net.kind[g]);
+                for (int k = 0; k < ar; k++) {
+                    const uint32_t src = net.resolve((uint32_t)net.in[k][g]);
+                    if (is_gate(net.kind[src])) alap[src] = std::min(alap[src], alap[g] - 1);
+                }
+            }
+    }
+
+    // returns modelled ms; fills steps (without slots)
+    double build(bool pack, std::vector<b200net::Step>& steps) const
+    {
+        const size_t n = net.n;
+        const int32_t D = (int32_t)net.levels.size();
+        steps.clear();
+        steps.resize(D);
+        std::vector<int32_t> when(n, -1);  // step (1-based) a node's value is produced in; 0 = source
+        for (size_t i = 0; i < n; i++)
+            if (net.kind[i] == B200NET_INPUT || net.kind[i] == B200NET_DFF) when[i] = 0;
+        // the throughput rate later steps would charge for a job that is not pulled forward
+        const double wide = 4736.0;
+        const double ms_per_job = step_cost((size_t)wide * world, nullptr) / (wide * world);
+        std::vector<uint32_t> pending;  // gates not yet scheduled, kept sorted by (alap, asap)
+        for (const auto& lv : net.levels) pending.insert(pending.end(), lv.begin(), lv.end());
+        std::stable_sort(pending.begin(), pending.end(), [&](uint32_t a, uint32_t b) {
+            return alap[a] != alap[b] ? alap[a] < alap[b] : net.level[a] < net.level[b];
+        });
+        auto ready = [&](uint32_t g, int32_t L) {
+            const int ar = arity(net.kind[g]);
+            for (int k = 0; k < ar; k++) {
+                const int32_t w = when[net.resolve((uint32_t)net.in[k][g])];
+                if (w < 0 || w >= L) return false;
+            }
+            return true;
+        };
+        double total_ms = 0.0;
+        for (int32_t L = 1; L <= D; L++) {
+            std::vector<uint32_t> take, cand;
+            size_t mj = 0;
+            for (uint32_t g : pending) {
+                const bool mandatory = pack ? alap[g] <= L : net.level[g] == L;
+                if (mandatory) {
+                    take.push_back(g);
+                    mj += jobs[g];
+                } else if (pack && net.level[g] <= L && ready(g, L)) {
+                    if (jobs[g] == 0) take.push_back(g);  // bootstrap-free gates cost nothing: as soon as possible
+                    else cand.push_back(g);
+                }
+            }
+            if (pack && !cand.empty()) {
+                // candidate fill targets: the capacity points of the launch plan, per rank
+                static const size_t points[] = {74, 148, 222, 296, 592, 888, 1184, 2368, 3552, 4736};
+                std::vector<size_t> pre(cand.size() + 1, 0);
+                for (size_t k = 0; k < cand.size(); k++) pre[k + 1] = pre[k] + jobs[cand[k]];
+                double best = step_cost(mj, nullptr);
+                size_t best_k = 0;
+                for (size_t pt : points) {
+                    const size_t target = pt * (size_t)world;
+                    if (target <= mj) continue;
+                    // largest prefix of the candidates that fits the target
+                    size_t k = std::upper_bound(pre.begin(), pre.end(), target - mj) - pre.begin() - 1;
+                    if (k == 0) continue;
+                    const double score = step_cost(mj + pre[k], nullptr) - ms_per_job * (double)pre[k];
+                    if (score < best - 1e-9) best = score, best_k = k;
+                    if (k == cand.size()) break;
+                }
+                take.insert(take.end(), cand.begin(), cand.begin() + best_k);
+                mj += pre[best_k];
+            }
+            for (uint32_t g : take) when[g] = L;
+            pending.erase(std::remove_if(pending.begin(), pending.end(), [&](uint32_t g) { return when[g] == L; }),
+                          pending.end());
+            // keep slot order deterministic: by node id inside a step
+            std::sort(take.begin(), take.end());
+            b200net::Step& st = steps[L - 1];
+            bool shard = false;
+            total_ms += step_cost(mj, &shard);
+            if (shard) {
+                st.shd = std::move(take);
+                st.jobs_shd = mj;
+            } else {
+                st.rep = std::move(take);
+                st.jobs_rep = mj;
+            }
+        }
+        return total_ms;
+    }
+};
+
+void assign_slots(b200net* net, int world)
+{
+    net->slot.assign(net->n, 0xFFFFFFFFu);
+    uint32_t next = 0;
+    for (uint32_t i : net->inputs) net->slot[i] = next++;
+    for (uint32_t i : net->dffs) net->slot[i] = next++;
+    for (auto& st : net->steps) {
+        st.base_rep = next;
+        for (uint32_t g : st.rep) net->slot[g] = next++;
+        st.cut.assign(world + 1, 0);
+        st.chunk = 0;
+        st.base_shd = next;
+        if (!st.shd.empty()) {
+            // contiguous shares balanced by rotation count (a MUX is two rotations)
+            size_t total = 0, run = 0;
+            for (uint32_t g : st.shd) total += std::max(1, bootstraps(net->kind[g]));
+            int r = 1;
+            for (size_t k = 0; k < st.shd.size() && r < world; k++) {
+                run += std::max(1, bootstraps(net->kind[st.shd[k]]));
+                while (r < world && run * world >= total * r) st.cut[r++] = k + 1;
+            }
+            for (; r <= world; r++) st.cut[r] = st.shd.size();
+            st.cut[world] = st.shd.size();
+            for (int q = 0; q < world; q++) st.chunk = std::max(st.chunk, st.cut[q + 1] - st.cut[q]);
+            for (int q = 0; q < world; q++)
+                for (size_t k = st.cut[q]; k < st.cut[q + 1]; k++)
+                    net->slot[st.shd[k]] = st.base_shd + (uint32_t)(q * st.chunk + (k - st.cut[q]));
+            next += (uint32_t)(st.chunk * world);
+        }
+    }
+    net->n_slots = next;
+    net->tick_src.clear();
+    net->tick_dst.clear();
+    for (uint32_t d : net->dffs) {
+        net->tick_src.push_back(net->slot[net->resolve(net->in[0][d])]);
+        net->tick_dst.push_back(net->slot[d]);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200net_schedule(b200net* net, int world, unsigned flags)
+{
+    if (!net) return fail("null argument");
+    if (world < 1) return fail("world_size must be >= 1");
+    Scheduler sc(*net, world, 0.05);
+    sc.compute_alap();
+    std::vector<b200net::Step> asap, packed;
+    const double ms_asap = sc.build(false, asap);
+    net->packed = false;
+    net->model_ms = ms_asap;
+    net->steps = std::move(asap);
+    if (flags & B200NET_PACK) {
+        const double ms_packed = sc.build(true, packed);
+        if (ms_packed < ms_asap) {
+            net->steps = std::move(packed);
+            net->packed = true;
+            net->model_ms = ms_packed;
+        }
+    }
+    // drop empty trailing / inner steps (packing can empty a level)
+    net->steps.erase(std::remove_if(net->steps.begin(), net->steps.end(),
+                                    [](const b200net::Step& s) { return s.rep.empty() && s.shd.empty(); }),
+                     net->steps.end());
+    net->world = world;
+    assign_slots(net, world);
+    net->batches.clear();  // the per-level arrays of b200net_layout do not describe this slot assignment
+    net->level_base.clear();
+    return 0;
+}
+
+int b200net_bind_rank(b200net* net, b200fhe_ctx* ctx, int rank, int world, unsigned flags)
+{
+    if (!net || !ctx) return fail("null argument");
+    if (rank < 0 || rank >= world) return fail("rank out of range");
+    if (world != b200fhe_comm_world(ctx) && world != 1) return fail("world size differs from the context's communicator");
+    if (b200net_schedule(net, world, flags)) return 1;
+    net->ctx = ctx;
+    net->rank = rank;
+    if (b200fhe_arena_alloc(ctx, std::max<size_t>(net->n_slots, 1))) return fail(b200fhe_last_error());
+    b200fhe_program_destroy(net->run_prog);
+    b200fhe_program_destroy(net->tick_prog);
+    net->run_prog = net->tick_prog = nullptr;
+    if (b200fhe_program_create(ctx, &net->run_prog) || b200fhe_program_create(ctx, &net->tick_prog))
+        return fail(b200fhe_last_error());
+    std::vector<uint8_t> op;
+    std::vector<uint32_t> a, b, c, o;
+    for (const auto& st : net->steps) {
+        op.clear(), a.clear(), b.clear(), c.clear(), o.clear();
+        auto add = [&](uint32_t g) {
+            op.push_back(net->kind[g]);
+            auto s = [&](int k) { return net->in[k][g] >= 0 ? net->slot[net->resolve(net->in[k][g])] : 0u; };
+            a.push_back(s(0));
+            b.push_back(s(1));
+            c.push_back(s(2));
+            o.push_back(net->slot[g]);
+        };
+        for (uint32_t g : st.rep) add(g);
+        if (!st.shd.empty())
+            for (size_t k = st.cut[rank]; k < st.cut[rank + 1]; k++) add(st.shd[k]);
+        if (!op.empty() &&
+            b200fhe_program_batch(net->run_prog, op.data(), a.data(), b.data(), c.data(), o.data(), op.size()))
+            return fail(b200fhe_last_error());
+        if (!st.shd.empty() && world > 1 && b200fhe_program_exchange(net->run_prog, st.base_shd, st.chunk))
+            return fail(b200fhe_last_error());
+    }
+    if (!net->tick_src.empty() &&
+        b200fhe_program_tick(net->tick_prog, net->tick_src.data(), net->tick_dst.data(), net->tick_src.size()))
+        return fail(b200fhe_last_error());
+    if (b200fhe_program_finalize(net->run_prog) || b200fhe_program_finalize(net->tick_prog))
+        return fail(b200fhe_last_error());
+    net->compiled = true;
+    return 0;
+}
+
+size_t b200net_num_steps(const b200net* net) { return net ? net->steps.size() : 0; }
+size_t b200net_step_gates(const b200net* net, size_t step, int rank, uint32_t* nodes, size_t cap)
+{
+    if (!net || step >= net->steps.size() || rank < 0 || rank >= net->world) return 0;
+    const auto& st = net->steps[step];
+    size_t n = 0;
+    auto put = [&](uint32_t g) {
+        if (nodes && n < cap) nodes[n] = g;
+        n++;
+    };
+    for (uint32_t g : st.rep) put(g);
+    if (!st.shd.empty())
+        for (size_t k = st.cut[rank]; k < st.cut[rank + 1]; k++) put(st.shd[k]);
+    return n;
+}
+int b200net_step_exchange(const b200net* net, size_t step, uint32_t* first_slot, size_t* slots_per_rank)
+{
+    if (!net || step >= net->steps.size()) return fail("step out of range");
+    const auto& st = net->steps[step];
+    if (first_slot) *first_slot = st.base_shd;
+    if (slots_per_rank) *slots_per_rank = (st.shd.empty() || net->world == 1) ? 0 : st.chunk;
+    return 0;
+}
+size_t b200net_step_jobs(const b200net* net, size_t step, int* sharded)
+{
+    if (!net || step >= net->steps.size()) return 0;
+    const auto& st = net->steps[step];
+    if (sharded) *sharded = st.shd.empty() ? 0 : 1;
+    return st.jobs_rep + st.jobs_shd;
+}
+int b200net_schedule_info(const b200net* net, size_t* steps, size_t* collectives, size_t* exchanged_slots,
+                          double* model_ms, int* packed)
+{
+    if (!net) return fail("null argument");
+    size_t nc = 0, ns = 0;
+    for (const auto& st : net->steps)
+        if (!st.shd.empty() && net->world > 1) nc++, ns += st.chunk * net->world;
+    if (steps) *steps = net->steps.size();
+    if (collectives) *collectives = nc;
+    if (exchanged_slots) *exchanged_slots = ns;
+    if (model_ms) *model_ms = net->model_ms;
+    if (packed) *packed = net->packed ? 1 : 0;
     return 0;
 }
 

@@ -16,9 +16,16 @@
 //
 // Usage (option names of src/main.cpp:100-175):
 //   iyokan-b200 tfhe --blueprint B.toml --evalkey EK -i req.enc -o res.enc -c N [--skip-reset] [--quiet]
+// Multi-GPU (what `--num-gpu N` asks of the reference, src/iyokan_cufhe.cpp:533): one process per GPU, launched N
+// times with RANK / LOCAL_RANK / WORLD_SIZE in the environment (e.g. by torchrun or scripts/launch_ranks.sh); rank 0
+// publishes the communicator id through the file named by B200FHE_ID_FILE (default /tmp/b200fhe_id_<MASTER_PORT>).
+// Every rank evaluates its share of the static schedule (b200net_bind_rank); rank 0 writes the result packet.
 // Snapshot/resume and the plaintext mode live in the Python front end (python -m iyokan_b200).
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <thread>
 #include <cstring>
 #include <map>
 #include <string>
@@ -145,7 +152,7 @@ int main(int argc, char** argv)
 {
     std::string blueprintPath, evalkeyPath, inPath, outPath;
     int numCycles = -1;
-    bool skipReset = false, quiet = false;
+    bool skipReset = false, quiet = false, statsJson = false;
     if (argc < 2 || std::string(argv[1]) != "tfhe") error::die("usage: iyokan-b200 tfhe --blueprint B --evalkey EK -i IN -o OUT -c N");
     for (int i = 2; i < argc; i++) {
         const std::string a = argv[i];
@@ -160,6 +167,7 @@ int main(int argc, char** argv)
         else if (a == "-c") numCycles = std::stoi(next());
         else if (a == "--skip-reset") skipReset = true;
         else if (a == "--quiet") quiet = true;
+        else if (a == "--stats-json") statsJson = true;  // one JSON line on stdout: clock time, schedule, launches (bench.py)
         else if (a == "--verbose" || a == "--enable-gpu" || a == "--show-combinational-progress") {}
         else if (a == "--cpu" || a == "--gpu" || a == "--num-gpu" || a == "--gpu_num" || a == "--sched") next();  // CPU scheduler knobs
         else error::die("unknown option ", a);
@@ -208,14 +216,46 @@ int main(int argc, char** argv)
     if (numCycles < 0) numCycles = req.numCycles.value_or(-1);
     if (numCycles < 0) error::die("the number of cycles is given neither by -c nor by the request packet");
 
+    auto envInt = [](const char* name, int dflt) {
+        const char* v = std::getenv(name);
+        return v ? std::atoi(v) : dflt;
+    };
+    const int rank = envInt("RANK", 0), world = envInt("WORLD_SIZE", 1), localRank = envInt("LOCAL_RANK", rank);
     b200fhe_ctx* ctx = nullptr;
-    if (b200fhe_create(&ctx, 0)) error::die("b200fhe_create: ", b200fhe_last_error());
+    if (b200fhe_create(&ctx, localRank)) error::die("b200fhe_create: ", b200fhe_last_error());
     if (b200fhe_load_keys(ctx, reinterpret_cast<const uint32_t*>(ek.bklvl01.get()),
                           reinterpret_cast<const uint16_t*>(ek.iksklvl10.get())))
         error::die("b200fhe_load_keys: ", b200fhe_last_error());
+    if (world > 1) {  // communicator id: rank 0 writes it to a file, the others wait for it
+        const char* idFile = std::getenv("B200FHE_ID_FILE");
+        const std::string path = idFile ? idFile : "/tmp/b200fhe_id_" + std::string(std::getenv("MASTER_PORT") ? std::getenv("MASTER_PORT") : "0");
+        uint8_t id[128];
+        if (rank == 0) {
+            if (b200fhe_comm_unique_id(id)) error::die("b200fhe_comm_unique_id: ", b200fhe_last_error());
+            std::ofstream(path + ".tmp", std::ios::binary).write(reinterpret_cast<const char*>(id), 128);
+            std::rename((path + ".tmp").c_str(), path.c_str());
+        } else {
+            for (int tries = 0;; tries++) {
+                std::ifstream f(path, std::ios::binary);
+                if (f && f.read(reinterpret_cast<char*>(id), 128)) break;
+                if (tries > 6000) error::die("timed out waiting for the communicator id in ", path);
+                std::this_thread::sleep_for(std::chrono::milliseconds(10));
+            }
+        }
+        if (b200fhe_comm_init(ctx, rank, world, id)) error::die("b200fhe_comm_init: ", b200fhe_last_error());
+        if (rank == 0) std::remove(path.c_str());  // every rank has joined once comm_init returns
+    }
     b200net* net = nullptr;
     ck(b200net_create(&net, d.kind.size(), d.kind.data(), d.in0.data(), d.in1.data(), d.in2.data()), "b200net_create");
-    ck(b200net_bind(net, ctx, 1), "b200net_bind");
+    ck(b200net_bind_rank(net, ctx, rank, world, B200NET_PACK), "b200net_bind_rank");
+    {
+        size_t steps = 0, coll = 0, slots = 0;
+        double model = 0;
+        int packed = 0;
+        b200net_schedule_info(net, &steps, &coll, &slots, &model, &packed);
+        spdlog::info("rank {}/{}: {} steps ({}), {} all-gathers and {} KiB exchanged per clock, modelled {:.1f} ms per clock", rank,
+                     world, steps, packed ? "slack-packed" : "ASAP levels", coll, slots * 1280 / 1024, model);
+    }
     spdlog::info("{} nodes, {} levels, {} bootstraps per cycle, {} DFF", b200net_num_nodes(net), b200net_num_levels(net),
                  b200net_bootstraps_per_cycle(net), b200net_num_dff(net));
 
@@ -251,11 +291,14 @@ int main(int argc, char** argv)
     }
 
     // ---- cycle protocol (TFHEppFrontend::go) ----
-    const auto t0 = std::chrono::steady_clock::now();
     if (hasReset && !skipReset) {
         set(resetNode(), {trivial(true)});
         ck(b200net_run(net), "b200net_run");
     }
+    if (b200fhe_sync(ctx)) error::die("b200fhe_sync: ", b200fhe_last_error());
+    // the clock cycles are timed on their own (the reference prints one "done. (N us)" per cycle, iyokan_tfhepp.cpp:557)
+    const uint64_t launches0 = b200fhe_launch_count(ctx);
+    const auto t0 = std::chrono::steady_clock::now();
     for (int c = 0; c < numCycles; c++) {
         ck(b200net_tick(net), "b200net_tick");
         if (c == 0) {
@@ -284,8 +327,21 @@ int main(int argc, char** argv)
     }
     if (b200fhe_sync(ctx)) error::die("b200fhe_sync: ", b200fhe_last_error());
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    spdlog::info("done. ({} us, {:.0f} bootstraps/s)", (long long)(secs * 1e6),
+    spdlog::info("done. ({} us for {} cycle(s), {:.0f} bootstraps/s)", (long long)(secs * 1e6), numCycles,
                  secs > 0 ? b200net_bootstraps_per_cycle(net) * (double)numCycles / secs : 0.0);
+    if (statsJson) {
+        size_t steps = 0, coll = 0, slots = 0;
+        double model = 0;
+        int packed = 0;
+        b200net_schedule_info(net, &steps, &coll, &slots, &model, &packed);
+        std::printf("{\"rank\": %d, \"world\": %d, \"cycles\": %d, \"seconds\": %.6f, \"bootstraps_per_cycle\": %zu, \"nodes\": %zu, "
+                    "\"levels\": %zu, \"steps\": %zu, \"packed\": %s, \"collectives_per_cycle\": %zu, \"exchanged_bytes_per_cycle\": %zu, "
+                    "\"model_s_per_cycle\": %.6f, \"gpu_launches_per_cycle\": %.1f}\n",
+                    rank, world, numCycles, secs, b200net_bootstraps_per_cycle(net), b200net_num_nodes(net), b200net_num_levels(net), steps,
+                    packed ? "true" : "false", coll, slots * 1280, model / 1e3,
+                    numCycles > 0 ? (double)(b200fhe_launch_count(ctx) - launches0) / numCycles : 0.0);
+        std::fflush(stdout);
+    }
 
     // ---- result packet (makeResPacket, iyokan_tfhepp.cpp:176-227) ----
     auto get = [&](const std::vector<uint32_t>& nodes) {
@@ -295,14 +351,20 @@ int main(int argc, char** argv)
     };
     TFHEPacket res{{}, {}, {}, {}, {}, numCycles};
     for (const auto& [name, width] : bp.atPortWidths()) {
+        // one entry per port bit, written at its own index (makeResPacket resizes to atPortBit + 1,
+        // iyokan_tfhepp.cpp:182-190); bits tied to ground or left unconnected stay trivial 0
         std::vector<uint32_t> nodes;
-        bool isOutput = false;
+        std::vector<int> bits;
         for (int b = 0; b < width; b++)
             if (const auto port = bp.at(name, b); port && port->portLabel.kind == "output") {
-                isOutput = true;
                 nodes.push_back((uint32_t)d.node(*port));
+                bits.push_back(b);
             }
-        if (isOutput) res.bits.emplace(name, get(nodes));
+        if (bits.empty()) continue;
+        std::vector<TLWELvl0> vals(bits.back() + 1, trivial(false));
+        const auto got = get(nodes);
+        for (size_t k = 0; k < bits.size(); k++) vals[bits[k]] = got[k];
+        res.bits.emplace(name, std::move(vals));
     }
     for (const auto& ram : bp.builtinRAMs()) {
         const size_t n = (size_t(1) << ram.inAddrWidth) * ram.outRdataWidth;
@@ -313,7 +375,7 @@ int main(int argc, char** argv)
             for (auto& v : nodes) v = (uint32_t)d.in0[v];
         res.ramInTLWE.emplace(ram.name, get(nodes));
     }
-    writeToArchive(outPath, res);
+    if (rank == 0) writeToArchive(outPath, res);
     b200net_destroy(net);
     b200fhe_destroy(ctx);
     return 0;

@@ -73,6 +73,19 @@ def load() -> ctypes.CDLL:
         "b200fhe_plan_rotation": (ci, [ci, vp, vp, vp, ci]),
         "b200fhe_plan_ms": (ctypes.c_double, [ci]),
         "b200fhe_stream": (vp, [vp]),
+        "b200fhe_program_create": (ci, [vp, ctypes.POINTER(vp)]),
+        "b200fhe_program_destroy": (None, [vp]),
+        "b200fhe_program_batch": (ci, [vp, vp, vp, vp, vp, vp, sz]),
+        "b200fhe_program_tick": (ci, [vp, vp, vp, sz]),
+        "b200fhe_program_exchange": (ci, [vp, sz, sz]),
+        "b200fhe_program_finalize": (ci, [vp]),
+        "b200fhe_program_launch": (ci, [vp]),
+        "b200fhe_program_info": (ci, [vp, vp, vp, vp, vp, vp, vp]),
+        "b200fhe_comm_unique_id": (ci, [vp]),
+        "b200fhe_comm_init": (ci, [vp, ci, ci, vp]),
+        "b200fhe_comm_rank": (ci, [vp]),
+        "b200fhe_comm_world": (ci, [vp]),
+        "b200fhe_exchange": (ci, [vp, sz, sz]),
         "b200fhe_test_bootstrap_lvl1": (ci, [vp, vp, vp, sz]),
         "b200fhe_test_keyswitch": (ci, [vp, vp, vp, sz]),
         "b200fhe_test_read_bk_ntt": (ci, [vp, vp, sz, sz]),
@@ -92,6 +105,9 @@ EXPORTS = [
     "b200fhe_query", "b200fhe_gates_host", "b200fhe_host_alloc", "b200fhe_host_free", "b200fhe_launch_count",
     "b200fhe_last_batch_ms", "b200fhe_last_batch_segments", "b200fhe_plan_rotation", "b200fhe_plan_ms", "b200fhe_stream", "b200fhe_test_bootstrap_lvl1", "b200fhe_test_keyswitch",
     "b200fhe_test_read_bk_ntt",
+    "b200fhe_program_create", "b200fhe_program_destroy", "b200fhe_program_batch", "b200fhe_program_tick",
+    "b200fhe_program_exchange", "b200fhe_program_finalize", "b200fhe_program_launch", "b200fhe_program_info",
+    "b200fhe_comm_unique_id", "b200fhe_comm_init", "b200fhe_comm_rank", "b200fhe_comm_world", "b200fhe_exchange",
 ]
 
 
@@ -140,6 +156,57 @@ def plan_rotation(njobs: int):
 def plan_ms(njobs: int) -> float:
     """Modelled blind-rotation time (ms) of a frontier of `njobs` rotations under the launch plan."""
     return float(load().b200fhe_plan_ms(int(njobs)))
+
+
+def comm_unique_id() -> bytes:
+    """128-byte communicator id (ncclUniqueId); rank 0 creates it and hands it to the other ranks."""
+    lib = load()
+    buf = (ctypes.c_uint8 * 128)()
+    if lib.b200fhe_comm_unique_id(buf):
+        raise B200FheError(lib.b200fhe_last_error().decode())
+    return bytes(buf)
+
+
+class Program:
+    """A static schedule (frontiers, exchanges, tick) recorded once and replayed as one CUDA graph."""
+
+    def __init__(self, ctx: "Context"):
+        self._lib, self.ctx = ctx._lib, ctx
+        h = ctypes.c_void_p()
+        ctx._ck(self._lib.b200fhe_program_create(ctx._h, ctypes.byref(h)))
+        self._h = h
+
+    def batch(self, opcode, in0, in1, in2, out):
+        op = np.ascontiguousarray(opcode, dtype=np.uint8)
+        n = op.size
+        a, b, c, o = _u32(in0, n), _u32(in1, n), _u32(in2, n), _u32(out, n)
+        self.ctx._ck(self._lib.b200fhe_program_batch(self._h, _ptr(op), _ptr(a), _ptr(b), _ptr(c), _ptr(o), n))
+
+    def tick(self, src, dst):
+        s, d = _u32(src), _u32(dst)
+        self.ctx._ck(self._lib.b200fhe_program_tick(self._h, _ptr(s), _ptr(d), s.size))
+
+    def exchange(self, first_slot, slots_per_rank):
+        self.ctx._ck(self._lib.b200fhe_program_exchange(self._h, first_slot, slots_per_rank))
+
+    def finalize(self):
+        self.ctx._ck(self._lib.b200fhe_program_finalize(self._h))
+
+    def launch(self):
+        self.ctx._ck(self._lib.b200fhe_program_launch(self._h))
+
+    def info(self) -> dict:
+        r, l, e, s = (ctypes.c_uint64() for _ in range(4))
+        g, m = ctypes.c_int(), ctypes.c_double()
+        self.ctx._ck(self._lib.b200fhe_program_info(self._h, ctypes.byref(r), ctypes.byref(l), ctypes.byref(e), ctypes.byref(s),
+                                                    ctypes.byref(g), ctypes.byref(m)))
+        return {"rotations": r.value, "launches_per_replay": l.value, "exchanges": e.value, "exchanged_slots": s.value,
+                "is_graph": bool(g.value), "model_ms": m.value}
+
+    def close(self):
+        if self._h is not None:
+            self._lib.b200fhe_program_destroy(self._h)
+            self._h = None
 
 
 class Context:
@@ -229,6 +296,18 @@ class Context:
 
     def sync(self):
         self._ck(self._lib.b200fhe_sync(self._h))
+
+    # ---- multi-GPU exchange (NCCL bound inside the library) ----
+    def comm_init(self, rank: int, world: int, unique_id: bytes | None):
+        """Join the communicator of `world` ranks; `unique_id` = the 128 bytes rank 0 got from comm_unique_id()."""
+        buf = None if unique_id is None else (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ck(self._lib.b200fhe_comm_init(self._h, rank, world, buf))
+
+    def exchange(self, first_slot: int, slots_per_rank: int):
+        self._ck(self._lib.b200fhe_exchange(self._h, first_slot, slots_per_rank))
+
+    def program(self) -> "Program":
+        return Program(self)
 
     def query(self) -> int:
         return int(self._lib.b200fhe_query(self._h))

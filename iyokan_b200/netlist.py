@@ -210,6 +210,10 @@ def load_net():
             "b200net_layout": (ci, [vp, ci]), "b200net_bind": (ci, [vp, vp, ci]), "b200net_set": (ci, [vp, vp, vp, sz]), "b200net_restore": (ci, [vp, vp, vp, sz]),
             "b200net_get": (ci, [vp, vp, vp, sz]), "b200net_tick": (ci, [vp]), "b200net_run": (ci, [vp]),
             "b200net_run_level_shard": (ci, [vp, sz, ci, ci]),
+            "b200net_bind_rank": (ci, [vp, vp, ci, ci, ctypes.c_uint]), "b200net_schedule": (ci, [vp, ci, ctypes.c_uint]),
+            "b200net_num_steps": (sz, [vp]), "b200net_step_jobs": (sz, [vp, sz, vp]),
+            "b200net_schedule_info": (ci, [vp, vp, vp, vp, vp, vp]),
+            "b200net_step_gates": (sz, [vp, sz, ci, vp, sz]), "b200net_step_exchange": (ci, [vp, sz, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)
@@ -223,6 +227,8 @@ NET_EXPORTS = [
     "b200net_level_width", "b200net_level_bootstraps", "b200net_bootstraps_per_cycle", "b200net_num_dff", "b200net_node_level",
     "b200net_slot_of", "b200net_num_slots", "b200net_level_slot_base", "b200net_plain_eval", "b200net_plain_tick",
     "b200net_layout", "b200net_bind", "b200net_set", "b200net_restore", "b200net_get", "b200net_tick", "b200net_run", "b200net_run_level_shard",
+    "b200net_bind_rank", "b200net_schedule", "b200net_num_steps", "b200net_step_jobs", "b200net_schedule_info",
+    "b200net_step_gates", "b200net_step_exchange",
 ]
 
 
@@ -300,6 +306,49 @@ class NetEngine:
     def bind(self, ctx: Context, world_size: int = 1):
         self.ctx, self.world = ctx, world_size
         self._ck(self.lib.b200net_bind(self._h, ctx._h, world_size))
+
+    PACK = 1
+
+    def bind_rank(self, ctx: Context, rank: int = 0, world_size: int = 1, flags: int = 1):
+        """Schedule for `world_size` ranks and compile this rank's share into CUDA graphs (clock, tick)."""
+        self.ctx, self.world = ctx, world_size
+        self._ck(self.lib.b200net_bind_rank(self._h, ctx._h, rank, world_size, flags))
+
+    def schedule(self, world_size: int = 1, flags: int = 1):
+        """The static schedule alone (no GPU): steps, sharding decisions, slots."""
+        self.world = world_size
+        self._ck(self.lib.b200net_schedule(self._h, world_size, flags))
+
+    @property
+    def step_jobs(self):
+        out = []
+        for k in range(int(self.lib.b200net_num_steps(self._h))):
+            sh = ctypes.c_int()
+            out.append((int(self.lib.b200net_step_jobs(self._h, k, ctypes.byref(sh))), bool(sh.value)))
+        return out
+
+    @property
+    def num_steps(self):
+        return int(self.lib.b200net_num_steps(self._h))
+
+    def step_gates(self, step: int, rank: int) -> np.ndarray:
+        n = int(self.lib.b200net_step_gates(self._h, step, rank, None, 0))
+        out = np.zeros(max(n, 1), np.uint32)
+        self.lib.b200net_step_gates(self._h, step, rank, _p(out), n)
+        return out[:n]
+
+    def step_exchange(self, step: int):
+        first, per = ctypes.c_uint32(), ctypes.c_size_t()
+        self._ck(self.lib.b200net_step_exchange(self._h, step, ctypes.byref(first), ctypes.byref(per)))
+        return int(first.value), int(per.value)
+
+    def schedule_info(self) -> dict:
+        st, co, ex = (ctypes.c_size_t() for _ in range(3))
+        ms, pk = ctypes.c_double(), ctypes.c_int()
+        self._ck(self.lib.b200net_schedule_info(self._h, ctypes.byref(st), ctypes.byref(co), ctypes.byref(ex), ctypes.byref(ms),
+                                                ctypes.byref(pk)))
+        return {"steps": st.value, "collectives": co.value, "exchanged_slots": ex.value, "model_ms": ms.value,
+                "packed": bool(pk.value)}
 
     def set(self, nodes, tlwe):
         nodes = np.ascontiguousarray(nodes, np.uint32)
@@ -405,7 +454,7 @@ class EncryptedRunner:
     def __init__(self, nl: Netlist, ctx: Context, encrypt=None, eng: NetEngine | None = None):
         self.nl, self.ctx, self.encrypt = nl, ctx, encrypt
         self.eng = eng or NetEngine(nl)
-        self.eng.bind(ctx, 1)
+        self.eng.bind_rank(ctx, 0, 1)
         dffs = np.nonzero(nl.kind == DFF)[0]
         if dffs.size:  # DFF initial value: trivial 0 (iyokan_tfhepp.hpp:23-27)
             self.eng.set(dffs, np.tile(trivial(0), (dffs.size, 1)))

@@ -23,6 +23,7 @@ IYOKAN_PACKET = HERE / "_ref" / "iyokan-packet"   # the reference's own packet t
 REF_LINK_TEST = HERE / "_ref" / "b200_gate_test"  # tests/ref_link/b200_gate_test.cpp: TFHEpp types over the C ABI
 IYOKAN_REF = HERE / "_ref" / "iyokan"             # the reference's own iyokan (plain + tfhe on CPU), built unmodified
 IYOKAN_B200 = HERE / "_ref" / "iyokan-b200"       # iyokan_b200/host/iyokan_b200_main.cpp: the reference's loader + our engine
+B200_TEST0 = HERE / "_ref" / "b200_test0"         # the reference's src/test0.cpp templated tests on the B200 plugin (iyokan_b200.hpp)
 
 N0, N1, L, T = 636, 1024, 3, 7
 TLWE0, TLWE1, ROWS = N0 + 1, N1 + 1, 6
@@ -76,10 +77,11 @@ def build(force: bool = False) -> None:
         so = HERE.parent / "iyokan_b200" / "csrc" / "libb200fhe.so"
         src = HERE.parent / "tests" / "ref_link" / "b200_gate_test.cpp"
         host = HERE.parent / "iyokan_b200" / "host"
-        deps = [so, src, host / "libb200net.so", host / "iyokan_b200_main.cpp"]
-        if all(d.exists() for d in deps) and (force or not REF_LINK_TEST.exists() or not IYOKAN_B200.exists()
-                                              or min(REF_LINK_TEST.stat().st_mtime, IYOKAN_B200.stat().st_mtime)
-                                              < max(d.stat().st_mtime for d in deps)):
+        deps = [so, src, host / "libb200net.so", host / "iyokan_b200_main.cpp", host / "iyokan_b200.hpp",
+                HERE.parent / "tests" / "ref_link" / "b200_test0.cpp"]
+        outs = [REF_LINK_TEST, IYOKAN_B200, B200_TEST0]
+        if all(d.exists() for d in deps) and (force or not all(o.exists() for o in outs)
+                                              or min(o.stat().st_mtime for o in outs) < max(d.stat().st_mtime for d in deps)):
             _optional(["make", "-C", str(HERE), "-j4", "reflink"])
 
 

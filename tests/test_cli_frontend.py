@@ -126,6 +126,14 @@ def test_error_behaviour(tmp_path):
                    "-c", 1) == 1
     with pytest.raises(FrontendError):
         Frontend(B.read_blueprint(bp), "tfhe", None)   # encrypted mode never falls back to the CPU
+    # a RAM / ROM image of the wrong length is refused, as the reference does ("wrong length of RAM",
+    # iyokan_tfhepp.cpp:242-259): lookup.toml holds a 16-bit ROM and a 16-bit RAM
+    (tmp_path / "short.in").write_text('cycles = 1\n[[ram]]\nname = "ram"\nsize = 8\nbytes = [255]\n')
+    assert run_cli("plain", "--blueprint", FIX / "lookup.toml", "-i", tmp_path / "short.in", "-o", tmp_path / "r") == 1
+    (tmp_path / "long.in").write_text('cycles = 1\n[[rom]]\nname = "rom"\nsize = 24\nbytes = [1, 2, 3]\n')
+    assert run_cli("plain", "--blueprint", FIX / "lookup.toml", "-i", tmp_path / "long.in", "-o", tmp_path / "r") == 1
+    (tmp_path / "fit.in").write_text('cycles = 1\n[[rom]]\nname = "rom"\nsize = 16\nbytes = [1, 2]\n')
+    assert run_cli("plain", "--blueprint", FIX / "lookup.toml", "-i", tmp_path / "fit.in", "-o", tmp_path / "r") == 0
 
 
 def test_module_entry_point(tmp_path):

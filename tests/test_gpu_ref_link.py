@@ -79,3 +79,26 @@ def test_iyokan_b200_binary_with_the_reference_loader(tmp_path, blueprint, cycle
     for name in want.ram:
         assert np.array_equal(got.ram[name], want.ram[name]), name
     ek.unlink()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not O.B200_TEST0.exists(), reason="oracle/_ref/b200_test0 not built")
+def test_reference_test0_suite_on_the_b200_plugin(tmp_path):
+    """The reference's own templated unit tests (src/test0.cpp:43-455) instantiated with B200NetworkBuilder: the plugin
+    iyokan_b200/host/iyokan_b200.hpp compiled against the unmodified src/iyokan.hpp (Task / DepNode / ReadyQueue / Worker /
+    NetworkBuilder / IyokanL1JSONReader are the reference's), gates evaluated through the C ABI, one batch per frontier."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
+    import make_ref_assets
+
+    make_ref_assets.materialise(tmp_path / "test")   # the tests open test/iyokanl1-json/*.json relative to the cwd
+    r = subprocess.run([str(O.B200_TEST0)], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for t in ("testNOT", "testMUX", "testBinopGates", "testFromJSONtest_pass_4bit", "testFromJSONtest_and_4bit",
+              "testFromJSONtest_and_4_2bit", "testFromJSONtest_mux_4bit", "testFromJSONtest_addr_4bit",
+              "testFromJSONtest_register_4bit", "testSequentialCircuit", "testFromJSONtest_counter_4bit",
+              "testPrioritySetVisitor"):
+        assert f"ok  {t}<B200NetworkBuilder>" in r.stdout, t
+    assert "test0 suite green on the B200 back-end" in r.stdout

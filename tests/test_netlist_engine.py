@@ -111,3 +111,55 @@ def test_cost_model_reproduces_the_measured_clock_cycles():
             assert m["bootstraps_per_cycle"] == meas["bootstraps_per_cycle"]
             checked += 1
     assert checked >= 6
+
+
+@pytest.mark.parametrize("name", ["cahp-pearl-mux", "mux-ram-8-16-16", "counter-4bit"])
+@pytest.mark.parametrize("world", [1, 2, 8])
+@pytest.mark.parametrize("flags", [0, 1])
+def test_static_schedule_is_a_valid_partition(name, world, flags):
+    """b200net_schedule: every gate is evaluated exactly once (replicated gates once per rank, sharded gates by exactly
+    one rank), only after everything it reads, sharded outputs sit in the exchanged slot range of their step at the
+    owner's offset, and packing never makes the modelled clock slower than ASAP levels."""
+    nl = N.Netlist.load(NL / f"{name}.npz")
+    eng = N.NetEngine(nl)
+    eng.schedule(world, 0)
+    asap_ms = eng.schedule_info()["model_ms"]
+    eng.schedule(world, flags)
+    info = eng.schedule_info()
+    assert info["model_ms"] <= asap_ms + 1e-9
+    gates = np.nonzero(nl.kind < 15)[0]
+    when = np.full(nl.n, -1)          # step that produces a node's value (0 for sources)
+    when[(nl.kind == N.INPUT) | (nl.kind == N.DFF)] = 0
+    owners = np.zeros(nl.n, np.int64)
+    nsharded = 0
+    for k in range(eng.num_steps):
+        first, per = eng.step_exchange(k)
+        per_rank = [eng.step_gates(k, r) for r in range(world)]
+        common = set(per_rank[0].tolist())
+        for g in per_rank[1:]:
+            common &= set(g.tolist())
+        for r, g in enumerate(per_rank):
+            for node in g:
+                owners[node] += 1
+                assert when[node] in (-1, k + 1)
+                # inputs come from earlier steps
+                for arr in (nl.in0, nl.in1, nl.in2):
+                    src = arr[node]
+                    if src < 0:
+                        continue
+                    while nl.kind[src] == N.OUTPUT:
+                        src = nl.in0[src]
+                    assert 0 <= when[src] <= k, (name, k, node)
+                if node not in common or world == 1:
+                    if world > 1:
+                        assert per > 0 and first + r * per <= eng.slot_of(node) < first + (r + 1) * per
+                        nsharded += 1
+        for g in per_rank:
+            when[g] = k + 1
+    assert np.all(when[gates] > 0)
+    shared = owners[gates]
+    assert set(np.unique(shared)) <= {1, world}       # sharded: one owner; replicated: all ranks
+    assert info["collectives"] == sum(1 for k in range(eng.num_steps) if eng.step_exchange(k)[1] > 0)
+    if world > 1 and name != "counter-4bit":
+        assert nsharded > 0 and info["collectives"] > 0
+    eng.close()

@@ -1,5 +1,6 @@
-"""N > 1 path on CPU: level-sliced sharding + per-level all-gather with the gloo backend, world_size 2,
-plaintext back-end standing in for the GPU (same orchestration code, iyokan_b200/shard.py)."""
+"""N > 1 path on CPU: the engine's static schedule (b200net_schedule: replicated / sharded steps, slot ranges,
+one all-gather per sharded step) replayed with the gloo backend, world_size 2, plaintext back-end standing in for
+the GPU.  On the GPU the same schedule is compiled into one CUDA graph per rank (b200net_bind_rank)."""
 import json
 import os
 import socket
@@ -12,19 +13,19 @@ import torch.multiprocessing as mp
 NL = Path(__file__).resolve().parent / "golden" / "netlists"
 
 
-def _worker(rank, world, port, name, min_width, q):
+def _worker(rank, world, port, name, flags, q):
     import torch.distributed as dist
 
     from iyokan_b200 import netlist as N
-    from iyokan_b200.shard import PlainBackend, ShardedRunner
+    from iyokan_b200.shard import PlainBackend, ScheduledRunner
 
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     case = json.load(open(NL / "cases.json"))[name]
     nl = N.Netlist.load(NL / f"{name}.npz")
     eng = N.NetEngine(nl)
-    be = PlainBackend(nl, eng, world)
-    run = ShardedRunner(nl, eng, be, rank, world, min_shard_width=min_width)
+    be = PlainBackend(nl, eng, world, flags)
+    run = ScheduledRunner(nl, eng, be, rank, world)
     req = case["request"]
     for mem, e in req["rom"].items():
         be.set_nodes(nl.mem[mem], N.bits_of(e["bytes"], e["size"])[:len(nl.mem[mem])])
@@ -58,12 +59,13 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("name,min_width", [("mux-ram-8-16-16", 0), ("cahp-pearl-mux", 64), ("cahp-ruby-mux", None)])
-def test_two_rank_sharded_run_matches_reference_golden(name, min_width):
+@pytest.mark.parametrize("name,flags", [("mux-ram-8-16-16", 0), ("cahp-pearl-mux", 1), ("cahp-ruby-mux", 1)])
+def test_two_rank_sharded_run_matches_reference_golden(name, flags):
+    # flags: 0 = ASAP levels, 1 = slack-aware packing (B200NET_PACK)
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, name, min_width, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, flags, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in range(world)]

@@ -443,6 +443,9 @@ def main():
                                    "pipe_cycles_per_rotation": pipe_cycles_per_rotation, "peak": alu_peak,
                                    "achieved": dom["jobs"] / (dom["ms"] / 1e3), "unit": "rotations/s",
                                    "frac": dom["jobs"] / (dom["ms"] / 1e3) / alu_peak}
+        from iyokan_b200.lib import plan_table
+
+        line["roofline"]["plan_table"] = plan_table()   # ms per wave of each shape, measured at key load on this device
         if net_lines:
             line["netlist"] = net_lines[0]
             if len(net_lines) > 1:

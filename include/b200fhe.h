@@ -157,6 +157,11 @@ int b200fhe_plan_rotation(int njobs, int *variant, int *jobs_per_cta, int *jobs,
 /* modelled blind-rotation time (ms, B200 tables) of that plan: what a scheduler uses to decide whether
  * splitting a dependency level across GPUs pays for the exchange */
 double b200fhe_plan_ms(int njobs);
+/* the table behind the plan: per shape (kernel variant, jobs per CTA) the jobs one wave of 148 SMs takes and its
+ * duration.  Compile-time defaults were measured on a B200 at 1965 MHz; b200fhe_load_keys re-measures them on the
+ * device at hand, and b200fhe_comm_init makes all ranks agree (max) so that every rank derives the same schedule.
+ * Returns the number of shapes, negated while the table still holds the defaults. */
+int b200fhe_plan_table(int *variant, int *jobs_per_cta, int *wave_jobs, double *wave_ms, int max_shapes);
 void *b200fhe_stream(const b200fhe_ctx *ctx);
 
 /* test hooks: stage-level access used by the parity tests --------------------------------- */

@@ -526,6 +526,7 @@ struct NcclApi {
     int (*GetUniqueId)(NcclId*) = nullptr;
     int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -543,6 +544,7 @@ static int nccl_load()
     a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
     a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
     a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(h, "ncclAllGather"));
+    a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
     a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
     a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
     if (!a.GetUniqueId || !a.CommInitRank || !a.AllGather || !a.CommDestroy) return fail("libnccl lacks the expected symbols");
@@ -716,6 +718,53 @@ static int br_dispatch_one(b200fhe_ctx* c, int variant, int G, int njobs, const 
         }
     }
     return fail("kernel variant must be 3, 4, 6 or 7");
+}
+
+// Measures one wave of every shape on this device (dummy jobs on a zeroed slot: the kernels' time does not depend on
+// the data) and replaces the table's defaults, so that a differently clocked or power-capped part plans - and, through
+// b200fhe_plan_ms, schedules netlists - with its own numbers.  Called by b200fhe_load_keys; ~0.1 s.
+static int calibrate(b200fhe_ctx* c)
+{
+    const char* off = getenv("B200FHE_NO_CALIBRATE");
+    if (off && off[0] == '1') return 0;
+    int maxw = 0;
+    for (const BrShape& sh : g_plan.shape) maxw = std::max(maxw, sh.wave_jobs);
+    uint16_t* d_slot = nullptr;
+    uint32_t* d_u = nullptr;
+    BrJob* d_jobs = nullptr;
+    CK(cudaMalloc(&d_slot, SLOT_STRIDE * 2));
+    CK(cudaMalloc(&d_u, (size_t)maxw * U_STRIDE * 4));
+    CK(cudaMalloc(&d_jobs, (size_t)maxw * sizeof(BrJob)));
+    CK(cudaMemsetAsync(d_slot, 0, SLOT_STRIDE * 2, c->stream));
+    std::vector<BrJob> jobs(maxw, BrJob{{0u, 0u, 0u}, {1, 0, 0}, 0, 0u});
+    CK(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(BrJob), cudaMemcpyHostToDevice, c->stream));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const uint64_t l0 = c->launches;
+    for (int k = 0; k < N_SHAPES; k++) {
+        BrShape& sh = g_plan.shape[k];
+        float best = 1e30f;
+        for (int rep = 0; rep < 2; rep++) {  // first run warms the instruction cache and L2
+            CK(cudaEventRecord(e0, c->stream));
+            if (br_dispatch_one(c, sh.variant, sh.G, sh.wave_jobs, d_slot, d_u, d_jobs)) return 1;
+            CK(cudaEventRecord(e1, c->stream));
+            CK(cudaEventSynchronize(e1));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0) best = std::min(best, ms);
+        }
+        sh.wave_ms = best;
+    }
+    c->launches = l0;  // not the caller's work
+    g_plan.calibrated = true;
+    g_plan.dp_valid = false;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_slot);
+    cudaFree(d_u);
+    cudaFree(d_jobs);
+    return 0;
 }
 
 // rotation job k writes ubuf[k]: segments are contiguous ranges of the job list
@@ -915,7 +964,7 @@ int b200fhe_load_keys(b200fhe_ctx* c, const uint32_t* bk_raw, const uint16_t* ks
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaFree(d_raw));
     c->keys = true;
-    return 0;
+    return calibrate(c);
 }
 
 int b200fhe_arena_alloc(b200fhe_ctx* c, size_t n_slots)
@@ -1103,6 +1152,18 @@ int b200fhe_plan_rotation(int njobs, int* variant, int* jobs_per_cta, int* jobs,
     return n;
 }
 
+int b200fhe_plan_table(int* variant, int* jobs_per_cta, int* wave_jobs, double* wave_ms, int max_shapes)
+{
+    const int n = N_SHAPES < max_shapes ? N_SHAPES : max_shapes;
+    for (int k = 0; k < n; k++) {
+        if (variant) variant[k] = g_plan.shape[k].variant;
+        if (jobs_per_cta) jobs_per_cta[k] = g_plan.shape[k].G;
+        if (wave_jobs) wave_jobs[k] = g_plan.shape[k].wave_jobs;
+        if (wave_ms) wave_ms[k] = g_plan.shape[k].wave_ms;
+    }
+    return g_plan.calibrated ? n : -n;
+}
+
 double b200fhe_plan_ms(int njobs)
 {
     if (njobs <= 0) return 0.0;
@@ -1272,6 +1333,20 @@ int b200fhe_comm_init(b200fhe_ctx* c, int rank, int world, const uint8_t* id128)
     std::memcpy(id.internal, id128, 128);
     const int rc = g_nccl.CommInitRank(&c->comm, world, id, rank);
     if (rc) return nccl_fail("ncclCommInitRank", rc);
+    // every rank must derive the SAME schedule from b200fhe_plan_ms: agree on the launch-plan table (max over ranks)
+    if (g_nccl.AllReduce) {
+        double h[N_SHAPES], *d = nullptr;
+        for (int k = 0; k < N_SHAPES; k++) h[k] = g_plan.shape[k].wave_ms;
+        CK(cudaMalloc(&d, sizeof(h)));
+        CK(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+        const int rr = g_nccl.AllReduce(d, d, N_SHAPES, /*ncclFloat64*/ 8, /*ncclMax*/ 2, c->comm, c->stream);
+        if (rr) return nccl_fail("ncclAllReduce", rr);
+        CK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaFree(d));
+        for (int k = 0; k < N_SHAPES; k++) g_plan.shape[k].wave_ms = h[k];
+        g_plan.dp_valid = false;
+    }
     return 0;
 }
 

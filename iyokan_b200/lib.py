@@ -72,6 +72,7 @@ def load() -> ctypes.CDLL:
         "b200fhe_last_batch_segments": (ci, [vp, vp, vp, vp, vp, ci]),
         "b200fhe_plan_rotation": (ci, [ci, vp, vp, vp, ci]),
         "b200fhe_plan_ms": (ctypes.c_double, [ci]),
+        "b200fhe_plan_table": (ci, [vp, vp, vp, vp, ci]),
         "b200fhe_stream": (vp, [vp]),
         "b200fhe_program_create": (ci, [vp, ctypes.POINTER(vp)]),
         "b200fhe_program_destroy": (None, [vp]),
@@ -103,7 +104,7 @@ EXPORTS = [
     "b200fhe_arena_alloc", "b200fhe_arena_attach", "b200fhe_arena_slots", "b200fhe_arena_dev_ptr",
     "b200fhe_upload", "b200fhe_download", "b200fhe_gate_batch", "b200fhe_dff_tick", "b200fhe_sync",
     "b200fhe_query", "b200fhe_gates_host", "b200fhe_host_alloc", "b200fhe_host_free", "b200fhe_launch_count",
-    "b200fhe_last_batch_ms", "b200fhe_last_batch_segments", "b200fhe_plan_rotation", "b200fhe_plan_ms", "b200fhe_stream", "b200fhe_test_bootstrap_lvl1", "b200fhe_test_keyswitch",
+    "b200fhe_last_batch_ms", "b200fhe_last_batch_segments", "b200fhe_plan_rotation", "b200fhe_plan_ms", "b200fhe_plan_table", "b200fhe_stream", "b200fhe_test_bootstrap_lvl1", "b200fhe_test_keyswitch",
     "b200fhe_test_read_bk_ntt",
     "b200fhe_program_create", "b200fhe_program_destroy", "b200fhe_program_batch", "b200fhe_program_tick",
     "b200fhe_program_exchange", "b200fhe_program_finalize", "b200fhe_program_launch", "b200fhe_program_info",
@@ -151,6 +152,15 @@ def plan_rotation(njobs: int):
     v, g, n = (np.zeros(8, np.int32) for _ in range(3))
     k = lib.b200fhe_plan_rotation(int(njobs), _ptr(v), _ptr(g), _ptr(n), 8)
     return [(int(v[i]), int(g[i]), int(n[i])) for i in range(k)]
+
+
+def plan_table() -> dict:
+    """The launch-plan table: {"calibrated": bool, "shapes": [(variant, jobs_per_cta, wave_jobs, wave_ms)]}."""
+    lib = load()
+    v, g, w = (np.zeros(8, np.int32) for _ in range(3))
+    ms = np.zeros(8, np.float64)
+    k = lib.b200fhe_plan_table(_ptr(v), _ptr(g), _ptr(w), _ptr(ms), 8)
+    return {"calibrated": k > 0, "shapes": [(int(v[i]), int(g[i]), int(w[i]), float(ms[i])) for i in range(abs(k))]}
 
 
 def plan_ms(njobs: int) -> float:

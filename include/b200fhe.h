@@ -39,13 +39,26 @@
 extern "C" {
 #endif
 
+/* Parameter set: a compile-time flavour, as in the reference (-DIYOKAN_80BIT_SECURITY=On, CMakeLists.txt:28-30).
+ * Callers of libb200fhe80.so define B200FHE_80BIT before including this header. */
+#ifdef B200FHE_80BIT
+/* 80-bit parameter set (TFHEpp include/params/CGGI16.hpp): n = 500, 32-bit lvl0 torus, l = 2, Bg = 2^10, t = 8 */
+typedef uint32_t b200fhe_torus0; /* lvl0param::T */
+#define B200FHE_N0 500           /* lvl0 dimension; a TLWE lvl0 is 501 uint32 = 2004 bytes */
+#define B200FHE_TLWE0_LEN 501
+#define B200FHE_BK_WORDS (500ull * 4 * 2 * 1024)       /* uint32 [n][(k+1)l][k+1][N]  raw TRGSW */
+#define B200FHE_KSK_ELEMS (1024ull * 8 * 3 * 501)      /* uint32 [N][t][3][n+1] */
+#else
 /* 128-bit parameter set (TFHEpp include/params/128bit.hpp) */
+typedef uint16_t b200fhe_torus0;
 #define B200FHE_N0 636           /* lvl0 dimension; a TLWE lvl0 is 637 uint16 = 1274 bytes */
-#define B200FHE_N1 1024          /* lvl1 ring degree */
 #define B200FHE_TLWE0_LEN 637
-#define B200FHE_TLWE1_LEN 1025
 #define B200FHE_BK_WORDS (636ull * 6 * 2 * 1024)       /* uint32 [n][(k+1)l][k+1][N]  raw TRGSW */
-#define B200FHE_KSK_HALFS (1024ull * 7 * 3 * 637)      /* uint16 [N][t][3][n+1] */
+#define B200FHE_KSK_ELEMS (1024ull * 7 * 3 * 637)      /* uint16 [N][t][3][n+1] */
+#define B200FHE_KSK_HALFS B200FHE_KSK_ELEMS
+#endif
+#define B200FHE_N1 1024          /* lvl1 ring degree */
+#define B200FHE_TLWE1_LEN 1025
 
 /* Gate opcodes.  ANDNOT = HomANDYN, ORNOT = HomORYN (src/iyokan_tfhepp.hpp:133,136).
  * MUX computes in2 ? in1 : in0 (HomMUX(out, in(2), in(1), in(0)), iyokan_tfhepp.hpp:140). */
@@ -76,17 +89,17 @@ int b200fhe_set_kernel_variant(b200fhe_ctx *ctx, int variant);
 
 /* keys: raw bootstrapping key + key-switching key in the reference's memory layout.
  * Copies to the device, converts the bootstrapping key to NTT form there. */
-int b200fhe_load_keys(b200fhe_ctx *ctx, const uint32_t *bk_raw, const uint16_t *ksk);
+int b200fhe_load_keys(b200fhe_ctx *ctx, const uint32_t *bk_raw, const b200fhe_torus0 *ksk);
 
 /* ciphertext arena ------------------------------------------------------------------------ */
 int b200fhe_arena_alloc(b200fhe_ctx *ctx, size_t n_slots);
-/* use caller-owned device memory (n_slots * 1280 bytes, zero-initialised) as the arena */
+/* use caller-owned device memory (n_slots * 1280 bytes [2048 at 80 bits], zero-initialised) as the arena */
 int b200fhe_arena_attach(b200fhe_ctx *ctx, void *dev_ptr, size_t n_slots);
 size_t b200fhe_arena_slots(const b200fhe_ctx *ctx);
 void *b200fhe_arena_dev_ptr(const b200fhe_ctx *ctx);
-/* tlwe_host is [n][637] uint16, densely packed (the reference's std::array<uint16_t,637>) */
-int b200fhe_upload(b200fhe_ctx *ctx, const uint32_t *slot_ids, const uint16_t *tlwe_host, size_t n);
-int b200fhe_download(b200fhe_ctx *ctx, const uint32_t *slot_ids, uint16_t *tlwe_host, size_t n);
+/* tlwe_host is [n][TLWE0_LEN] lvl0 torus words, densely packed (the reference's std::array<T, n+1>) */
+int b200fhe_upload(b200fhe_ctx *ctx, const uint32_t *slot_ids, const b200fhe_torus0 *tlwe_host, size_t n);
+int b200fhe_download(b200fhe_ctx *ctx, const uint32_t *slot_ids, b200fhe_torus0 *tlwe_host, size_t n);
 
 /* evaluation (asynchronous on the context's stream) --------------------------------------- */
 /* One frontier: gate i reads slots in0[i], in1[i], in2[i] (unused operands ignored, may be NULL
@@ -134,8 +147,8 @@ int b200fhe_exchange(b200fhe_ctx *ctx, size_t first_slot, size_t slots_per_rank)
 
 /* End-to-end convenience with HOST operands: uploads, evaluates, downloads (synchronous).
  * in*_host / out_host are [n][637] uint16; needs an arena of at least 4*n slots. */
-int b200fhe_gates_host(b200fhe_ctx *ctx, const uint8_t *opcode, const uint16_t *in0_host,
-                       const uint16_t *in1_host, const uint16_t *in2_host, uint16_t *out_host, size_t n);
+int b200fhe_gates_host(b200fhe_ctx *ctx, const uint8_t *opcode, const b200fhe_torus0 *in0_host,
+                       const b200fhe_torus0 *in1_host, const b200fhe_torus0 *in2_host, b200fhe_torus0 *out_host, size_t n);
 
 /* pinned host memory helpers (so callers written in any language can stage without torch) */
 int b200fhe_host_alloc(void **ptr, size_t bytes);
@@ -167,9 +180,9 @@ void *b200fhe_stream(const b200fhe_ctx *ctx);
 /* test hooks: stage-level access used by the parity tests --------------------------------- */
 /* blind rotation + sample extraction only: c [n][637] uint16 (already linearly combined)
  * -> lvl1 TLWE [n][1025] uint32 (GateBootstrappingTLWE2TLWE, gatebootstrapping.hpp:188-197) */
-int b200fhe_test_bootstrap_lvl1(b200fhe_ctx *ctx, const uint16_t *c_host, uint32_t *tlwe1_host, size_t n);
+int b200fhe_test_bootstrap_lvl1(b200fhe_ctx *ctx, const b200fhe_torus0 *c_host, uint32_t *tlwe1_host, size_t n);
 /* identity key switch only: [n][1025] uint32 -> [n][637] uint16 (keyswitch.hpp:11-52) */
-int b200fhe_test_keyswitch(b200fhe_ctx *ctx, const uint32_t *tlwe1_host, uint16_t *tlwe0_host, size_t n);
+int b200fhe_test_keyswitch(b200fhe_ctx *ctx, const uint32_t *tlwe1_host, b200fhe_torus0 *tlwe0_host, size_t n);
 /* NTT-domain bootstrapping key as stored on the device: uint32 [636][6][6][1024] */
 int b200fhe_test_read_bk_ntt(b200fhe_ctx *ctx, uint32_t *out_host, size_t first_i, size_t count_i);
 

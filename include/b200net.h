@@ -58,12 +58,12 @@ int b200net_plain_tick(const b200net *net, uint8_t *values);
 int b200net_layout(b200net *net, int world_size);
 /* encrypted back-end on one GPU context (keys already loaded).  Lays out and allocates the arena. */
 int b200net_bind(b200net *net, b200fhe_ctx *ctx, int world_size);
-/* tlwe is [n][637] uint16; nodes must be INPUT or DFF nodes for set, any node for get */
-int b200net_set(b200net *net, const uint32_t *nodes, const uint16_t *tlwe, size_t n);
+/* tlwe is [n][TLWE0_LEN] lvl0 torus words; nodes must be INPUT or DFF nodes for set, any node for get */
+int b200net_set(b200net *net, const uint32_t *nodes, const b200fhe_torus0 *tlwe, size_t n);
 /* resume from a snapshot (iyokan --resume, src/iyokan_tfhepp.cpp:603-617): restores the value of ANY node that
  * holds state - gate outputs included, since the next tick copies them into the DFFs */
-int b200net_restore(b200net *net, const uint32_t *nodes, const uint16_t *tlwe, size_t n);
-int b200net_get(b200net *net, const uint32_t *nodes, uint16_t *tlwe, size_t n);
+int b200net_restore(b200net *net, const uint32_t *nodes, const b200fhe_torus0 *tlwe, size_t n);
+int b200net_get(b200net *net, const uint32_t *nodes, b200fhe_torus0 *tlwe, size_t n);
 int b200net_tick(b200net *net);                               /* all DFFs: Q <- D, one call */
 int b200net_run(b200net *net);                                /* every level, whole width */
 /* multi-GPU building block: evaluate only rank's contiguous share of one level */

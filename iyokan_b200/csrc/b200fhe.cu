@@ -19,10 +19,13 @@
 #include <vector>
 
 #include "../../include/b200fhe.h"
+#ifndef B200FHE_80BIT
 #include "br4_phases.h"
 #include "br6_phases.h"
 #include "br7_phases.h"
+#endif
 #include "br_phases.h"
+#include "brg_phases.h"
 #include "gate_jobs.h"
 #include "ks_phases.h"
 
@@ -32,11 +35,65 @@ using namespace b200;
 // kernels
 // =====================================================================================
 
+// Generic shape (brg_phases.h): any gadget length / limb count / lvl0 torus width; the kernel of the 80-bit flavour,
+// also selectable at 128 bits (variant 1) where the parity tests pin it against the oracle.
+template <int G>
+__global__ void __launch_bounds__(64 * G, 1)
+brg_kernel(const BrJob* __restrict__ jobs, int njobs, const torus0_t* __restrict__ arena,
+           const uint32_t* __restrict__ bk_ntt, const tw_t* __restrict__ tw2f_g, const tw_t* __restrict__ tw2i_g,
+           uint32_t* __restrict__ ubuf, int n_iter)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    BrgSmem<G> sm;
+    sm.carve(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = warp >> 1, q = warp & 1;
+    for (int k = tid; k < TW2_LEN; k += 64 * G) {
+        sm.tw2f[k] = tw2f_g[k];
+        sm.tw2i[k] = tw2i_g[k];
+    }
+    int job = blockIdx.x * G + g;
+    const bool valid = job < njobs;
+    if (!valid) job = njobs - 1;  // duplicate work, keeps every barrier uniform
+    const BrJob jb = jobs[job];
+    uint32_t accr[32];
+    brg_prologue<G>(sm, jb, arena, g, q, lane, accr);
+    __syncthreads();
+    for (int i = 0; i < n_iter; i++) {
+        const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
+        {
+            uint32_t dreg[32];
+            brg_rotate_diff<G>(sm, i, g, q, lane, accr, dreg);
+#pragma unroll 1
+            for (int d = 0; d < GL; d++) {
+                brg_fwd_a<G>(sm, g, q, lane, d, dreg);
+                __syncwarp();
+                brg_fwd_b<G>(sm, g, q, lane, d);
+            }
+        }
+        __syncthreads();
+        brg_pointwise<G>(sm, bk_i, tid);
+        __syncthreads();
+        {
+            uint32_t sum[32];
+#pragma unroll 1
+            for (int l = 0; l < LIMBS; l++) {
+                brg_inv_a<G>(sm, g, q, lane, l);
+                __syncwarp();
+                brg_inv_b<G>(sm, g, q, lane, l, sum);
+            }
+            brg_acc_update<G>(sm, g, q, lane, sum, accr);
+        }
+        __syncwarp();
+    }
+    if (valid) brg_epilogue<G>(sm, g, q, lane, ubuf + (size_t)job * U_STRIDE);
+}
+
+#ifndef B200FHE_80BIT
 // 12-warp throughput shape: a warp owns one accumulator polynomial and runs its three transforms in lock step
 // (ct_stage3 / gs_stage3): 3x the ILP per warp and one twiddle fetch for three butterflies
 template <int G>
 __global__ void __launch_bounds__(64 * G, 1)
-br3_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ arena,
+br3_kernel(const BrJob* __restrict__ jobs, int njobs, const torus0_t* __restrict__ arena,
            const uint32_t* __restrict__ bk_ntt, const tw_t* __restrict__ tw2f_g, const tw_t* __restrict__ tw2i_g,
            uint32_t* __restrict__ ubuf, int n_iter)
 {
@@ -90,7 +147,7 @@ __device__ __forceinline__ void named_barrier_sync(int id, int nthreads)
 // The CTA is cut into G/J barrier groups of J jobs; group k starts k/(G/J) of a step late (skew_cycles apart).
 template <int G, int J>
 __global__ void __launch_bounds__(64 * G, 1)
-br7_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ arena,
+br7_kernel(const BrJob* __restrict__ jobs, int njobs, const torus0_t* __restrict__ arena,
            const uint32_t* __restrict__ bk_ntt, const tw_t* __restrict__ tw2f_g, const tw_t* __restrict__ tw2i_g,
            uint32_t* __restrict__ ubuf, int n_iter, int skew_cycles)
 {
@@ -183,7 +240,7 @@ __device__ __forceinline__ void key_stage_issue(const Br4Smem& sm, const uint32_
 }
 
 __global__ void __launch_bounds__(BR4_THREADS, 1)
-br4_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ arena,
+br4_kernel(const BrJob* __restrict__ jobs, int njobs, const torus0_t* __restrict__ arena,
            const uint32_t* __restrict__ bk_ntt, const BlockTw* __restrict__ tw_g, uint32_t* __restrict__ ubuf, int n_iter)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -247,7 +304,7 @@ __device__ __forceinline__ T* map_to_cta(T* p, uint32_t rank)  // generic addres
 
 // ---- fine-grained cluster shape: one job per 2-CTA cluster, 3 teams of 128 threads per CTA (br6_phases.h) ----
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BR6_THREADS, 1)
-br6_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict__ arena,
+br6_kernel(const BrJob* __restrict__ jobs, int njobs, const torus0_t* __restrict__ arena,
            const uint32_t* __restrict__ bk_ntt, const Block8Tw* __restrict__ tw_g, uint32_t* __restrict__ ubuf, int n_iter)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -333,9 +390,11 @@ br6_kernel(const BrJob* __restrict__ jobs, int njobs, const uint16_t* __restrict
 
 
 
+#endif  // !B200FHE_80BIT
+
 __global__ void __launch_bounds__(KS_THREADS * KS_GROUPS)
 ks_kernel(const KsJob* __restrict__ jobs, const uint32_t* __restrict__ ubuf,
-          const uint32_t* __restrict__ ksk_words, uint16_t* __restrict__ arena)
+          const uint32_t* __restrict__ ksk_words, torus0_t* __restrict__ arena)
 {
     __shared__ uint16_t codes[N1];
     __shared__ uint32_t b_sh;
@@ -397,7 +456,7 @@ ks_split_kernel(const KsJob* __restrict__ jobs, const uint32_t* __restrict__ ubu
 }
 __global__ void __launch_bounds__(KS_THREADS)
 ks_combine_kernel(const KsJob* __restrict__ jobs, const uint32_t* __restrict__ ubuf,
-                  const uint32_t* __restrict__ partial, uint16_t* __restrict__ arena)
+                  const uint32_t* __restrict__ partial, torus0_t* __restrict__ arena)
 {
     const KsJob job = jobs[blockIdx.x];
     const int k = threadIdx.x;
@@ -441,18 +500,18 @@ bk_prep_kernel(const uint32_t* __restrict__ bk_raw, uint32_t* __restrict__ bk_nt
     const int l = task % LIMBS, q = (task / LIMBS) % 2, r = (task / (2 * LIMBS)) % ROWS, i = task / (2 * LIMBS * ROWS);
     const uint32_t* raw = bk_raw + ((size_t)(i * ROWS + r) * 2 + q) * N1;
     uint32_t* out = bk_ntt + ((size_t)(i * BK_COLS + q * LIMBS + l) * ROWS + r) * N1;
-    bk_prep_a(raw, l, lane, tiles[warp]);
+    brg_bk_prep_a(raw, l, lane, tiles[warp]);
     __syncwarp();
     bk_prep_b(tiles[warp], tw2f, scale, lane, out);
 }
 
 // test hook helpers: c [n][637] dense -> arena-like [n][640]
-__global__ void pad_tlwe0_kernel(const uint16_t* __restrict__ dense, uint16_t* __restrict__ padded, size_t n)
+__global__ void pad_tlwe0_kernel(const torus0_t* __restrict__ dense, torus0_t* __restrict__ padded, size_t n)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * SLOT_STRIDE) return;
     const size_t s = idx / SLOT_STRIDE, k = idx % SLOT_STRIDE;
-    padded[idx] = k < TLWE0_LEN ? dense[s * TLWE0_LEN + k] : (uint16_t)0;
+    padded[idx] = k < TLWE0_LEN ? dense[s * TLWE0_LEN + k] : (torus0_t)0;
 }
 
 // =====================================================================================
@@ -478,20 +537,27 @@ constexpr int BR_MAX_SEGMENTS = 5;  // launches one frontier's blind rotations a
 struct b200fhe_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+#ifdef B200FHE_80BIT
+    int G = 4;
+    int variant = 1;
+#else
     int G = 8;
     int variant = 7;  // pinned shape when autotune is off (b200fhe_set_kernel_variant / _jobs_per_cta)
+#endif
     bool autotune = true;  // pick (variant, G) per batch size unless the caller pinned them
     int br7_group = 8;     // jobs per barrier group of br7_kernel (8 = CTA-wide pointwise stage, 4 or 2 = skewed groups)
     int br7_skew = 0;      // start delay between consecutive groups, SM cycles
     NttTables* tab = nullptr;
     tw_t* d_tw2f = nullptr;
     tw_t* d_tw2i = nullptr;
+#ifndef B200FHE_80BIT
     BlockTw* d_blocktw = nullptr;   // team-NTT twiddles (br4_kernel)
     Block8Tw* d_block8tw = nullptr; // 128-thread team NTT (br6_kernel)
+#endif
     uint32_t* d_bk_ntt = nullptr;   // [636][6][6][1024]
-    uint16_t* d_ksk = nullptr;      // [1024][7][3][640]
+    torus0_t* d_ksk = nullptr;      // [1024][t][3][SLOT_STRIDE]
     bool keys = false;
-    uint16_t* d_arena = nullptr;
+    torus0_t* d_arena = nullptr;
     bool arena_owned = false;
     size_t n_slots = 0;
     // job staging (pinned host + device), grown on demand
@@ -564,10 +630,17 @@ static int nccl_fail(const char* what, int rc)
 // B200 at 1965 MHz (profiles/r02_latency_table.json); b200fhe_calibrate() re-measures them on the device
 // at hand (one short wave per shape), so a differently clocked or power-capped part plans with its own
 // numbers.  The plan is an unbounded-knapsack DP over "one more wave of shape s" (cheap: 5 shapes).
+#ifdef B200FHE_80BIT
+constexpr int N_SHAPES = 1;
+#else
 constexpr int N_SHAPES = 5;
+#endif
 struct BrShape { int variant, G, wave_jobs; double wave_ms; };
 struct BrSegment { int variant, G, count; };
 struct PlanTable {
+#ifdef B200FHE_80BIT
+    BrShape shape[N_SHAPES] = {{1, 4, 592, 12.0}};  // generic shape only (brg_kernel<4>); calibrated at key load
+#else
     BrShape shape[N_SHAPES] = {
         {7, 8, 1184, 18.98}, // 16-warp throughput shape: 62.4 k rotations/s
         {3, 6, 888, 14.70},  // 12-warp throughput shape: 60.4 k/s, fills the gap between one and two 16-warp waves
@@ -575,10 +648,11 @@ struct PlanTable {
         {4, 1, 148, 3.02},   // one job per SM
         {6, 1, 74, 2.06},    // one job per 2-SM cluster: lowest latency
     };
+#endif
     double launch_ms = 0.01;  // per extra launch: breaks ties in favour of fewer segments
     bool calibrated = false;
     // DP cache: best[m] = (ms, shape of the last wave) for m jobs, m < DP_MAX
-    static constexpr int DP_MAX = 4 * 1184 + 1;
+    static constexpr int DP_MAX = 4 * 1184 + 1;  // >= a few waves of the widest shape
     double best_ms[DP_MAX];
     int8_t best_shape[DP_MAX];
     bool dp_valid = false;
@@ -646,7 +720,19 @@ static int plan_rotation(const b200fhe_ctx* c, int njobs, BrSegment (&seg)[BR_MA
 }
 
 template <int G>
-static int br3_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+static int brg_launch(b200fhe_ctx* c, int njobs, const torus0_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+{
+    const int grid = (njobs + G - 1) / G;
+    brg_kernel<G><<<grid, 64 * G, BrgSmem<G>::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_tw2f,
+                                                                  c->d_tw2i, ubuf, N0);
+    CK(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+#ifndef B200FHE_80BIT
+template <int G>
+static int br3_launch(b200fhe_ctx* c, int njobs, const torus0_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
 {
     const int grid = (njobs + G - 1) / G;
     br3_kernel<G><<<grid, 64 * G, BrSmem<G>::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_tw2f,
@@ -657,7 +743,7 @@ static int br3_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
 }
 
 template <int G, int J>
-static int br7_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+static int br7_launch(b200fhe_ctx* c, int njobs, const torus0_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
 {
     const int grid = (njobs + G - 1) / G;
     br7_kernel<G, J><<<grid, 64 * G, Br7Smem<G>::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_tw2f,
@@ -667,7 +753,7 @@ static int br7_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
     return 0;
 }
 
-static int br4_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+static int br4_launch(b200fhe_ctx* c, int njobs, const torus0_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
 {
     br4_kernel<<<njobs, BR4_THREADS, Br4Smem::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_blocktw, ubuf, N0);
     CK(cudaGetLastError());
@@ -675,7 +761,7 @@ static int br4_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
     return 0;
 }
 
-static int br6_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+static int br6_launch(b200fhe_ctx* c, int njobs, const torus0_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
 {
     br6_kernel<<<2 * njobs, BR6_THREADS, Br6Smem::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_block8tw, ubuf, N0);
     CK(cudaGetLastError());
@@ -683,9 +769,14 @@ static int br6_launch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t
     return 0;
 }
 
+#endif
+
 // dynamic shared memory opt-in of every blind-rotation shape, once per device (never inside a graph capture)
 static int set_kernel_attrs()
 {
+    CK(cudaFuncSetAttribute(brg_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BrgSmem<4>::BYTES));
+    CK(cudaFuncSetAttribute(brg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BrgSmem<2>::BYTES));
+#ifndef B200FHE_80BIT
     CK(cudaFuncSetAttribute(br3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BrSmem<2>::BYTES));
     CK(cudaFuncSetAttribute(br3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BrSmem<4>::BYTES));
     CK(cudaFuncSetAttribute(br3_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BrSmem<6>::BYTES));
@@ -694,12 +785,21 @@ static int set_kernel_attrs()
     CK(cudaFuncSetAttribute(br7_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br7Smem<8>::BYTES));
     CK(cudaFuncSetAttribute(br4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br4Smem::BYTES));
     CK(cudaFuncSetAttribute(br6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br6Smem::BYTES));
+#endif
     return 0;
 }
 
-static int br_dispatch_one(b200fhe_ctx* c, int variant, int G, int njobs, const uint16_t* arena, uint32_t* ubuf,
+static int br_dispatch_one(b200fhe_ctx* c, int variant, int G, int njobs, const torus0_t* arena, uint32_t* ubuf,
                            const BrJob* d_jobs)
 {
+    if (variant == 1) {
+        switch (G) {
+        case 2: return brg_launch<2>(c, njobs, arena, ubuf, d_jobs);
+        case 4: return brg_launch<4>(c, njobs, arena, ubuf, d_jobs);
+        default: return fail("variant 1 (generic shape) supports 2 or 4 jobs per CTA");
+        }
+    }
+#ifndef B200FHE_80BIT
     if (variant == 7) {
         switch (c->br7_group) {
         case 2: return br7_launch<8, 2>(c, njobs, arena, ubuf, d_jobs);
@@ -717,7 +817,10 @@ static int br_dispatch_one(b200fhe_ctx* c, int variant, int G, int njobs, const 
         default: return fail("variant 3 supports 2, 4 or 6 jobs per CTA");
         }
     }
-    return fail("kernel variant must be 3, 4, 6 or 7");
+    return fail("kernel variant must be 1, 3, 4, 6 or 7");
+#else
+    return fail("the 80-bit flavour carries the generic shape only (variant 1)");
+#endif
 }
 
 // Measures one wave of every shape on this device (dummy jobs on a zeroed slot: the kernels' time does not depend on
@@ -729,13 +832,13 @@ static int calibrate(b200fhe_ctx* c)
     if (off && off[0] == '1') return 0;
     int maxw = 0;
     for (const BrShape& sh : g_plan.shape) maxw = std::max(maxw, sh.wave_jobs);
-    uint16_t* d_slot = nullptr;
+    torus0_t* d_slot = nullptr;
     uint32_t* d_u = nullptr;
     BrJob* d_jobs = nullptr;
-    CK(cudaMalloc(&d_slot, SLOT_STRIDE * 2));
+    CK(cudaMalloc(&d_slot, SLOT_BYTES));
     CK(cudaMalloc(&d_u, (size_t)maxw * U_STRIDE * 4));
     CK(cudaMalloc(&d_jobs, (size_t)maxw * sizeof(BrJob)));
-    CK(cudaMemsetAsync(d_slot, 0, SLOT_STRIDE * 2, c->stream));
+    CK(cudaMemsetAsync(d_slot, 0, SLOT_BYTES, c->stream));
     std::vector<BrJob> jobs(maxw, BrJob{{0u, 0u, 0u}, {1, 0, 0}, 0, 0u});
     CK(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(BrJob), cudaMemcpyHostToDevice, c->stream));
     cudaEvent_t e0, e1;
@@ -768,7 +871,7 @@ static int calibrate(b200fhe_ctx* c)
 }
 
 // rotation job k writes ubuf[k]: segments are contiguous ranges of the job list
-static int br_dispatch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_t* ubuf, const BrJob* d_jobs,
+static int br_dispatch(b200fhe_ctx* c, int njobs, const torus0_t* arena, uint32_t* ubuf, const BrJob* d_jobs,
                        bool timing = true)
 {
     BrSegment seg[BR_MAX_SEGMENTS];
@@ -790,7 +893,7 @@ static int br_dispatch(b200fhe_ctx* c, int njobs, const uint16_t* arena, uint32_
 }
 
 // key switch of `nks` gates: one CTA per gate, or KS_SPLIT CTAs per gate + combine for narrow frontiers
-static int ks_dispatch(b200fhe_ctx* c, size_t nks, const KsJob* d_jobs, const uint32_t* ubuf, uint16_t* arena)
+static int ks_dispatch(b200fhe_ctx* c, size_t nks, const KsJob* d_jobs, const uint32_t* ubuf, torus0_t* arena)
 {
     const uint32_t* ksk = reinterpret_cast<const uint32_t*>(c->d_ksk);
     if (nks <= (size_t)KS_SPLIT_MAX_GATES) {
@@ -868,6 +971,7 @@ int b200fhe_create(b200fhe_ctx** out, int device)
     CK(cudaMalloc(&c->d_tw2i, sizeof(c->tab->tw2i)));
     CK(cudaMemcpyAsync(c->d_tw2f, c->tab->tw2f, sizeof(c->tab->tw2f), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_tw2i, c->tab->tw2i, sizeof(c->tab->tw2i), cudaMemcpyHostToDevice, c->stream));
+#ifndef B200FHE_80BIT
     BlockTw* btw = new BlockTw();
     block_tw_init(*c->tab, *btw);
     CK(cudaMalloc(&c->d_blocktw, sizeof(BlockTw)));
@@ -876,10 +980,13 @@ int b200fhe_create(b200fhe_ctx** out, int device)
     block8_tw_init(*c->tab, *b8tw);
     CK(cudaMalloc(&c->d_block8tw, sizeof(Block8Tw)));
     CK(cudaMemcpyAsync(c->d_block8tw, b8tw, sizeof(Block8Tw), cudaMemcpyHostToDevice, c->stream));
+#endif
     CK(cudaMalloc(&c->d_kspart, (size_t)KS_SPLIT_MAX_GATES * KS_SPLIT * 2 * KS_THREADS * 4));
     CK(cudaStreamSynchronize(c->stream));
+#ifndef B200FHE_80BIT
     delete btw;
     delete b8tw;
+#endif
     *out = c;
     return 0;
 }
@@ -891,8 +998,10 @@ void b200fhe_destroy(b200fhe_ctx* c)
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tw2f);
     cudaFree(c->d_tw2i);
+#ifndef B200FHE_80BIT
     cudaFree(c->d_blocktw);
     cudaFree(c->d_block8tw);
+#endif
     cudaFree(c->d_bk_ntt);
     cudaFree(c->d_ksk);
     if (c->arena_owned) cudaFree(c->d_arena);
@@ -919,11 +1028,16 @@ int b200fhe_set_jobs_per_cta(b200fhe_ctx* c, int g)
     if (!c) return fail("null context");
     if (g == 0) {  // back to the batch-size heuristic
         c->autotune = true;
+#ifdef B200FHE_80BIT
+        c->G = 4;
+        c->variant = 1;
+#else
         c->G = 8;
         c->variant = 7;
+#endif
         return 0;
     }
-    if (g != 2 && g != 4 && g != 6 && g != 8) return fail("jobs per CTA must be 2, 4, 6 (variant 3) or 8 (variant 7)");
+    if (g != 2 && g != 4 && g != 6 && g != 8) return fail("jobs per CTA must be 2, 4 (variants 1, 3), 6 (variant 3) or 8 (variant 7)");
     c->G = g;
     c->autotune = false;
     return 0;
@@ -933,13 +1047,14 @@ int b200fhe_set_kernel_variant(b200fhe_ctx* c, int variant)
 {
     if (!c) return fail("null context");
     if (variant == 0) return b200fhe_set_jobs_per_cta(c, 0);
-    if (variant != 3 && variant != 4 && variant != 6 && variant != 7) return fail("kernel variant must be 0 (auto), 3, 4, 6 or 7");
+    if (variant != 1 && variant != 3 && variant != 4 && variant != 6 && variant != 7)
+        return fail("kernel variant must be 0 (auto), 1, 3, 4, 6 or 7");
     c->variant = variant;
     c->autotune = false;
     return 0;
 }
 
-int b200fhe_load_keys(b200fhe_ctx* c, const uint32_t* bk_raw, const uint16_t* ksk)
+int b200fhe_load_keys(b200fhe_ctx* c, const uint32_t* bk_raw, const torus0_t* ksk)
 {
     if (!c || !bk_raw || !ksk) return fail("null argument");
     if (set_dev(c)) return 1;
@@ -948,7 +1063,7 @@ int b200fhe_load_keys(b200fhe_ctx* c, const uint32_t* bk_raw, const uint16_t* ks
     const size_t bk_ntt_bytes = (size_t)N0 * BK_COLS * ROWS * N1 * 4;
     const size_t ksk_rows = (size_t)N1 * KS_T * 3;
     if (!c->d_bk_ntt) CK(cudaMalloc(&c->d_bk_ntt, bk_ntt_bytes));
-    if (!c->d_ksk) CK(cudaMalloc(&c->d_ksk, ksk_rows * KSK_ROW * 2));
+    if (!c->d_ksk) CK(cudaMalloc(&c->d_ksk, ksk_rows * KSK_ROW * sizeof(torus0_t)));
     uint32_t* d_raw = nullptr;
     CK(cudaMalloc(&d_raw, bk_raw_bytes));
     CK(cudaMemcpyAsync(d_raw, bk_raw, bk_raw_bytes, cudaMemcpyHostToDevice, c->stream));
@@ -958,8 +1073,8 @@ int b200fhe_load_keys(b200fhe_ctx* c, const uint32_t* bk_raw, const uint16_t* ks
     CK(cudaGetLastError());
     c->launches++;
     // key-switching key: pad every 637-element row to 640 (1280 B, 16-byte aligned rows)
-    CK(cudaMemsetAsync(c->d_ksk, 0, ksk_rows * KSK_ROW * 2, c->stream));
-    CK(cudaMemcpy2DAsync(c->d_ksk, KSK_ROW * 2, ksk, TLWE0_LEN * 2, TLWE0_LEN * 2, ksk_rows, cudaMemcpyHostToDevice,
+    CK(cudaMemsetAsync(c->d_ksk, 0, ksk_rows * KSK_ROW * sizeof(torus0_t), c->stream));
+    CK(cudaMemcpy2DAsync(c->d_ksk, KSK_ROW * sizeof(torus0_t), ksk, TLWE0_LEN * sizeof(torus0_t), TLWE0_LEN * sizeof(torus0_t), ksk_rows, cudaMemcpyHostToDevice,
                          c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaFree(d_raw));
@@ -974,10 +1089,10 @@ int b200fhe_arena_alloc(b200fhe_ctx* c, size_t n_slots)
     CK(cudaStreamSynchronize(c->stream));
     if (c->arena_owned && c->d_arena) CK(cudaFree(c->d_arena));
     c->d_arena = nullptr;
-    CK(cudaMalloc(&c->d_arena, n_slots * SLOT_STRIDE * 2));
+    CK(cudaMalloc(&c->d_arena, n_slots * SLOT_BYTES));
     // on the context's own (non-blocking) stream: a legacy-stream memset would not be ordered with the
     // uploads that follow and could wipe them
-    CK(cudaMemsetAsync(c->d_arena, 0, n_slots * SLOT_STRIDE * 2, c->stream));
+    CK(cudaMemsetAsync(c->d_arena, 0, n_slots * SLOT_BYTES, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->arena_owned = true;
     c->n_slots = n_slots;
@@ -990,7 +1105,7 @@ int b200fhe_arena_attach(b200fhe_ctx* c, void* dev_ptr, size_t n_slots)
     if (set_dev(c)) return 1;
     CK(cudaStreamSynchronize(c->stream));
     if (c->arena_owned && c->d_arena) CK(cudaFree(c->d_arena));
-    c->d_arena = reinterpret_cast<uint16_t*>(dev_ptr);
+    c->d_arena = reinterpret_cast<torus0_t*>(dev_ptr);
     c->arena_owned = false;
     c->n_slots = n_slots;
     return 0;
@@ -1010,29 +1125,29 @@ static int check_slots(b200fhe_ctx* c, const uint32_t* ids, size_t n)
 }
 
 // copies runs of consecutive slot ids with one strided copy each
-int b200fhe_upload(b200fhe_ctx* c, const uint32_t* ids, const uint16_t* host, size_t n)
+int b200fhe_upload(b200fhe_ctx* c, const uint32_t* ids, const torus0_t* host, size_t n)
 {
     if (!c || (n && (!ids || !host))) return fail("null argument");
     if (set_dev(c) || check_slots(c, ids, n)) return 1;
     for (size_t i = 0; i < n;) {
         size_t j = i + 1;
         while (j < n && ids[j] == ids[j - 1] + 1) j++;
-        CK(cudaMemcpy2DAsync(c->d_arena + (size_t)ids[i] * SLOT_STRIDE, SLOT_STRIDE * 2, host + i * TLWE0_LEN,
-                             TLWE0_LEN * 2, TLWE0_LEN * 2, j - i, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpy2DAsync(c->d_arena + (size_t)ids[i] * SLOT_STRIDE, SLOT_BYTES, host + i * TLWE0_LEN,
+                             TLWE0_LEN * sizeof(torus0_t), TLWE0_LEN * sizeof(torus0_t), j - i, cudaMemcpyHostToDevice, c->stream));
         i = j;
     }
     return 0;
 }
 
-int b200fhe_download(b200fhe_ctx* c, const uint32_t* ids, uint16_t* host, size_t n)
+int b200fhe_download(b200fhe_ctx* c, const uint32_t* ids, torus0_t* host, size_t n)
 {
     if (!c || (n && (!ids || !host))) return fail("null argument");
     if (set_dev(c) || check_slots(c, ids, n)) return 1;
     for (size_t i = 0; i < n;) {
         size_t j = i + 1;
         while (j < n && ids[j] == ids[j - 1] + 1) j++;
-        CK(cudaMemcpy2DAsync(host + i * TLWE0_LEN, TLWE0_LEN * 2, c->d_arena + (size_t)ids[i] * SLOT_STRIDE,
-                             SLOT_STRIDE * 2, TLWE0_LEN * 2, j - i, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpy2DAsync(host + i * TLWE0_LEN, TLWE0_LEN * sizeof(torus0_t), c->d_arena + (size_t)ids[i] * SLOT_STRIDE,
+                             SLOT_BYTES, TLWE0_LEN * sizeof(torus0_t), j - i, cudaMemcpyDeviceToHost, c->stream));
         i = j;
     }
     CK(cudaStreamSynchronize(c->stream));
@@ -1203,8 +1318,8 @@ int b200fhe_last_batch_segments(b200fhe_ctx* c, int* variant, int* jobs_per_cta,
     return n;
 }
 
-int b200fhe_gates_host(b200fhe_ctx* c, const uint8_t* opcode, const uint16_t* in0_host, const uint16_t* in1_host,
-                       const uint16_t* in2_host, uint16_t* out_host, size_t n)
+int b200fhe_gates_host(b200fhe_ctx* c, const uint8_t* opcode, const torus0_t* in0_host, const torus0_t* in1_host,
+                       const torus0_t* in2_host, torus0_t* out_host, size_t n)
 {
     if (!c) return fail("null context");
     if (n == 0) return 0;
@@ -1213,7 +1328,7 @@ int b200fhe_gates_host(b200fhe_ctx* c, const uint8_t* opcode, const uint16_t* in
     if (set_dev(c)) return 1;
     std::vector<uint32_t> ids(4 * n);
     for (size_t i = 0; i < 4 * n; i++) ids[i] = (uint32_t)i;
-    const uint16_t* ins[3] = {in0_host, in1_host, in2_host};
+    const torus0_t* ins[3] = {in0_host, in1_host, in2_host};
     for (int k = 0; k < 3; k++)
         if (ins[k] && b200fhe_upload(c, ids.data() + k * n, ins[k], n)) return 1;
     if (b200fhe_gate_batch(c, opcode, ids.data(), ids.data() + n, ids.data() + 2 * n, ids.data() + 3 * n, n)) return 1;
@@ -1245,8 +1360,8 @@ static int exchange_issue(b200fhe_ctx* c, size_t first_slot, size_t slots_per_ra
     if (c->world == 1 || slots_per_rank == 0) return 0;
     if (!c->comm) return fail("no communicator: call b200fhe_comm_init first");
     if (first_slot + slots_per_rank * (size_t)c->world > c->n_slots) return fail("exchange range exceeds the arena");
-    uint8_t* base = reinterpret_cast<uint8_t*>(c->d_arena) + first_slot * (size_t)SLOT_STRIDE * 2;
-    const size_t bytes = slots_per_rank * (size_t)SLOT_STRIDE * 2;
+    uint8_t* base = reinterpret_cast<uint8_t*>(c->d_arena) + first_slot * (size_t)SLOT_BYTES;
+    const size_t bytes = slots_per_rank * (size_t)SLOT_BYTES;
     const int rc = g_nccl.AllGather(base + (size_t)c->rank * bytes, base, bytes, /*ncclUint8*/ 1, c->comm, c->stream);
     if (rc) return nccl_fail("ncclAllGather", rc);
     return 0;
@@ -1532,24 +1647,24 @@ extern "C" {
 
 // ---- test hooks -------------------------------------------------------------------------
 
-int b200fhe_test_bootstrap_lvl1(b200fhe_ctx* c, const uint16_t* c_host, uint32_t* tlwe1_host, size_t n)
+int b200fhe_test_bootstrap_lvl1(b200fhe_ctx* c, const torus0_t* c_host, uint32_t* tlwe1_host, size_t n)
 {
     if (!c || !c_host || !tlwe1_host) return fail("null argument");
     if (!c->keys) return fail("keys not loaded");
     if (n == 0) return 0;
     if (set_dev(c)) return 1;
-    uint16_t *d_dense = nullptr, *d_pad = nullptr;
+    torus0_t *d_dense = nullptr, *d_pad = nullptr;
     uint32_t* d_u = nullptr;
     BrJob* d_jobs = nullptr;
     std::vector<BrJob> jobs(n);
     for (size_t i = 0; i < n; i++) {
         jobs[i] = BrJob{{(uint32_t)i, 0u, 0u}, {1, 0, 0}, 0, 0u};
     }
-    CK(cudaMalloc(&d_dense, n * TLWE0_LEN * 2));
-    CK(cudaMalloc(&d_pad, n * SLOT_STRIDE * 2));
+    CK(cudaMalloc(&d_dense, n * TLWE0_LEN * sizeof(torus0_t)));
+    CK(cudaMalloc(&d_pad, n * SLOT_BYTES));
     CK(cudaMalloc(&d_u, n * (size_t)U_STRIDE * 4));
     CK(cudaMalloc(&d_jobs, n * sizeof(BrJob)));
-    CK(cudaMemcpyAsync(d_dense, c_host, n * TLWE0_LEN * 2, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_dense, c_host, n * TLWE0_LEN * sizeof(torus0_t), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d_jobs, jobs.data(), n * sizeof(BrJob), cudaMemcpyHostToDevice, c->stream));
     const size_t tot = n * SLOT_STRIDE;
     pad_tlwe0_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(d_dense, d_pad, n);
@@ -1565,25 +1680,25 @@ int b200fhe_test_bootstrap_lvl1(b200fhe_ctx* c, const uint16_t* c_host, uint32_t
     return 0;
 }
 
-int b200fhe_test_keyswitch(b200fhe_ctx* c, const uint32_t* tlwe1_host, uint16_t* tlwe0_host, size_t n)
+int b200fhe_test_keyswitch(b200fhe_ctx* c, const uint32_t* tlwe1_host, torus0_t* tlwe0_host, size_t n)
 {
     if (!c || !tlwe1_host || !tlwe0_host) return fail("null argument");
     if (!c->keys) return fail("keys not loaded");
     if (n == 0) return 0;
     if (set_dev(c)) return 1;
     uint32_t* d_u = nullptr;
-    uint16_t* d_out = nullptr;
+    torus0_t* d_out = nullptr;
     KsJob* d_jobs = nullptr;
     std::vector<KsJob> jobs(n);
     for (size_t i = 0; i < n; i++) jobs[i] = KsJob{(uint32_t)i, KS_NONE, (uint32_t)i, 0u};
     CK(cudaMalloc(&d_u, n * (size_t)U_STRIDE * 4));
-    CK(cudaMalloc(&d_out, n * SLOT_STRIDE * 2));
+    CK(cudaMalloc(&d_out, n * SLOT_BYTES));
     CK(cudaMalloc(&d_jobs, n * sizeof(KsJob)));
     CK(cudaMemcpy2DAsync(d_u, U_STRIDE * 4, tlwe1_host, TLWE1_LEN * 4, TLWE1_LEN * 4, n, cudaMemcpyHostToDevice,
                          c->stream));
     CK(cudaMemcpyAsync(d_jobs, jobs.data(), n * sizeof(KsJob), cudaMemcpyHostToDevice, c->stream));
     if (ks_dispatch(c, n, d_jobs, d_u, d_out)) return 1;
-    CK(cudaMemcpy2DAsync(tlwe0_host, TLWE0_LEN * 2, d_out, SLOT_STRIDE * 2, TLWE0_LEN * 2, n, cudaMemcpyDeviceToHost,
+    CK(cudaMemcpy2DAsync(tlwe0_host, TLWE0_LEN * sizeof(torus0_t), d_out, SLOT_BYTES, TLWE0_LEN * sizeof(torus0_t), n, cudaMemcpyDeviceToHost,
                          c->stream));
     CK(cudaStreamSynchronize(c->stream));
     cudaFree(d_u);

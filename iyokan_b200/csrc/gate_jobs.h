@@ -53,7 +53,7 @@ inline const char* build_gate_jobs(const uint8_t* opcode, const uint32_t* in0, c
             BrJob& j = br[cnt.nbr];
             j.in[0] = a; j.in[1] = b; j.in[2] = 0;
             j.sgn[0] = (int8_t)sa; j.sgn[1] = (int8_t)sb; j.sgn[2] = 0; j.pad = 0;
-            j.off = (uint32_t)(off * (int)MU0) & 0xFFFFu;
+            j.off = ((uint32_t)off * MU0) & T0_MASK;
             ks[cnt.nks++] = KsJob{(uint32_t)cnt.nbr, KS_NONE, o, 0u};
             cnt.nbr++;
         } else if (op == OP_MUX) {
@@ -62,11 +62,11 @@ inline const char* build_gate_jobs(const uint8_t* opcode, const uint32_t* in0, c
             BrJob& j1 = br[cnt.nbr];
             j1.in[0] = a; j1.in[1] = b; j1.in[2] = s;
             j1.sgn[0] = 0; j1.sgn[1] = 1; j1.sgn[2] = 1; j1.pad = 0;
-            j1.off = (0u - MU0) & 0xFFFFu;
+            j1.off = (0u - MU0) & T0_MASK;
             BrJob& j0 = br[cnt.nbr + 1];
             j0.in[0] = a; j0.in[1] = b; j0.in[2] = s;
             j0.sgn[0] = 1; j0.sgn[1] = 0; j0.sgn[2] = -1; j0.pad = 0;
-            j0.off = (0u - MU0) & 0xFFFFu;
+            j0.off = (0u - MU0) & T0_MASK;
             ks[cnt.nks++] = KsJob{(uint32_t)cnt.nbr, (uint32_t)cnt.nbr + 1, o, MU0};  // + mu after the switch, :260
             cnt.nbr += 2;
         } else if (op == OP_NOT || op == OP_COPY) {

@@ -17,7 +17,8 @@
 
 namespace b200 {
 
-constexpr int KS_THREADS = SLOT_STRIDE / 2;  // 320 threads, one 32-bit word (2 coefficients) each
+constexpr int KS_THREADS = SLOT_WORDS;       // one 32-bit word of the output slot per thread: 320 threads x 2 uint16
+                                             // coefficients (128-bit flavour), 512 threads x 1 uint32 coefficient (80-bit)
 constexpr uint32_t KS_NONE = 0xFFFFFFFFu;
 
 struct KsJob {
@@ -34,14 +35,24 @@ B200_HD uint16_t ks_code(const uint32_t* ubuf, const KsJob& job, int i)
     return (uint16_t)((u + (1u << (32 - 1 - KS_T * KS_BASEBIT))) >> (32 - KS_T * KS_BASEBIT));
 }
 
+// keyswitch.hpp:27-39: 32 -> 16-bit rounding of b when the lvl0 torus is narrower, plain copy when it is 32 bits wide
 B200_HD uint32_t ks_b_rounded(const uint32_t* ubuf, const KsJob& job)
 {
     uint32_t b = ubuf[(size_t)job.u0 * U_STRIDE + N1];
     if (job.u1 != KS_NONE) b += ubuf[(size_t)job.u1 * U_STRIDE + N1];
-    return ((b + (1u << 15)) >> 16) & 0xFFFFu;
+    if (T0_BITS == 32) return b;
+    return ((b + (1u << (31 - (T0_BITS & 31)))) >> (32 - (T0_BITS & 31))) & T0_MASK;
 }
 
-constexpr int KS_GROUPS = 3;  // row groups per CTA: group y walks coefficients i = y, y+3, ... (latency / 3)
+// one selected key row word into the accumulators: two uint16 lanes (the low halves add exactly modulo 2^16
+// inside a 32-bit add) or one uint32 coefficient
+B200_HD void ks_add(uint32_t w, uint32_t& lo, uint32_t& hi)
+{
+    lo += w;
+    if (T0_BITS == 16) hi += w >> 16;
+}
+
+constexpr int KS_GROUPS = T0_BITS == 16 ? 3 : 2;  // row groups per CTA: group y walks coefficients i = y, y+G, ...
 constexpr int KS_SPLIT = 4;   // CTAs per key switch on the narrow-frontier path (256 coefficients each)
 constexpr int KS_SPLIT_MAX_GATES = 148;  // frontiers up to this size use the split path
 
@@ -57,9 +68,7 @@ B200_HD void ks_accumulate_group(const uint32_t* ksk_words, const uint16_t* code
         for (int j = 0; j < KS_T; j++) {
             const uint32_t g = (code >> (2 * (KS_T - 1 - j))) & 3u;
             const uint32_t* row = ksk_words + (size_t)((i * KS_T + j) * 3 + (g ? g - 1 : 0)) * KS_THREADS;
-            const uint32_t w = g ? row[k] : 0u;
-            lo += w;
-            hi += w >> 16;
+            ks_add(g ? row[k] : 0u, lo, hi);
         }
     }
     lo_out = lo;
@@ -78,9 +87,7 @@ B200_HD void ks_accumulate_range(const uint32_t* ksk_words, const uint16_t* code
         for (int j = 0; j < KS_T; j++) {
             const uint32_t g = (code >> (2 * (KS_T - 1 - j))) & 3u;
             const uint32_t* row = ksk_words + (size_t)((i * KS_T + j) * 3 + (g ? g - 1 : 0)) * KS_THREADS;
-            const uint32_t w = g ? row[k] : 0u;
-            lo += w;
-            hi += w >> 16;
+            ks_add(g ? row[k] : 0u, lo, hi);
         }
     }
     lo_out = lo;
@@ -90,6 +97,7 @@ B200_HD void ks_accumulate_range(const uint32_t* ksk_words, const uint16_t* code
 B200_HD uint32_t ks_finish(uint32_t lo, uint32_t hi, uint32_t b_rounded, uint32_t post, int k)
 {
     uint32_t r_lo = 0u - lo, r_hi = 0u - hi;
+    if (T0_BITS == 32) return k == N0 ? r_lo + b_rounded + post : r_lo;
     if (k == N0 / 2) r_lo += b_rounded + post;  // coefficient 636 = b lives in the low half of word 318
     return (r_lo & 0xFFFFu) | (r_hi << 16);
 }
@@ -104,9 +112,7 @@ B200_HD uint32_t ks_accumulate(const uint32_t* ksk_words, const uint16_t* codes,
         for (int j = 0; j < KS_T; j++) {
             const uint32_t g = (code >> (2 * (KS_T - 1 - j))) & 3u;
             const uint32_t* row = ksk_words + (size_t)((i * KS_T + j) * 3 + (g ? g - 1 : 0)) * KS_THREADS;
-            const uint32_t w = g ? row[k] : 0u;
-            lo += w;
-            hi += w >> 16;
+            ks_add(g ? row[k] : 0u, lo, hi);
         }
     }
     uint32_t r_lo = 0u - lo, r_hi = 0u - hi;
@@ -124,11 +130,12 @@ B200_HD uint32_t unary_word(const UnaryJob& job, const uint32_t* arena_words, in
     const uint32_t w = (job.op == OP_NOT || job.op == OP_COPY) ? arena_words[(size_t)job.src * KS_THREADS + k] : 0u;
     if (job.op == OP_COPY) return w;
     if (job.op == OP_NOT) {
+        if (T0_BITS == 32) return 0u - w;
         const uint32_t lo = (0u - w) & 0xFFFFu, hi = (0u - (w >> 16)) & 0xFFFFu;
         return lo | (hi << 16);
     }
-    const uint32_t b = (job.op == OP_CONST1) ? MU0 : ((0u - MU0) & 0xFFFFu);
-    return (k == N0 / 2) ? b : 0u;
+    const uint32_t b = (job.op == OP_CONST1) ? MU0 : ((0u - MU0) & T0_MASK);
+    return (k == (T0_BITS == 32 ? N0 : N0 / 2)) ? b : 0u;
 }
 
 }  // namespace b200

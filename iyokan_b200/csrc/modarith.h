@@ -7,11 +7,13 @@
 // every per-limb integer result is bounded by 6*1024*32*1024 = 201,326,592 < p/2 and is
 // recovered exactly from its residue mod p; the three results are recombined mod 2^32.
 // (SURVEY.md Appendix A derives the 2^48.6 bound that forces either this split or a >49-bit modulus.)
+// 80-bit flavour (l = 2, Bg = 2^10): 4 rows x 1024 x 512 x 64 = 2^27 < p/2 with FIVE limbs of 7,7,6,6,6 bits.
 //
 // p = 2^29 - 14335 = 536856577, p = 1 (mod 2048).  Values are kept lazily in [0, 8p) (8p < 2^32):
 //   shoup_mul : any 32-bit y  -> y*w mod p in [0, 2p)      (Harvey / Shoup, 3 integer multiplies)
 //   fix29     : any 32-bit x  -> x mod p   in [0, p + 8c)  (c = 2^29 - p), one shift + one multiply-add
 #pragma once
+#include "fhe_params.h"
 #include "hd.h"
 
 namespace b200 {
@@ -22,7 +24,7 @@ constexpr uint32_t P4 = 4u * P;
 constexpr uint32_t PC = (1u << 29) - P;      // 14335
 constexpr uint32_t PINVNEG = 331335679u;     // -p^{-1} mod 2^32
 constexpr uint32_t PSI = 127625803u;         // primitive 2048-th root of unity mod p (5^((p-1)/2048))
-constexpr uint32_t CONV_BOUND = 6u * 1024u * 32u * 1024u;
+constexpr uint32_t CONV_BOUND = (uint32_t)ROWS * 1024u * (1u << (BGBIT - 1)) * (1u << (limb_width(0) - 1));  // widest limb first
 static_assert((uint64_t)P * PINVNEG % (1ull << 32) == (1ull << 32) - 1, "PINVNEG");
 static_assert(CONV_BOUND < P / 2, "exactness bound");
 static_assert((1u << 28) + 8u * PC + CONV_BOUND < P, "centred lift is unambiguous");

@@ -275,7 +275,7 @@ int b200net_bind(b200net* net, b200fhe_ctx* ctx, int world)
     return 0;
 }
 
-int b200net_set(b200net* net, const uint32_t* nodes, const uint16_t* tlwe, size_t n)
+int b200net_set(b200net* net, const uint32_t* nodes, const b200fhe_torus0* tlwe, size_t n)
 {
     if (!net || !net->ctx) return fail("netlist is not bound to a context");
     std::vector<uint32_t> s(n);
@@ -289,7 +289,7 @@ int b200net_set(b200net* net, const uint32_t* nodes, const uint16_t* tlwe, size_
     return 0;
 }
 
-int b200net_restore(b200net* net, const uint32_t* nodes, const uint16_t* tlwe, size_t n)
+int b200net_restore(b200net* net, const uint32_t* nodes, const b200fhe_torus0* tlwe, size_t n)
 {
     if (!net || !net->ctx) return fail("netlist is not bound to a context");
     std::vector<uint32_t> s(n);
@@ -302,7 +302,7 @@ int b200net_restore(b200net* net, const uint32_t* nodes, const uint16_t* tlwe, s
     return 0;
 }
 
-int b200net_get(b200net* net, const uint32_t* nodes, uint16_t* tlwe, size_t n)
+int b200net_get(b200net* net, const uint32_t* nodes, b200fhe_torus0* tlwe, size_t n)
 {
     if (!net || !net->ctx) return fail("netlist is not bound to a context");
     std::vector<uint32_t> s(n);

@@ -7,18 +7,28 @@ no sm_100a GPU is present, every entry point raises.
 from __future__ import annotations
 
 import ctypes
+import os
 from pathlib import Path
 
 import numpy as np
 
 CSRC = Path(__file__).resolve().parent / "csrc"
-LIB_PATH = CSRC / "libb200fhe.so"
+# Parameter flavour: a property of the process, like the reference's compile-time IYOKAN_80BIT_SECURITY switch
+# (CMakeLists.txt:28-30).  B200FHE_FLAVOUR="" loads libb200fhe.so (128-bit set), "80" loads libb200fhe80.so (80-bit set).
+FLAVOUR = os.environ.get("B200FHE_FLAVOUR", "")
+if FLAVOUR not in ("", "80"):
+    raise ImportError(f"B200FHE_FLAVOUR must be '' (128-bit) or '80', not {FLAVOUR!r}")
+LIB_PATH = CSRC / f"libb200fhe{FLAVOUR}.so"
 
-N0, N1 = 636, 1024
-TLWE0_LEN, TLWE1_LEN = 637, 1025
-BK_SHAPE = (636, 6, 2, 1024)        # raw TRGSW bootstrapping key, uint32
-KSK_SHAPE = (1024, 7, 3, 637)       # identity key-switching key, uint16
-BK_NTT_SHAPE = (636, 6, 6, 1024)    # device form: [i][poly*3+limb][row][position]
+N1, TLWE1_LEN = 1024, 1025
+if FLAVOUR == "80":   # TFHEpp include/params/CGGI16.hpp
+    N0, GL, KS_T, LIMBS, T0, MU0, SLOT_BYTES = 500, 2, 8, 5, np.uint32, 1 << 29, 2048
+else:                 # TFHEpp include/params/128bit.hpp
+    N0, GL, KS_T, LIMBS, T0, MU0, SLOT_BYTES = 636, 3, 7, 3, np.uint16, 1 << 13, 1280
+TLWE0_LEN = N0 + 1
+BK_SHAPE = (N0, 2 * GL, 2, 1024)              # raw TRGSW bootstrapping key, uint32
+KSK_SHAPE = (1024, KS_T, 3, TLWE0_LEN)        # identity key-switching key, lvl0 torus words
+BK_NTT_SHAPE = (N0, 2 * LIMBS, 2 * GL, 1024)  # device form: [i][poly*LIMBS+limb][row][position]
 
 OPS = {
     "AND": 0, "NAND": 1, "ANDNOT": 2, "OR": 3, "NOR": 4, "ORNOT": 5, "XOR": 6, "XNOR": 7,
@@ -253,9 +263,9 @@ class Context:
 
     def load_keys(self, bk_raw: np.ndarray, ksk: np.ndarray):
         bk_raw = np.ascontiguousarray(bk_raw, dtype=np.uint32)
-        ksk = np.ascontiguousarray(ksk, dtype=np.uint16)
+        ksk = np.ascontiguousarray(ksk, dtype=T0)
         if bk_raw.size != int(np.prod(BK_SHAPE)) or ksk.size != int(np.prod(KSK_SHAPE)):
-            raise ValueError("key arrays have the wrong size for the 128-bit parameter set")
+            raise ValueError("key arrays have the wrong size for this parameter set")
         self._ck(self._lib.b200fhe_load_keys(self._h, _ptr(bk_raw), _ptr(ksk)))
 
     def arena_alloc(self, n_slots: int):
@@ -278,16 +288,16 @@ class Context:
 
     def upload(self, slot_ids, tlwe: np.ndarray):
         ids = _u32(slot_ids)
-        tlwe = np.ascontiguousarray(tlwe, dtype=np.uint16)
+        tlwe = np.ascontiguousarray(tlwe, dtype=T0)
         if tlwe.size != ids.size * TLWE0_LEN:
-            raise ValueError("tlwe array must be [n][637] uint16")
+            raise ValueError(f"tlwe array must be [n][{TLWE0_LEN}] {np.dtype(T0).name}")
         self._ck(self._lib.b200fhe_upload(self._h, _ptr(ids), _ptr(tlwe), ids.size))
         self.sync()  # the source may be pageable numpy memory
 
     def download(self, slot_ids, out: np.ndarray | None = None) -> np.ndarray:
         ids = _u32(slot_ids)
         if out is None:
-            out = np.empty((ids.size, TLWE0_LEN), np.uint16)
+            out = np.empty((ids.size, TLWE0_LEN), T0)
         self._ck(self._lib.b200fhe_download(self._h, _ptr(ids), _ptr(out), ids.size))
         return out
 
@@ -325,9 +335,9 @@ class Context:
     def gates_host(self, opcode, in0, in1, in2, out: np.ndarray | None = None) -> np.ndarray:
         op = np.ascontiguousarray(opcode, dtype=np.uint8)
         n = op.size
-        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.uint16) for a in (in0, in1, in2)]
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=T0) for a in (in0, in1, in2)]
         if out is None:
-            out = np.empty((n, TLWE0_LEN), np.uint16)
+            out = np.empty((n, TLWE0_LEN), T0)
         self._ck(self._lib.b200fhe_gates_host(self._h, _ptr(op), _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]),
                                                _ptr(out), n))
         return out
@@ -352,14 +362,14 @@ class Context:
 
     # ---- stage-level test hooks ----
     def test_bootstrap_lvl1(self, c: np.ndarray) -> np.ndarray:
-        c = np.ascontiguousarray(c, dtype=np.uint16).reshape(-1, TLWE0_LEN)
+        c = np.ascontiguousarray(c, dtype=T0).reshape(-1, TLWE0_LEN)
         out = np.empty((c.shape[0], TLWE1_LEN), np.uint32)
         self._ck(self._lib.b200fhe_test_bootstrap_lvl1(self._h, _ptr(c), _ptr(out), c.shape[0]))
         return out
 
     def test_keyswitch(self, u: np.ndarray) -> np.ndarray:
         u = np.ascontiguousarray(u, dtype=np.uint32).reshape(-1, TLWE1_LEN)
-        out = np.empty((u.shape[0], TLWE0_LEN), np.uint16)
+        out = np.empty((u.shape[0], TLWE0_LEN), T0)
         self._ck(self._lib.b200fhe_test_keyswitch(self._h, _ptr(u), _ptr(out), u.shape[0]))
         return out
 

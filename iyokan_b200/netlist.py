@@ -15,13 +15,12 @@ from pathlib import Path
 
 import numpy as np
 
-from .lib import OPS, TLWE0_LEN, B200FheError, Context
+from .lib import FLAVOUR, MU0, OPS, T0, TLWE0_LEN, B200FheError, Context
 
 HOST = Path(__file__).resolve().parent / "host"
-NET_LIB = HOST / "libb200net.so"
+NET_LIB = HOST / f"libb200net{FLAVOUR}.so"
 
 INPUT, DFF, OUTPUT = 32, 33, 34
-MU0 = 1 << 13
 
 
 class NetBuilder:
@@ -352,19 +351,19 @@ class NetEngine:
 
     def set(self, nodes, tlwe):
         nodes = np.ascontiguousarray(nodes, np.uint32)
-        tlwe = np.ascontiguousarray(tlwe, np.uint16)
+        tlwe = np.ascontiguousarray(tlwe, T0)
         assert tlwe.size == nodes.size * TLWE0_LEN
         self._ck(self.lib.b200net_set(self._h, _p(nodes), _p(tlwe), nodes.size))
 
     def restore(self, nodes, tlwe):
         nodes = np.ascontiguousarray(nodes, np.uint32)
-        tlwe = np.ascontiguousarray(tlwe, np.uint16)
+        tlwe = np.ascontiguousarray(tlwe, T0)
         assert tlwe.size == nodes.size * TLWE0_LEN
         self._ck(self.lib.b200net_restore(self._h, _p(nodes), _p(tlwe), nodes.size))
 
     def get(self, nodes) -> np.ndarray:
         nodes = np.ascontiguousarray(nodes, np.uint32)
-        out = np.empty((nodes.size, TLWE0_LEN), np.uint16)
+        out = np.empty((nodes.size, TLWE0_LEN), T0)
         self._ck(self.lib.b200net_get(self._h, _p(nodes), _p(out), nodes.size))
         return out
 
@@ -380,8 +379,8 @@ class NetEngine:
 
 def trivial(bit) -> np.ndarray:
     """Noiseless ciphertext (0,...,0, +-mu): what Iyokan feeds for reset/constants (iyokan_tfhepp.hpp:23-27)."""
-    t = np.zeros(TLWE0_LEN, np.uint16)
-    t[-1] = MU0 if bit else (-MU0) & 0xFFFF
+    t = np.zeros(TLWE0_LEN, T0)
+    t[-1] = MU0 if bit else (-MU0) & ((1 << (8 * np.dtype(T0).itemsize)) - 1)
     return t
 
 
@@ -461,7 +460,7 @@ class EncryptedRunner:
 
     def _ct(self, x):
         x = np.asarray(x)
-        if x.dtype == np.uint16 and x.ndim == 2 and x.shape[1] == TLWE0_LEN:
+        if x.dtype == T0 and x.ndim == 2 and x.shape[1] == TLWE0_LEN:
             return x
         if self.encrypt is None:
             raise ValueError("plaintext bits given but no encrypt callback")

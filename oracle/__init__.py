@@ -17,17 +17,27 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libtfhe_oracle.so"
-REF_DRIVER = HERE / "_ref" / "ref_driver"
+# Parameter flavour, fixed per process like the reference's compile-time switch (IYOKAN_80BIT_SECURITY): the environment
+# variable B200FHE_FLAVOUR ("" = 128-bit, "80" = 80-bit) is read once, at import, by this package and by iyokan_b200.lib.
+FLAVOUR = os.environ.get("B200FHE_FLAVOUR", "")
+if FLAVOUR not in ("", "80"):
+    raise ImportError(f"B200FHE_FLAVOUR must be '' (128-bit) or '80', not {FLAVOUR!r}")
+LIB_PATH = HERE / f"libtfhe_oracle{FLAVOUR}.so"
+REF_DRIVER = HERE / "_ref" / f"ref_driver{FLAVOUR}"
 IYOKAN_PACKET = HERE / "_ref" / "iyokan-packet"   # the reference's own packet tool, built unmodified
 REF_LINK_TEST = HERE / "_ref" / "b200_gate_test"  # tests/ref_link/b200_gate_test.cpp: TFHEpp types over the C ABI
 IYOKAN_REF = HERE / "_ref" / "iyokan"             # the reference's own iyokan (plain + tfhe on CPU), built unmodified
 IYOKAN_B200 = HERE / "_ref" / "iyokan-b200"       # iyokan_b200/host/iyokan_b200_main.cpp: the reference's loader + our engine
 B200_TEST0 = HERE / "_ref" / "b200_test0"         # the reference's src/test0.cpp templated tests on the B200 plugin (iyokan_b200.hpp)
 
-N0, N1, L, T = 636, 1024, 3, 7
-TLWE0, TLWE1, ROWS = N0 + 1, N1 + 1, 6
-MU0, MU1 = 1 << 13, 1 << 29
+if FLAVOUR == "80":   # TFHEpp include/params/CGGI16.hpp
+    N0, N1, L, T = 500, 1024, 2, 8
+    MU0, T0, S0 = 1 << 29, np.uint32, np.int32
+else:                 # TFHEpp include/params/128bit.hpp
+    N0, N1, L, T = 636, 1024, 3, 7
+    MU0, T0, S0 = 1 << 13, np.uint16, np.int16
+TLWE0, TLWE1, ROWS = N0 + 1, N1 + 1, 2 * L
+MU1 = 1 << 29
 
 OPS = {
     "AND": 0, "NAND": 1, "ANDNOT": 2, "OR": 3, "NOR": 4, "ORNOT": 5, "XOR": 6, "XNOR": 7,
@@ -65,7 +75,8 @@ def _optional(cmd) -> None:
 
 def build(force: bool = False) -> None:
     """Compile the C restatement (and the reference driver when the reference tree exists)."""
-    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < (HERE / "tfhe_oracle.c").stat().st_mtime:
+    libs = [HERE / "libtfhe_oracle.so", HERE / "libtfhe_oracle80.so"]
+    if force or not all(x.exists() for x in libs) or min(x.stat().st_mtime for x in libs) < (HERE / "tfhe_oracle.c").stat().st_mtime:
         subprocess.run(["make", "-C", str(HERE), "oracle"], check=True, capture_output=True)
     if Path("/root/reference/thirdparty/cuFHE/thirdparties/TFHEpp/include").is_dir():
         if (force or not REF_DRIVER.exists() or not IYOKAN_PACKET.exists()
@@ -118,18 +129,18 @@ class Keys:
     def load(d):
         d = Path(d)
         return Keys(
-            np.fromfile(d / "sk0.bin", dtype=np.uint16),
+            np.fromfile(d / "sk0.bin", dtype=T0),
             np.fromfile(d / "sk1.bin", dtype=np.uint32).astype(np.int32),
             np.fromfile(d / "bk.bin", dtype=np.uint32).reshape(N0, ROWS, 2, N1),
-            np.fromfile(d / "ksk.bin", dtype=np.uint16).reshape(N1, T, 3, TLWE0),
+            np.fromfile(d / "ksk.bin", dtype=T0).reshape(N1, T, 3, TLWE0),
         )
 
 
 def keygen(seed: int) -> Keys:
-    sk0 = np.empty(N0, np.uint16)
+    sk0 = np.empty(N0, T0)
     sk1 = np.empty(N1, np.int32)
     bk = np.empty((N0, ROWS, 2, N1), np.uint32)
-    ksk = np.empty((N1, T, 3, TLWE0), np.uint16)
+    ksk = np.empty((N1, T, 3, TLWE0), T0)
     lib().orc_keygen(ctypes.c_uint64(seed), _p(sk0), _p(sk1), _p(bk), _p(ksk))
     return Keys(sk0, sk1, bk, ksk)
 
@@ -145,21 +156,21 @@ def cached_keys(seed: int) -> Keys:
 
 def encrypt_bits(seed: int, keys: Keys, bits) -> np.ndarray:
     bits = np.ascontiguousarray(bits, dtype=np.uint8)
-    out = np.empty((bits.size, TLWE0), np.uint16)
+    out = np.empty((bits.size, TLWE0), T0)
     lib().orc_encrypt_bits(ctypes.c_uint64(seed), _p(keys.sk0), _p(bits), ctypes.c_size_t(bits.size), _p(out))
     return out
 
 
 def decrypt_bits(keys: Keys, c) -> np.ndarray:
-    c = np.ascontiguousarray(c, dtype=np.uint16).reshape(-1, TLWE0)
+    c = np.ascontiguousarray(c, dtype=T0).reshape(-1, TLWE0)
     bits = np.empty(c.shape[0], np.uint8)
     lib().orc_decrypt_bits(_p(keys.sk0), _p(c), ctypes.c_size_t(c.shape[0]), _p(bits))
     return bits
 
 
 def phase(keys: Keys, c) -> np.ndarray:
-    c = np.ascontiguousarray(c, dtype=np.uint16).reshape(-1, TLWE0)
-    ph = np.empty(c.shape[0], np.int16)
+    c = np.ascontiguousarray(c, dtype=T0).reshape(-1, TLWE0)
+    ph = np.empty(c.shape[0], S0)
     lib().orc_phase(_p(keys.sk0), _p(c), ctypes.c_size_t(c.shape[0]), _p(ph))
     return ph
 
@@ -177,9 +188,9 @@ def gate_batch(keys: Keys, ops, in0, in1=None, in2=None, nthreads: int = 0) -> n
     arrs = []
     for a in (in0, in1, in2):
         if a is None:
-            a = np.zeros((n, TLWE0), np.uint16)
-        arrs.append(np.ascontiguousarray(a, dtype=np.uint16).reshape(n, TLWE0))
-    out = np.empty((n, TLWE0), np.uint16)
+            a = np.zeros((n, TLWE0), T0)
+        arrs.append(np.ascontiguousarray(a, dtype=T0).reshape(n, TLWE0))
+    out = np.empty((n, TLWE0), T0)
     lib().orc_gate_batch(_p(ops), _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(out), ctypes.c_size_t(n),
                          _p(keys.bk), _p(keys.ksk), ctypes.c_int(nthreads))
     return out
@@ -207,7 +218,7 @@ def cmux_step(acc, trgsw, abar: int) -> np.ndarray:
 
 
 def mod_switch(c):
-    c = np.ascontiguousarray(c, dtype=np.uint16)
+    c = np.ascontiguousarray(c, dtype=T0)
     abar = np.empty(N0, np.uint32)
     bbar = ctypes.c_uint32(0)
     lib().orc_mod_switch(_p(c), _p(abar), ctypes.byref(bbar))
@@ -215,14 +226,14 @@ def mod_switch(c):
 
 
 def blind_rotate(keys: Keys, c) -> np.ndarray:
-    c = np.ascontiguousarray(c, dtype=np.uint16)
+    c = np.ascontiguousarray(c, dtype=T0)
     acc = np.empty((2, N1), np.uint32)
     lib().orc_blind_rotate(_p(c), _p(keys.bk), _p(acc))
     return acc
 
 
 def bootstrap_to_lvl1(keys: Keys, c) -> np.ndarray:
-    c = np.ascontiguousarray(c, dtype=np.uint16).reshape(-1, TLWE0)
+    c = np.ascontiguousarray(c, dtype=T0).reshape(-1, TLWE0)
     out = np.empty((c.shape[0], TLWE1), np.uint32)
     for i in range(c.shape[0]):
         lib().orc_bootstrap_to_lvl1(_p(c[i]), _p(keys.bk), _p(out[i]))
@@ -231,7 +242,7 @@ def bootstrap_to_lvl1(keys: Keys, c) -> np.ndarray:
 
 def keyswitch(keys: Keys, u) -> np.ndarray:
     u = np.ascontiguousarray(u, dtype=np.uint32).reshape(-1, TLWE1)
-    out = np.empty((u.shape[0], TLWE0), np.uint16)
+    out = np.empty((u.shape[0], TLWE0), T0)
     for i in range(u.shape[0]):
         lib().orc_keyswitch(_p(u[i]), _p(keys.ksk), _p(out[i]))
     return out

@@ -36,10 +36,18 @@
 
 using namespace TFHEpp;
 using TLWE0 = TLWE<lvl0param>;
+using T0 = lvl0param::T;                       // uint16_t (128-bit set), uint32_t (80-bit set, -DUSE_80BIT_SECURITY)
+constexpr size_t TLWE0_LEN = lvl0param::n + 1;
 
+#ifdef USE_80BIT_SECURITY
+static_assert(sizeof(TLWE0) == 501 * 4, "80-bit parameter build expected (params/CGGI16.hpp)");
+static_assert(sizeof(BootstrappingKey<lvl01param>) == 500ull * 4 * 2 * 1024 * 4);
+static_assert(sizeof(KeySwitchingKey<lvl10param>) == 1024ull * 8 * 3 * 501 * 4);
+#else
 static_assert(sizeof(TLWE0) == 637 * 2, "128-bit parameter build expected");
 static_assert(sizeof(BootstrappingKey<lvl01param>) == 636ull * 6 * 2 * 1024 * 4);
 static_assert(sizeof(KeySwitchingKey<lvl10param>) == 1024ull * 7 * 3 * 637 * 2);
+#endif
 
 // Opcode numbering shared with include/b200fhe.h.
 enum Op : uint8_t {
@@ -77,7 +85,7 @@ static void spit(const std::string& path, const void* p, size_t bytes)
 
 static Key<lvl0param> load_sk0(const std::string& dir)
 {
-    auto v = slurp<uint16_t>(dir + "/sk0.bin");
+    auto v = slurp<T0>(dir + "/sk0.bin");
     if (v.size() != lvl0param::n) die("sk0.bin size");
     Key<lvl0param> k;
     std::memcpy(k.data(), v.data(), sizeof(k));
@@ -94,9 +102,9 @@ static void load_evalkey(const std::string& dir, EvalKey& ek)
         std::memcpy(ek.bklvl01.get(), v.data(), v.size() * 4);
     }
     {
-        auto v = slurp<uint16_t>(dir + "/ksk.bin");
-        if (v.size() * 2 != sizeof(KeySwitchingKey<lvl10param>)) die("ksk.bin size");
-        std::memcpy(ek.iksklvl10.get(), v.data(), v.size() * 2);
+        auto v = slurp<T0>(dir + "/ksk.bin");
+        if (v.size() * sizeof(T0) != sizeof(KeySwitchingKey<lvl10param>)) die("ksk.bin size");
+        std::memcpy(ek.iksklvl10.get(), v.data(), v.size() * sizeof(T0));
     }
     ek.emplacebk2bkfft<lvl01param>();  // FFT form derived from the same raw key
 }
@@ -129,18 +137,69 @@ static int cmd_encrypt(const std::string& dir, const std::string& bits, const st
 static int cmd_decrypt(const std::string& dir, const std::string& in, const std::string& out)
 {
     auto key = load_sk0(dir);
-    auto raw = slurp<uint16_t>(in);
+    auto raw = slurp<T0>(in);
     size_t n = raw.size() / 637;
     std::vector<uint8_t> p(n);
     for (size_t i = 0; i < n; i++) {
         TLWE0 c;
-        std::memcpy(c.data(), raw.data() + i * 637, sizeof(c));
+        std::memcpy(c.data(), raw.data() + i * TLWE0_LEN, sizeof(c));
         p[i] = tlweSymDecrypt<lvl0param>(c, key);
     }
     spit(out, p.data(), n);
     return 0;
 }
 
+#ifdef USE_80BIT_SECURITY
+// The pinned TFHEpp's br->iks HomGate overload (gate.hpp:8-18) does not compile with a 32-bit lvl0 torus: it takes the
+// offset as a signed template argument and gate.hpp:82,99,116,167,184 pass -mu, which narrows.
+// The 80-bit driver therefore forms the linear combination itself - the three lines of HomGate, with the
+// (casign, cbsign, offset) table of gate.hpp:59-230 - and calls the reference's own GateBootstrapping
+// (gatebootstrapping.hpp:241-250: BlindRotate + SampleExtractIndex + IdentityKeySwitch), which is everything else.
+static void hom_gate80(TLWE0& r, const TLWE0& a, const TLWE0& b, int sa, int sb, int off, const EvalKey& ek)
+{
+    TLWE0 c;
+    for (size_t i = 0; i <= lvl0param::n; i++) c[i] = (T0)((uint32_t)sa * a[i] + (uint32_t)sb * b[i]);
+    c[lvl0param::n] += (T0)((uint32_t)off * lvl0param::μ);
+    GateBootstrapping<lvl01param, lvl1param::μ, lvl10param>(r, c, ek);
+}
+static void run_gate(uint8_t op, TLWE0& r, const TLWE0& a, const TLWE0& b, const TLWE0& c,
+                     const EvalKey& ek)
+{
+    switch (op) {
+    case OP_NAND:   hom_gate80(r, a, b, -1, -1, +1, ek); break;  // gate.hpp:65
+    case OP_NOR:    hom_gate80(r, a, b, -1, -1, -1, ek); break;  // :82
+    case OP_XNOR:   hom_gate80(r, a, b, -2, -2, -2, ek); break;  // :99
+    case OP_AND:    hom_gate80(r, a, b, +1, +1, -1, ek); break;  // :116
+    case OP_OR:     hom_gate80(r, a, b, +1, +1, +1, ek); break;  // :133
+    case OP_XOR:    hom_gate80(r, a, b, +2, +2, +2, ek); break;  // :150
+    case OP_ANDNY:  hom_gate80(r, a, b, -1, +1, -1, ek); break;  // :167
+    case OP_ANDNOT: hom_gate80(r, a, b, +1, -1, -1, ek); break;  // :184 HomANDYN
+    case OP_ORNY:   hom_gate80(r, a, b, -1, +1, +1, ek); break;  // :201
+    case OP_ORNOT:  hom_gate80(r, a, b, +1, -1, +1, ek); break;  // :218 HomORYN
+    case OP_MUX: {  // HomMUX<lvl0param>, gate.hpp:231-262 (lvl0 branch), cs = c, c1 = b, c0 = a
+        TLWE0 t1, t0;
+        for (size_t i = 0; i <= lvl0param::n; i++) {
+            t1[i] = c[i] + b[i];
+            t0[i] = (T0)(0u - c[i]) + a[i];
+        }
+        t1[lvl0param::n] -= lvl0param::μ;
+        t0[lvl0param::n] -= lvl0param::μ;
+        TLWE<lvl1param> u1, u0;
+        GateBootstrappingTLWE2TLWEFFT<lvl01param>(u1, t1, *ek.bkfftlvl01, μpolygen<lvl1param, lvl1param::μ>());
+        GateBootstrappingTLWE2TLWEFFT<lvl01param>(u0, t0, *ek.bkfftlvl01, μpolygen<lvl1param, lvl1param::μ>());
+        for (size_t i = 0; i <= lvl1param::n; i++) u1[i] += u0[i];
+        IdentityKeySwitch<lvl10param>(r, u1, *ek.iksklvl10);
+        r[lvl0param::n] += lvl0param::μ;
+        break;
+    }
+    case OP_NOT:    for (size_t i = 0; i <= lvl0param::n; i++) r[i] = (T0)(0u - a[i]); break;  // HomNOT, gate.hpp:47-51
+    case OP_COPY:   r = a; break;
+    case OP_CONST0: r = {}; r[lvl0param::n] = (T0)(0u - lvl0param::μ); break;                  // gate.hpp:32-44
+    case OP_CONST1: r = {}; r[lvl0param::n] = lvl0param::μ; break;
+    default: die("bad opcode");
+    }
+}
+#else
 static void run_gate(uint8_t op, TLWE0& r, const TLWE0& a, const TLWE0& b, const TLWE0& c,
                      const EvalKey& ek)
 {
@@ -168,6 +227,8 @@ static void run_gate(uint8_t op, TLWE0& r, const TLWE0& a, const TLWE0& b, const
     }
 }
 
+#endif
+
 // gates DIR ops.bin in0.bin in1.bin in2.bin out.bin nthreads [repeat]
 // in*.bin are u16[count][637]; pass "-" for an unused operand.
 static int cmd_gates(int argc, char** argv)
@@ -179,8 +240,8 @@ static int cmd_gates(int argc, char** argv)
     auto load = [&](const char* p) {
         std::vector<TLWE0> v(n);
         if (std::strcmp(p, "-") != 0) {
-            auto raw = slurp<uint16_t>(p);
-            if (raw.size() != n * 637) die("operand size mismatch");
+            auto raw = slurp<T0>(p);
+            if (raw.size() != n * TLWE0_LEN) die("operand size mismatch");
             std::memcpy(v.data(), raw.data(), n * sizeof(TLWE0));
         }
         return v;
@@ -220,12 +281,12 @@ static int cmd_blindrotate(const std::string& dir, const std::string& in, const 
 {
     EvalKey ek;
     load_evalkey(dir, ek);
-    auto raw = slurp<uint16_t>(in);
-    size_t n = raw.size() / 637;
+    auto raw = slurp<T0>(in);
+    size_t n = raw.size() / TLWE0_LEN;
     std::vector<TLWE<lvl1param>> res(n);
     for (size_t i = 0; i < n; i++) {
         TLWE0 c;
-        std::memcpy(c.data(), raw.data() + i * 637, sizeof(c));
+        std::memcpy(c.data(), raw.data() + i * TLWE0_LEN, sizeof(c));
         GateBootstrappingTLWE2TLWEFFT<lvl01param>(res[i], c, *ek.bkfftlvl01,
                                                   μpolygen<lvl1param, lvl1param::μ>());
     }
@@ -237,9 +298,9 @@ static int cmd_blindrotate(const std::string& dir, const std::string& in, const 
 static int cmd_keyswitch(const std::string& dir, const std::string& in, const std::string& out)
 {
     auto ksk = std::make_unique_for_overwrite<KeySwitchingKey<lvl10param>>();
-    auto v = slurp<uint16_t>(dir + "/ksk.bin");
-    if (v.size() * 2 != sizeof(*ksk)) die("ksk.bin size");
-    std::memcpy(ksk.get(), v.data(), v.size() * 2);
+    auto v = slurp<T0>(dir + "/ksk.bin");
+    if (v.size() * sizeof(T0) != sizeof(*ksk)) die("ksk.bin size");
+    std::memcpy(ksk.get(), v.data(), v.size() * sizeof(T0));
     auto raw = slurp<uint32_t>(in);
     size_t n = raw.size() / 1025;
     std::vector<TLWE0> res(n);
@@ -291,7 +352,7 @@ static int cmd_cmuxstep(const std::string& tg, const std::string& accin, uint32_
 {
     auto t = slurp<uint32_t>(tg);
     auto a = slurp<uint32_t>(accin);
-    if (t.size() != 6 * 2 * 1024 || a.size() != 2 * 1024) die("cmuxstep sizes");
+    if (t.size() != 2 * lvl1param::l * 2 * 1024 || a.size() != 2 * 1024) die("cmuxstep sizes");
     TRGSW<lvl1param> trgsw;
     std::memcpy(trgsw.data(), t.data(), sizeof(trgsw));
     BootstrappingKeyElementFFT<lvl01param> el;

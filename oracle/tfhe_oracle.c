@@ -51,11 +51,16 @@ static inline int32_t rng_gauss(rng_t *r, int64_t sigma_q16)
         s += (int64_t)(uint32_t)v + (int64_t)(uint32_t)(v >> 32);
     }
     s -= 6ll << 32;                                   /* stdev(s) = 2^32 */
-    return (int32_t)((s * sigma_q16 + (1ll << 47)) >> 48);
+    return (int32_t)(((__int128)s * sigma_q16 + ((__int128)1 << 47)) >> 48);
 }
-/* lvl0param::alpha * 2^16 and lvl1param::alpha * 2^32 (params/128bit.hpp:16,38) in Q16 */
+/* lvl0param::alpha * 2^w0 and lvl1param::alpha * 2^32 in Q16 (params/128bit.hpp:16,38; params/CGGI16.hpp:15,35) */
+#ifdef ORC_80BIT
+#define SIGMA0_Q16 ((int64_t)(2.44e-5 * 4294967296.0 * 65536.0 + 0.5))
+#define SIGMA1_Q16 ((int64_t)(3.73e-9 * 4294967296.0 * 65536.0 + 0.5))
+#else
 #define SIGMA0_Q16 ((int64_t)(0.0000925119974676756 * 65536.0 * 65536.0 + 0.5))
 #define SIGMA1_Q16 ((int64_t)(128.0 * 65536.0))
+#endif
 
 /* ------------------------------------------------------------------ */
 /* primitives                                                         */
@@ -146,16 +151,17 @@ void orc_cmux_step(uint32_t *acc, const uint32_t *trgsw, uint32_t abar)
 }
 
 /* TFHEPP/include/gatebootstrapping.hpp:26-30 (b, no rounding) and :58-65 (a, rounded).
- * uint16 operands are promoted to int in the reference, so abar may be 2N (== 0 mod 2N). */
-void orc_mod_switch(const uint16_t *c, uint32_t *abar, uint32_t *bbar)
+ * uint16 operands are promoted to int in the reference, so abar may be 2N (== 0 mod 2N); with the 32-bit lvl0 torus
+ * of the 80-bit set the sum is formed in uint32 and wraps, so abar stays below 2N. */
+void orc_mod_switch(const orc_t0 *c, uint32_t *abar, uint32_t *bbar)
 {
-    const int shift = 16 - 1 - ORC_NBIT;          /* digits - 1 - nbit = 5 */
+    const int shift = ORC_T0_BITS - 1 - ORC_NBIT;          /* digits - 1 - nbit = 5 (21) */
     *bbar = 2 * N1 - ((uint32_t)c[N0] >> shift);
-    for (int i = 0; i < N0; i++) abar[i] = ((uint32_t)c[i] + (1u << (shift - 1))) >> shift;
+    for (int i = 0; i < N0; i++) abar[i] = (uint32_t)((uint32_t)c[i] + (1u << (shift - 1))) >> shift;
 }
 
 /* TFHEPP/include/gatebootstrapping.hpp:19-71 BlindRotate with testvector mu_polygen (:233-239) */
-void orc_blind_rotate(const uint16_t *c, const uint32_t *bk, uint32_t *acc)
+void orc_blind_rotate(const orc_t0 *c, const uint32_t *bk, uint32_t *acc)
 {
     uint32_t abar[N0], bbar, tv[N1];
     orc_mod_switch(c, abar, &bbar);
@@ -177,26 +183,30 @@ void orc_sample_extract0(const uint32_t *acc, uint32_t *tlwe1)
 }
 
 /* TFHEPP/include/keyswitch.hpp:11-52 IdentityKeySwitch<lvl10param> */
-void orc_keyswitch(const uint32_t *tlwe1, const uint16_t *ksk, uint16_t *out)
+void orc_keyswitch(const uint32_t *tlwe1, const orc_t0 *ksk, orc_t0 *out)
 {
     const uint32_t prec_offset = 1u << (32 - (1 + ORC_BASEBIT * ORC_T));
     const uint32_t mask = (1u << ORC_BASEBIT) - 1;
-    uint16_t res[ORC_TLWE0];
+    orc_t0 res[ORC_TLWE0];
     memset(res, 0, sizeof(res));
-    res[N0] = (uint16_t)((tlwe1[N1] + (1u << 15)) >> 16);
+#if ORC_T0_BITS == 32
+    res[N0] = tlwe1[N1];                                             /* same width: plain copy, :27-29 */
+#else
+    res[N0] = (orc_t0)((tlwe1[N1] + (1u << 15)) >> 16);              /* 32 -> 16 bit rounding, :30-34 */
+#endif
     for (int i = 0; i < N1; i++) {
         const uint32_t aibar = tlwe1[i] + prec_offset;
         for (int j = 0; j < ORC_T; j++) {
             const uint32_t aij = (aibar >> (32 - (j + 1) * ORC_BASEBIT)) & mask;
             if (aij == 0) continue;
-            const uint16_t *row = ksk + (((size_t)i * ORC_T + j) * 3 + (aij - 1)) * ORC_TLWE0;
+            const orc_t0 *row = ksk + (((size_t)i * ORC_T + j) * 3 + (aij - 1)) * ORC_TLWE0;
             for (int k = 0; k <= N0; k++) res[k] -= row[k];
         }
     }
     memcpy(out, res, sizeof(res));
 }
 
-void orc_bootstrap_to_lvl1(const uint16_t *c, const uint32_t *bk, uint32_t *tlwe1)
+void orc_bootstrap_to_lvl1(const orc_t0 *c, const uint32_t *bk, uint32_t *tlwe1)
 {
     uint32_t acc[2 * N1];
     orc_blind_rotate(c, bk, acc);
@@ -231,24 +241,24 @@ int orc_num_bootstraps(uint8_t op)
     return gate_table(op, &g) ? 1 : 0;
 }
 
-void orc_gate(uint8_t op, const uint16_t *in0, const uint16_t *in1, const uint16_t *in2,
-              uint16_t *out, const uint32_t *bk, const uint16_t *ksk)
+void orc_gate(uint8_t op, const orc_t0 *in0, const orc_t0 *in1, const orc_t0 *in2,
+              orc_t0 *out, const uint32_t *bk, const orc_t0 *ksk)
 {
     gate_coef g;
-    uint16_t c[ORC_TLWE0];
+    orc_t0 c[ORC_TLWE0];
     uint32_t u[ORC_TLWE1];
     if (gate_table(op, &g)) {
         /* HomGate, gate.hpp:8-18 (uint16 wrap) */
-        for (int i = 0; i <= N0; i++) c[i] = (uint16_t)(g.sa * in0[i] + g.sb * in1[i]);
-        c[N0] = (uint16_t)(c[N0] + g.off * (int)ORC_MU0);
+        for (int i = 0; i <= N0; i++) c[i] = (orc_t0)((uint32_t)g.sa * in0[i] + (uint32_t)g.sb * in1[i]);
+        c[N0] = (orc_t0)(c[N0] + (uint32_t)g.off * ORC_MU0);
         orc_bootstrap_to_lvl1(c, bk, u);
         orc_keyswitch(u, ksk, out);
     } else if (op == ORC_MUX) {
         /* HomMUX<lvl0param>, gate.hpp:231-262 with cs=in2, c1=in1, c0=in0 */
-        uint16_t c0[ORC_TLWE0];
+        orc_t0 c0[ORC_TLWE0];
         uint32_t u0[ORC_TLWE1];
-        for (int i = 0; i <= N0; i++) c[i] = (uint16_t)(in2[i] + in1[i]);
-        for (int i = 0; i <= N0; i++) c0[i] = (uint16_t)(-in2[i] + in0[i]);
+        for (int i = 0; i <= N0; i++) c[i] = (orc_t0)(in2[i] + in1[i]);
+        for (int i = 0; i <= N0; i++) c0[i] = (orc_t0)(0u - in2[i] + in0[i]);
         c[N0] -= ORC_MU0;
         c0[N0] -= ORC_MU0;
         orc_bootstrap_to_lvl1(c, bk, u);
@@ -257,19 +267,19 @@ void orc_gate(uint8_t op, const uint16_t *in0, const uint16_t *in1, const uint16
         orc_keyswitch(u0, ksk, out);
         out[N0] += ORC_MU0;
     } else if (op == ORC_NOT) {                                   /* gate.hpp:47-51 */
-        for (int i = 0; i <= N0; i++) out[i] = (uint16_t)(-in0[i]);
+        for (int i = 0; i <= N0; i++) out[i] = (orc_t0)(0u - in0[i]);
     } else if (op == ORC_COPY) {                                  /* gate.hpp:53-57 */
-        memmove(out, in0, ORC_TLWE0 * 2);
+        memmove(out, in0, ORC_TLWE0 * sizeof(orc_t0));
     } else if (op == ORC_CONST1 || op == ORC_CONST0) {            /* gate.hpp:32-44 */
-        memset(out, 0, ORC_TLWE0 * 2);
-        out[N0] = (op == ORC_CONST1) ? (uint16_t)ORC_MU0 : (uint16_t)(-(int)ORC_MU0);
+        memset(out, 0, ORC_TLWE0 * sizeof(orc_t0));
+        out[N0] = (op == ORC_CONST1) ? (orc_t0)ORC_MU0 : (orc_t0)(0u - ORC_MU0);
     } else {
         abort();
     }
 }
 
-void orc_gate_batch(const uint8_t *ops, const uint16_t *in0, const uint16_t *in1, const uint16_t *in2,
-                    uint16_t *out, size_t count, const uint32_t *bk, const uint16_t *ksk, int nthreads)
+void orc_gate_batch(const uint8_t *ops, const orc_t0 *in0, const orc_t0 *in1, const orc_t0 *in2,
+                    orc_t0 *out, size_t count, const uint32_t *bk, const orc_t0 *ksk, int nthreads)
 {
 #ifdef _OPENMP
     if (nthreads <= 0) nthreads = omp_get_max_threads();
@@ -289,47 +299,48 @@ void orc_gate_batch(const uint8_t *ops, const uint16_t *in0, const uint16_t *in1
 /* ------------------------------------------------------------------ */
 
 /* tlweSymEncrypt<lvl0param>, TFHEPP/include/tlwe.hpp:12-25 */
-static void tlwe0_encrypt(rng_t *r, uint16_t m, const uint16_t *sk0, uint16_t *out)
+static void tlwe0_encrypt(rng_t *r, orc_t0 m, const orc_t0 *sk0, orc_t0 *out)
 {
-    uint16_t b = (uint16_t)(m + (uint16_t)rng_gauss(r, SIGMA0_Q16));
-    for (int i = 0; i < N0; i += 4) {
+    orc_t0 b = (orc_t0)(m + (orc_t0)rng_gauss(r, SIGMA0_Q16));
+    const int per = 64 / ORC_T0_BITS;              /* uniform a_i: 4 (2) torus words per 64-bit draw */
+    for (int i = 0; i < N0; i += per) {
         uint64_t v = rng_next(r);
-        for (int j = 0; j < 4; j++) {
-            uint16_t a = (uint16_t)(v >> (16 * j));
+        for (int j = 0; j < per && i + j < N0; j++) {
+            orc_t0 a = (orc_t0)(v >> (ORC_T0_BITS * j));
             out[i + j] = a;
-            b = (uint16_t)(b + a * sk0[i + j]);
+            b = (orc_t0)(b + a * sk0[i + j]);
         }
     }
     out[N0] = b;
 }
 
-void orc_encrypt_bits(uint64_t seed, const uint16_t *sk0, const uint8_t *bits, size_t count,
-                      uint16_t *out)
+void orc_encrypt_bits(uint64_t seed, const orc_t0 *sk0, const uint8_t *bits, size_t count,
+                      orc_t0 *out)
 {
 #pragma omp parallel for
     for (long g = 0; g < (long)count; g++) {
         rng_t r = rng_fork(seed, (uint64_t)g);
         /* bootsSymEncrypt, tlwe.hpp:101-110: message = bit ? mu : -mu */
-        tlwe0_encrypt(&r, bits[g] ? (uint16_t)ORC_MU0 : (uint16_t)(-(int)ORC_MU0), sk0,
+        tlwe0_encrypt(&r, bits[g] ? (orc_t0)ORC_MU0 : (orc_t0)(0u - ORC_MU0), sk0,
                       out + (size_t)g * ORC_TLWE0);
     }
 }
 
 /* tlweSymDecrypt, tlwe.hpp:77-87: bit = (signed phase > 0) */
-void orc_phase(const uint16_t *sk0, const uint16_t *in, size_t count, int16_t *phase)
+void orc_phase(const orc_t0 *sk0, const orc_t0 *in, size_t count, orc_s0 *phase)
 {
     for (size_t g = 0; g < count; g++) {
-        const uint16_t *c = in + g * ORC_TLWE0;
-        uint16_t ph = c[N0];
-        for (int i = 0; i < N0; i++) ph = (uint16_t)(ph - c[i] * sk0[i]);
-        phase[g] = (int16_t)ph;
+        const orc_t0 *c = in + g * ORC_TLWE0;
+        orc_t0 ph = c[N0];
+        for (int i = 0; i < N0; i++) ph = (orc_t0)(ph - c[i] * sk0[i]);
+        phase[g] = (orc_s0)ph;
     }
 }
 
-void orc_decrypt_bits(const uint16_t *sk0, const uint16_t *in, size_t count, uint8_t *bits)
+void orc_decrypt_bits(const orc_t0 *sk0, const orc_t0 *in, size_t count, uint8_t *bits)
 {
     for (size_t g = 0; g < count; g++) {
-        int16_t ph;
+        orc_s0 ph;
         orc_phase(sk0, in + g * ORC_TLWE0, 1, &ph);
         bits[g] = ph > 0;
     }
@@ -348,10 +359,10 @@ void orc_phase1(const int32_t *sk1, const uint32_t *tlwe1, size_t count, int32_t
 /* keys: lweKey ctor (TFHEPP/src/key.cpp:5-16; lvl0 binary, lvl1 ternary),
  * bkgen<lvl01param> (cloudkey.hpp:18-52) -> trgswSymEncrypt (trgsw.hpp:301-318, hgen :231-244)
  *   -> trlweSymEncryptZero (trlwe.hpp:7-24), ikskgen<lvl10param> (cloudkey.hpp:188-203). */
-void orc_keygen(uint64_t seed, uint16_t *sk0, int32_t *sk1, uint32_t *bk, uint16_t *ksk)
+void orc_keygen(uint64_t seed, orc_t0 *sk0, int32_t *sk1, uint32_t *bk, orc_t0 *ksk)
 {
     rng_t r = rng_fork(seed, 0xA11CE);
-    for (int i = 0; i < N0; i++) sk0[i] = (uint16_t)(rng_next(&r) & 1);
+    for (int i = 0; i < N0; i++) sk0[i] = (orc_t0)(rng_next(&r) & 1);
     for (int i = 0; i < N1; i++) sk1[i] = (int32_t)(rng_next(&r) % 3) - 1;
 
 #pragma omp parallel for schedule(dynamic, 4)
@@ -385,8 +396,8 @@ void orc_keygen(uint64_t seed, uint16_t *sk0, int32_t *sk1, uint32_t *bk, uint16
         rng_t ri = rng_fork(seed, 0x20000u + (uint64_t)i);
         for (int j = 0; j < ORC_T; j++)
             for (uint32_t k = 0; k < 3; k++) {
-                /* domainkey[i]*(k+1)*2^(16-(j+1)*basebit), truncated to the uint16 torus */
-                uint16_t m = (uint16_t)((uint32_t)sk1[i] * (k + 1) * (1u << (16 - (j + 1) * ORC_BASEBIT)));
+                /* domainkey[i]*(k+1)*2^(w0-(j+1)*basebit), truncated to the lvl0 torus */
+                orc_t0 m = (orc_t0)((uint32_t)sk1[i] * (k + 1) * (1u << (ORC_T0_BITS - (j + 1) * ORC_BASEBIT)));
                 tlwe0_encrypt(&ri, m, sk0, ksk + (((size_t)i * ORC_T + j) * 3 + k) * ORC_TLWE0);
             }
     }

@@ -1,7 +1,8 @@
 """Generate tests/golden/tfhepp_golden.npz from the UNMODIFIED reference (oracle/_ref/ref_driver).
 
 Run in the build container (needs /root/reference to have been compiled by `make -C oracle ref`):
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py                        # 128-bit parameters -> tfhepp_golden.npz
+    B200FHE_FLAVOUR=80 python tests/golden/make_golden.py     # 80-bit parameters (ref_driver80) -> tfhepp_golden80.npz
 The keys are produced by the oracle's deterministic integer-only key generator from KEY_SEED, so
 the tests can regenerate exactly the same key material anywhere; only the reference's OUTPUTS on
 those keys are stored.  A SHA-256 of the key arrays guards that assumption.
@@ -33,9 +34,10 @@ def main():
         # Decomposition<lvl1param> (trgsw.hpp:62-78), exact
         p = rng.integers(0, 2**32, (4, 1024), dtype=np.uint32)
         p[0, :8] = [0, 1, 2**31, 2**32 - 1, 2**26, 2**26 - 1, 2**13, 2**13 - 1]
+        p[0, 8:12] = [2**22, 2**22 - 1, 2**11, 2**11 - 1]
         p.tofile(d / "p.bin")
         O.ref("decompose", d / "p.bin", d / "dec.bin")
-        g["decompose_in"], g["decompose_out"] = p, np.fromfile(d / "dec.bin", dtype=np.int32).reshape(4, 3, 1024)
+        g["decompose_in"], g["decompose_out"] = p, np.fromfile(d / "dec.bin", dtype=np.int32).reshape(4, O.L, 1024)
         # PolynomialMulByXai / MulByXaiMinusOne (utils.hpp:113-144), exact
         q = rng.integers(0, 2**32, (8, 1024), dtype=np.uint32)
         a = np.array([0, 1, 5, 1023, 1024, 1025, 2047, 2048], dtype=np.uint32)
@@ -63,10 +65,10 @@ def main():
         O.ref("gates", d, d / "ops.bin", d / "ca.bin", d / "cb.bin", d / "cc.bin", d / "go.bin", 8)
         g["gate_ops"], g["gate_pa"], g["gate_pb"], g["gate_pc"] = ops, pa, pb, pc
         g["gate_enc_seeds"] = np.array([101, 102, 103], dtype=np.uint64)
-        g["gate_out_tfhepp"] = np.fromfile(d / "go.bin", dtype=np.uint16).reshape(n, 637)
+        g["gate_out_tfhepp"] = np.fromfile(d / "go.bin", dtype=O.T0).reshape(n, O.TLWE0)
         # blind rotation + extraction (gatebootstrapping.hpp:188-197): lvl1 TLWE of the reference
-        c = (-ca[:4].astype(np.int32) - cb[:4].astype(np.int32)).astype(np.uint16)
-        c[:, 636] += np.uint16(1 << 13)
+        c = (-ca[:4].astype(np.int64) - cb[:4].astype(np.int64)).astype(O.T0)
+        c[:, O.N0] += O.T0(O.MU0)
         c.tofile(d / "rot.bin")
         O.ref("blindrotate", d, d / "rot.bin", d / "rot_out.bin")
         g["br_in"] = c
@@ -75,8 +77,8 @@ def main():
         u = O.bootstrap_to_lvl1(keys, c)
         u.tofile(d / "ks_in.bin")
         O.ref("keyswitch", d, d / "ks_in.bin", d / "ks_out.bin")
-        g["ks_in"], g["ks_out_tfhepp"] = u, np.fromfile(d / "ks_out.bin", dtype=np.uint16).reshape(4, 637)
-    out = Path(__file__).with_name("tfhepp_golden.npz")
+        g["ks_in"], g["ks_out_tfhepp"] = u, np.fromfile(d / "ks_out.bin", dtype=O.T0).reshape(4, O.TLWE0)
+    out = Path(__file__).with_name(f"tfhepp_golden{O.FLAVOUR}.npz")
     np.savez_compressed(out, **g)
     print("wrote", out, out.stat().st_size, "bytes")
 

@@ -10,18 +10,23 @@
 #include <cstring>
 #include <vector>
 
+#ifndef B200FHE_80BIT
 #include "../../iyokan_b200/csrc/br4_phases.h"
 #include "../../iyokan_b200/csrc/br6_phases.h"
 #include "../../iyokan_b200/csrc/br7_phases.h"
+#endif
 #include "../../iyokan_b200/csrc/br_phases.h"
+#include "../../iyokan_b200/csrc/brg_phases.h"
 #include "../../iyokan_b200/csrc/gate_jobs.h"
 #include "../../iyokan_b200/csrc/ks_phases.h"
 
 using namespace b200;
 
 static NttTables g_tab;
+#ifndef B200FHE_80BIT
 static BlockTw g_btw;
 static Block8Tw g_b8tw;
+#endif
 static bool g_init = false;
 
 // Thread-order control: every phase function is claimed to be free of intra-phase cross-thread communication, so
@@ -35,8 +40,10 @@ extern "C" void sim_init()
 {
     if (!g_init) {
         ntt_tables_init(g_tab);
+#ifndef B200FHE_80BIT
         block_tw_init(g_tab, g_btw);
         block8_tw_init(g_tab, g_b8tw);
+#endif
         g_init = true;
     }
 }
@@ -116,15 +123,85 @@ extern "C" void sim_bk_prepare(const uint32_t* bk_raw, uint32_t* bk_ntt, int n_i
                 for (int l = 0; l < LIMBS; l++) {
                     const uint32_t* raw = bk_raw + ((size_t)(i * ROWS + r) * 2 + q) * N1;
                     uint32_t* out = bk_ntt + ((size_t)(i * BK_COLS + q * LIMBS + l) * ROWS + r) * N1;
-                    for (int lane = 0; lane < 32; lane++) bk_prep_a(raw, l, lane, tile.data());
+                    for (int lane = 0; lane < 32; lane++) brg_bk_prep_a(raw, l, lane, tile.data());
                     for (int lane = 0; lane < 32; lane++) bk_prep_b(tile.data(), g_tab.tw2f, g_tab.bk_scale, lane, out);
                 }
     }
 }
 
+// ---- variant 1: generic shape (brg_kernel), both flavours ----
+template <int G>
+static void sim_brg_cta(const BrJob* jobs, int njobs, int cta, const torus0_t* arena, const uint32_t* bk_ntt,
+                        uint32_t* ubuf, int n_iter)
+{
+    constexpr int T = 64 * G, W = 2 * G;
+    std::vector<uint8_t> smem(BrgSmem<G>::BYTES + 16);
+    BrgSmem<G> sm;
+    sm.carve(smem.data());
+    std::memcpy(sm.tw2f, g_tab.tw2f, sizeof(g_tab.tw2f));
+    std::memcpy(sm.tw2i, g_tab.tw2i, sizeof(g_tab.tw2i));
+    struct Regs {
+        uint32_t accr[32], dreg[32], sum[32];
+    };
+    std::vector<Regs> regs(T);
+    auto jobof = [&](int g) {
+        int j = cta * G + g;
+        return j < njobs ? j : njobs - 1;
+    };
+    for (int w = 0; w < W; w++)
+        for (int lane = 0; lane < 32; lane++)
+            brg_prologue<G>(sm, jobs[jobof(w >> 1)], arena, w >> 1, w & 1, lane, regs[w * 32 + lane].accr);
+    for (int i = 0; i < n_iter; i++) {
+        for (int ww = 0; ww < W; ww++) {
+            const int w = ord(ww, W), g = w >> 1, q = w & 1;
+            for (int l = 0; l < 32; l++) {
+                Regs& r = regs[w * 32 + ord(l, 32)];
+                brg_rotate_diff<G>(sm, i, g, q, ord(l, 32), r.accr, r.dreg);
+            }
+            for (int d = 0; d < GL; d++) {
+                for (int l = 0; l < 32; l++) brg_fwd_a<G>(sm, g, q, ord(l, 32), d, regs[w * 32 + ord(l, 32)].dreg);
+                for (int l = 0; l < 32; l++) brg_fwd_b<G>(sm, g, q, ord(l, 32), d);
+            }
+        }
+        const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
+        for (int t = 0; t < T; t++) brg_pointwise<G>(sm, bk_i, ord(t, T));
+        for (int ww = 0; ww < W; ww++) {
+            const int w = ord(ww, W), g = w >> 1, q = w & 1;
+            for (int lm = 0; lm < LIMBS; lm++) {
+                for (int l = 0; l < 32; l++) brg_inv_a<G>(sm, g, q, ord(l, 32), lm);
+                for (int l = 0; l < 32; l++) brg_inv_b<G>(sm, g, q, ord(l, 32), lm, regs[w * 32 + ord(l, 32)].sum);
+            }
+            for (int l = 0; l < 32; l++) {
+                Regs& r = regs[w * 32 + ord(l, 32)];
+                brg_acc_update<G>(sm, g, q, ord(l, 32), r.sum, r.accr);
+            }
+        }
+    }
+    for (int w = 0; w < W; w++) {
+        const int g = w >> 1, q = w & 1;
+        if (cta * G + g >= njobs) continue;
+        for (int lane = 0; lane < 32; lane++) brg_epilogue<G>(sm, g, q, lane, ubuf + (size_t)(cta * G + g) * U_STRIDE);
+    }
+}
+
+extern "C" void sim_blind_rotate1(int G, const void* jobs_raw, int njobs, const torus0_t* arena, const uint32_t* bk_ntt,
+                                  uint32_t* ubuf, int n_iter)
+{
+    sim_init();
+    const BrJob* jobs = reinterpret_cast<const BrJob*>(jobs_raw);
+    const int ncta = (njobs + G - 1) / G;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int cta = 0; cta < ncta; cta++) {
+        if (G == 2) sim_brg_cta<2>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
+        else if (G == 4) sim_brg_cta<4>(jobs, njobs, cta, arena, bk_ntt, ubuf, n_iter);
+        else std::abort();
+    }
+}
+
+#ifndef B200FHE_80BIT
 // ---- variant 3: interleaved transforms (br3_kernel) ----
 template <int G>
-static void sim_br3_cta(const BrJob* jobs, int njobs, int cta, const uint16_t* arena, const uint32_t* bk_ntt,
+static void sim_br3_cta(const BrJob* jobs, int njobs, int cta, const torus0_t* arena, const uint32_t* bk_ntt,
                         uint32_t* ubuf, int n_iter)
 {
     constexpr int T = 64 * G, W = 2 * G;
@@ -181,7 +258,7 @@ static void sim_br3_cta(const BrJob* jobs, int njobs, int cta, const uint16_t* a
     }
 }
 
-extern "C" void sim_blind_rotate3(int G, const void* jobs_raw, int njobs, const uint16_t* arena,
+extern "C" void sim_blind_rotate3(int G, const void* jobs_raw, int njobs, const torus0_t* arena,
                                   const uint32_t* bk_ntt, uint32_t* ubuf, int n_iter)
 {
     sim_init();
@@ -198,7 +275,7 @@ extern "C" void sim_blind_rotate3(int G, const void* jobs_raw, int njobs, const 
 
 // ---- variant 7: 16-warp throughput shape on swizzled tiles (br7_kernel) ----
 template <int G, int J>
-static void sim_br7_cta(const BrJob* jobs, int njobs, int cta, const uint16_t* arena, const uint32_t* bk_ntt,
+static void sim_br7_cta(const BrJob* jobs, int njobs, int cta, const torus0_t* arena, const uint32_t* bk_ntt,
                         uint32_t* ubuf, int n_iter)
 {
     constexpr int T = 64 * G, W = 2 * G;
@@ -256,7 +333,7 @@ static void sim_br7_cta(const BrJob* jobs, int njobs, int cta, const uint16_t* a
     }
 }
 
-extern "C" void sim_blind_rotate7(int G, const void* jobs_raw, int njobs, const uint16_t* arena,
+extern "C" void sim_blind_rotate7(int G, const void* jobs_raw, int njobs, const torus0_t* arena,
                                   const uint32_t* bk_ntt, uint32_t* ubuf, int n_iter)
 {
     sim_init();
@@ -322,7 +399,7 @@ extern "C" void sim_warp_inverse(const uint32_t* in, uint32_t* out)
     warp_inverse(in, out);
 }
 
-static void sim_br4_cta(const BrJob* jobs, int job, const uint16_t* arena, const uint32_t* bk_ntt, uint32_t* ubuf,
+static void sim_br4_cta(const BrJob* jobs, int job, const torus0_t* arena, const uint32_t* bk_ntt, uint32_t* ubuf,
                         int n_iter)
 {
     std::vector<uint8_t> smem(Br4Smem::BYTES + 128);
@@ -353,7 +430,7 @@ static void sim_br4_cta(const BrJob* jobs, int job, const uint16_t* arena, const
     for (int tid = 0; tid < BR4_THREADS; tid++) br4_epilogue(sm, tid, ubuf + (size_t)job * U_STRIDE);
 }
 
-extern "C" void sim_blind_rotate4(const void* jobs_raw, int njobs, const uint16_t* arena, const uint32_t* bk_ntt,
+extern "C" void sim_blind_rotate4(const void* jobs_raw, int njobs, const torus0_t* arena, const uint32_t* bk_ntt,
                                   uint32_t* ubuf, int n_iter)
 {
     sim_init();
@@ -395,7 +472,7 @@ extern "C" void sim_block8_inverse(const uint32_t* in, uint32_t* out)
     }
 }
 
-static void sim_br6_cluster(const BrJob* jobs, int job, const uint16_t* arena, const uint32_t* bk_ntt, uint32_t* ubuf,
+static void sim_br6_cluster(const BrJob* jobs, int job, const torus0_t* arena, const uint32_t* bk_ntt, uint32_t* ubuf,
                             int n_iter)
 {
     std::vector<uint8_t> smem[2] = {std::vector<uint8_t>(Br6Smem::BYTES + 128), std::vector<uint8_t>(Br6Smem::BYTES + 128)};
@@ -439,7 +516,7 @@ static void sim_br6_cluster(const BrJob* jobs, int job, const uint16_t* arena, c
         for (int tid = 0; tid < BR6_THREADS; tid++) br6_epilogue(sm[q], q, tid, ubuf + (size_t)job * U_STRIDE);
 }
 
-extern "C" void sim_blind_rotate6(const void* jobs_raw, int njobs, const uint16_t* arena, const uint32_t* bk_ntt,
+extern "C" void sim_blind_rotate6(const void* jobs_raw, int njobs, const torus0_t* arena, const uint32_t* bk_ntt,
                                   uint32_t* ubuf, int n_iter)
 {
     sim_init();
@@ -450,9 +527,11 @@ extern "C" void sim_blind_rotate6(const void* jobs_raw, int njobs, const uint16_
 
 
 
+#endif  // !B200FHE_80BIT
+
 // ksk_dev: uint16 [1024][7][3][640]; jobs: packed KsJob (16 bytes each)
-extern "C" void sim_keyswitch(const void* jobs_raw, int njobs, const uint32_t* ubuf, const uint16_t* ksk_dev,
-                              uint16_t* arena)
+extern "C" void sim_keyswitch(const void* jobs_raw, int njobs, const uint32_t* ubuf, const torus0_t* ksk_dev,
+                              torus0_t* arena)
 {
     const KsJob* jobs = reinterpret_cast<const KsJob*>(jobs_raw);
 #pragma omp parallel for schedule(dynamic, 1)
@@ -475,8 +554,8 @@ extern "C" void sim_keyswitch(const void* jobs_raw, int njobs, const uint32_t* u
 }
 
 // narrow-frontier path: KS_SPLIT CTAs per switch (ks_split_kernel) + ks_combine_kernel
-extern "C" void sim_keyswitch_split(const void* jobs_raw, int njobs, const uint32_t* ubuf, const uint16_t* ksk_dev,
-                                    uint16_t* arena)
+extern "C" void sim_keyswitch_split(const void* jobs_raw, int njobs, const uint32_t* ubuf, const torus0_t* ksk_dev,
+                                    torus0_t* arena)
 {
     const KsJob* jobs = reinterpret_cast<const KsJob*>(jobs_raw);
     constexpr int SPAN = N1 / KS_SPLIT;
@@ -511,7 +590,7 @@ extern "C" void sim_keyswitch_split(const void* jobs_raw, int njobs, const uint3
     }
 }
 
-extern "C" void sim_unary(const void* jobs_raw, int njobs, uint16_t* arena)
+extern "C" void sim_unary(const void* jobs_raw, int njobs, torus0_t* arena)
 {
     const UnaryJob* jobs = reinterpret_cast<const UnaryJob*>(jobs_raw);
     for (int n = 0; n < njobs; n++) {
@@ -524,8 +603,8 @@ extern "C" void sim_unary(const void* jobs_raw, int njobs, uint16_t* arena)
 // Whole gate frontier exactly as b200fhe_gate_batch runs it: job building, unary gather/scatter,
 // blind rotations, key switches.  Returns 0, or -1 with *err set.
 extern "C" int sim_gate_batch(int G, const uint8_t* opcode, const uint32_t* in0, const uint32_t* in1,
-                              const uint32_t* in2, const uint32_t* out, size_t n, uint16_t* arena, size_t n_slots,
-                              const uint32_t* bk_ntt, const uint16_t* ksk_dev, const char** err)
+                              const uint32_t* in2, const uint32_t* out, size_t n, torus0_t* arena, size_t n_slots,
+                              const uint32_t* bk_ntt, const torus0_t* ksk_dev, const char** err)
 {
     sim_init();
     std::vector<BrJob> br(2 * n + 1);
@@ -546,8 +625,12 @@ extern "C" int sim_gate_batch(int G, const uint8_t* opcode, const uint32_t* in0,
     }
     if (cnt.nbr) {
         std::vector<uint32_t> ubuf(cnt.nbr * (size_t)U_STRIDE);
+#ifndef B200FHE_80BIT
         if (G == 8) sim_blind_rotate7(G, br.data(), (int)cnt.nbr, arena, bk_ntt, ubuf.data(), N0);
-        else sim_blind_rotate3(G, br.data(), (int)cnt.nbr, arena, bk_ntt, ubuf.data(), N0);
+        else if (G > 0) sim_blind_rotate3(G, br.data(), (int)cnt.nbr, arena, bk_ntt, ubuf.data(), N0);
+        else
+#endif
+            sim_blind_rotate1(G < 0 ? -G : 4, br.data(), (int)cnt.nbr, arena, bk_ntt, ubuf.data(), N0);
         sim_keyswitch(ks.data(), (int)cnt.nks, ubuf.data(), ksk_dev, arena);
     }
     return 0;
@@ -556,3 +639,5 @@ extern "C" int sim_gate_batch(int G, const uint8_t* opcode, const uint32_t* in0,
 extern "C" int sim_sizeof_brjob() { return (int)sizeof(BrJob); }
 extern "C" int sim_sizeof_ksjob() { return (int)sizeof(KsJob); }
 extern "C" uint32_t sim_prime() { return P; }
+extern "C" int sim_flavour_bits() { return T0_BITS == 32 ? 80 : 128; }
+extern "C" int sim_n0() { return N0; }

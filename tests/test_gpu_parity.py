@@ -26,6 +26,21 @@ def test_bk_ntt_matches_cpu_simulator(gpu_ctx, bk_ntt_sim):
         assert np.array_equal(gpu_ctx.test_read_bk_ntt(first, 4), bk_ntt_sim[first:first + 4])
 
 
+@pytest.mark.parametrize("G", [2, 4])
+def test_blind_rotate_variant1_generic_bit_exact(gpu_ctx, keys, golden, G):
+    # generic shape (brg_kernel: the kernel of the 80-bit flavour), at 128 bits against the same oracle
+    gpu_ctx.set_kernel_variant(1)
+    gpu_ctx.set_jobs_per_cta(G)
+    try:
+        c = golden["br_in"][:3]
+        assert np.array_equal(gpu_ctx.test_bootstrap_lvl1(c), O.bootstrap_to_lvl1(keys, c))
+        many = np.tile(golden["br_in"][:4], (160, 1))   # 640 jobs: more than one wave at G = 4
+        got = gpu_ctx.test_bootstrap_lvl1(many)
+        assert np.array_equal(got, np.tile(O.bootstrap_to_lvl1(keys, golden["br_in"][:4]), (160, 1)))
+    finally:
+        gpu_ctx.set_kernel_variant(0)
+
+
 def test_blind_rotate_variant7_bit_exact(gpu_ctx, keys, golden):
     # 16-warp throughput shape: 8 jobs per CTA on swizzled tiles
     gpu_ctx.set_kernel_variant(7)

@@ -65,6 +65,28 @@ def test_bk_limbs_recombine(sim, keys, bk_ntt_sim):
 
 
 @pytest.mark.parametrize("G", [2, 4])
+def test_blind_rotate_variant1_generic_bit_exact(sim, keys, bk_ntt_sim, G):
+    # generic shape (brg_phases.h: loops over GL digits / LIMBS limbs, torus-width agnostic): the kernel of the
+    # 80-bit flavour, pinned here at 128 bits against the same oracle as the specialised shapes
+    rng = np.random.default_rng(10 + G)
+    n = 3  # ragged last CTA
+    pa, pb = rng.integers(0, 2, n, dtype=np.uint8), rng.integers(0, 2, n, dtype=np.uint8)
+    ca, cb = O.encrypt_bits(1, keys, pa), O.encrypt_bits(2, keys, pb)
+    arena = np.zeros((2 * n, 640), np.uint16)
+    arena[:n, :637], arena[n:, :637] = ca, cb
+    jobs = np.zeros(n, BRJOB)
+    for g in range(n):
+        jobs[g]["in"] = (g, n + g, 0)
+        jobs[g]["sgn"] = (-1, 1, 0)          # ANDNY: -a + b - mu
+        jobs[g]["off"] = (-(1 << 13)) & 0xFFFF
+    ubuf = np.zeros((n, 1028), np.uint32)
+    sim.sim_blind_rotate1(G, p(jobs), n, p(arena), p(bk_ntt_sim), p(ubuf), 636)
+    c = (-ca.astype(np.int32) + cb.astype(np.int32)).astype(np.uint16)
+    c[:, 636] -= np.uint16(1 << 13)
+    assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
+
+
+@pytest.mark.parametrize("G", [2, 4])
 def test_blind_rotate_variant3_bit_exact(sim, keys, bk_ntt_sim, G):
     # interleaved transforms (ct_stage3 / gs_stage3): same result as the other two decompositions
     rng = np.random.default_rng(30 + G)
@@ -173,7 +195,7 @@ def test_phases_are_thread_order_independent(sim, keys, bk_ntt_sim):
     """The simulator's claim (and the kernels' barrier placement) rests on every phase function being free of
     intra-phase cross-thread communication.  If that holds, running the threads and warps of each phase in
     descending or permuted order must not change a single bit; a read-after-write or write-after-read hazard inside
-    a phase (i.e. a missing barrier) would.  Checked for the four production shapes on 40 CMUX steps."""
+    a phase (i.e. a missing barrier) would.  Checked for the five production shapes on 40 CMUX steps."""
     rng = np.random.default_rng(99)
     n, steps = 2, 40
     ca, cb = O.encrypt_bits(15, keys, rng.integers(0, 2, n, dtype=np.uint8)), O.encrypt_bits(16, keys, rng.integers(0, 2, n, dtype=np.uint8))
@@ -186,6 +208,7 @@ def test_phases_are_thread_order_independent(sim, keys, bk_ntt_sim):
         jobs[g]["off"] = 1 << 13
     runs = {"br3": lambda u: sim.sim_blind_rotate3(2, p(jobs), n, p(arena), p(bk_ntt_sim), p(u), steps),
             "br7": lambda u: sim.sim_blind_rotate7(2, p(jobs), n, p(arena), p(bk_ntt_sim), p(u), steps),
+            "brg": lambda u: sim.sim_blind_rotate1(2, p(jobs), n, p(arena), p(bk_ntt_sim), p(u), steps),
             "br4": lambda u: sim.sim_blind_rotate4(p(jobs), n, p(arena), p(bk_ntt_sim), p(u), steps),
             "br6": lambda u: sim.sim_blind_rotate6(p(jobs), n, p(arena), p(bk_ntt_sim), p(u), steps)}
     try:

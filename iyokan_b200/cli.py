@@ -15,6 +15,7 @@ reference: message on stderr, exit status 1 (src/error.hpp:21-47)."""
 from __future__ import annotations
 
 import argparse
+import os
 import sys
 import time
 from pathlib import Path
@@ -100,6 +101,7 @@ def _run(args, mode):
             ctx.load_keys(bk, ksk)
         except (B200FheError, PacketError, OSError) as e:
             die(e)
+    ok = False
     try:
         if args.resume:
             if not Frontend.is_snapshot(args.resume) or Frontend.snapshot_mode(args.resume) != mode:
@@ -131,15 +133,19 @@ def _run(args, mode):
         if rank == 0 and args.stdout_csv and mode == "plain":
             for name in sorted(res.bits):
                 print(f"{fe.cycle},{name},{sum(int(b) << i for i, b in enumerate(res.bits[name]))}")
-    except (FrontendError, PacketError, ValueError, KeyError, OSError) as e:
+        ok = True
+    except (FrontendError, PacketError, ValueError, KeyError, OSError, ZeroDivisionError) as e:
         die(e)
     finally:
         if world > 1:
             import torch.distributed as dist
 
             if dist.is_initialized():
-                dist.barrier()
-                dist.destroy_process_group()
+                if ok:  # a rank that failed must not wait for the others (they may sit in a different collective)
+                    dist.barrier()
+                    dist.destroy_process_group()
+                else:
+                    os._exit(1)
         if ctx is not None:
             ctx.close()
     return 0

@@ -23,6 +23,9 @@
 #include "br4_phases.h"
 #include "br6_phases.h"
 #include "br7_phases.h"
+#ifdef B200FHE_WITH_BR8
+#include "br8_phases.h"  // quad-cluster experiment: measured slower than br6_kernel (profiles/r02_br8.md), not in the default build
+#endif
 #endif
 #include "br_phases.h"
 #include "brg_phases.h"
@@ -390,6 +393,105 @@ br6_kernel(const BrJob* __restrict__ jobs, int njobs, const torus0_t* __restrict
 
 
 
+#ifdef B200FHE_WITH_BR8
+// ---- quad-cluster shape: one job per 4-CTA cluster, CTA (q, h) = polynomial q, transform half h (br8_phases.h) ----
+__device__ __forceinline__ uint32_t map_shared_rank(uint32_t smem_addr, uint32_t rank)
+{
+    uint32_t out;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(smem_addr), "r"(rank));
+    return out;
+}
+__device__ __forceinline__ void mbar_expect(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(BR8_THREADS, 1)
+br8_kernel(const BrJob* __restrict__ jobs, int njobs, const torus0_t* __restrict__ arena,
+           const uint32_t* __restrict__ bk_ntt, const tw_t* __restrict__ twf_g, const tw_t* __restrict__ twi_g,
+           uint32_t* __restrict__ ubuf, int n_iter)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Br8Smem sm;
+    sm.carve(smem_raw);
+    const int tid = threadIdx.x, d = tid >> 6, t = tid & 63;
+    const uint32_t rank = cluster_ctarank();
+    const int q = (int)(rank >> 1), h = (int)(rank & 1);
+    const int job = blockIdx.x >> 2;
+    for (int k = tid; k < 1024; k += BR8_THREADS) {
+        sm.twf[k] = twf_g[k];
+        sm.twi[k] = twi_g[k];
+    }
+    if (tid == 0)
+        for (int b = 0; b < 5; b++) mbar_init(sm.mbar + b, 1);
+    const BrJob jb = jobs[job];
+    br8_prologue(sm, jb, arena, q, tid);
+    __syncthreads();
+    // this CTA's quarter of a step's key: columns (q, l), rows r, positions [512h, 512h + 512): 18 chunks of 2 KB
+    auto stage = [&](int i) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect(sm.mbar, BR8_KEY_WORDS * 4);
+        const uint32_t* src = bk_ntt + (size_t)i * BR4_KEY_WORDS + (size_t)q * LIMBS * ROWS * N1 + 512 * h;
+#pragma unroll
+        for (int c = 0; c < LIMBS * ROWS; c++)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(sm.keyb + c * 512)),
+                         "l"(src + (size_t)c * N1), "r"(2048u), "r"(smem_u32(sm.mbar))
+                         : "memory");
+    };
+    constexpr uint32_t HB = 512 * 4;  // payload of a half tile (the 64 padding words are never sent)
+    const uint32_t rA = rank ^ 2u, rB = rank ^ 1u;  // partner for the digit tiles / for the halves of this polynomial
+    Br8Peer peerA[2], peerB, peerC;
+    peerA[0].bar = map_shared_rank(smem_u32(sm.mbar + 1), rA);
+    peerA[1].bar = map_shared_rank(smem_u32(sm.mbar + 2), rA);
+    peerA[0].dst = map_shared_rank(smem_u32(sm.peer + (size_t)d * H_WORDS), rA);
+    peerA[1].dst = map_shared_rank(smem_u32(sm.peer + (size_t)(GL + d) * H_WORDS), rA);
+    peerB.bar = map_shared_rank(smem_u32(sm.mbar + 3), rB);
+    peerB.dst = map_shared_rank(smem_u32(sm.half2 + (size_t)d * H_WORDS), rB);
+    peerC.bar = map_shared_rank(smem_u32(sm.mbar + 4), rB);
+    peerC.dst = map_shared_rank(smem_u32(sm.accb + 512 * h), rB);
+    if (tid == 0 && n_iter > 0) stage(0);
+    cluster_arrive();  // every CTA has initialised its barriers before anyone stores into it
+    cluster_wait();
+
+    for (int i = 0; i < n_iter; i++) {
+        const int par = i & 1;
+        if (i > 0) mbar_wait(sm.mbar + 4, (uint32_t)((i - 1) & 1));  // the other half of the accumulator, step i-1
+        if (tid == 0) {
+            mbar_expect(sm.mbar + 1 + par, GL * HB);
+            mbar_expect(sm.mbar + 3, LIMBS * HB);
+            mbar_expect(sm.mbar + 4, 2048u);
+        }
+        uint32_t* mydig = sm.dig + (size_t)(par * GL + d) * H_WORDS;
+        br8_fwd_p1(sm, i, h, d, t);
+        named_barrier_sync(1 + d, BR8_TEAM);
+        br8_fwd_p2(mydig, sm.twf, h, t);
+        named_barrier_sync(1 + d, BR8_TEAM);
+        br8_fwd_p3(mydig, sm.twf, h, t, peerA[par]);               // results also go to CTA (1-q, h) as they are produced
+        mbar_wait(sm.mbar, (uint32_t)par);                          // key quarter of step i
+        mbar_wait(sm.mbar + 1 + par, (uint32_t)((i >> 1) & 1));     // digit tiles of the other polynomial
+        __syncthreads();                                            // the local teams' tiles are complete
+        br8_pointwise(sm, q, par, tid);
+        __syncthreads();
+        if (tid == 0 && i + 1 < n_iter) stage(i + 1);
+        uint32_t* myout = sm.outb + (size_t)d * H_WORDS;
+        br8_inv_pA(myout, sm.twi, h, t);
+        named_barrier_sync(1 + d, BR8_TEAM);
+        br8_inv_pB(myout, sm.twi, h, t);
+        named_barrier_sync(1 + d, BR8_TEAM);
+        br8_inv_pC(myout, h, t, peerB);                             // results also go to CTA (q, 1-h)
+        mbar_wait(sm.mbar + 3, (uint32_t)par);                      // the other half of the three limb columns
+        br8_inv_join(sm, h, d, t);                                  // (own values: each thread re-reads what it wrote)
+        __syncthreads();                                            // all three limbs are in the accumulator
+        br8_send_acc(sm, h, tid, peerC);
+    }
+    if (n_iter > 0) mbar_wait(sm.mbar + 4, (uint32_t)((n_iter - 1) & 1));
+    cluster_arrive();  // nobody exits while a peer's copy into it may be in flight
+    cluster_wait();
+    br8_epilogue(sm, q, h, tid, ubuf + (size_t)job * U_STRIDE);
+}
+
+#endif  // B200FHE_WITH_BR8
 #endif  // !B200FHE_80BIT
 
 __global__ void __launch_bounds__(KS_THREADS * KS_GROUPS)
@@ -550,6 +652,7 @@ struct b200fhe_ctx {
     NttTables* tab = nullptr;
     tw_t* d_tw2f = nullptr;
     tw_t* d_tw2i = nullptr;
+    tw_t* d_twfull = nullptr;       // [2][1024] psi_rev and inverse (br8_kernel)
 #ifndef B200FHE_80BIT
     BlockTw* d_blocktw = nullptr;   // team-NTT twiddles (br4_kernel)
     Block8Tw* d_block8tw = nullptr; // 128-thread team NTT (br6_kernel)
@@ -761,6 +864,17 @@ static int br4_launch(b200fhe_ctx* c, int njobs, const torus0_t* arena, uint32_t
     return 0;
 }
 
+#ifdef B200FHE_WITH_BR8
+static int br8_launch(b200fhe_ctx* c, int njobs, const torus0_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+{
+    br8_kernel<<<4 * njobs, BR8_THREADS, Br8Smem::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_twfull,
+                                                                       c->d_twfull + 1024, ubuf, N0);
+    CK(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+#endif
+
 static int br6_launch(b200fhe_ctx* c, int njobs, const torus0_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
 {
     br6_kernel<<<2 * njobs, BR6_THREADS, Br6Smem::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_block8tw, ubuf, N0);
@@ -785,6 +899,9 @@ static int set_kernel_attrs()
     CK(cudaFuncSetAttribute(br7_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br7Smem<8>::BYTES));
     CK(cudaFuncSetAttribute(br4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br4Smem::BYTES));
     CK(cudaFuncSetAttribute(br6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br6Smem::BYTES));
+#ifdef B200FHE_WITH_BR8
+    CK(cudaFuncSetAttribute(br8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br8Smem::BYTES));
+#endif
 #endif
     return 0;
 }
@@ -807,6 +924,9 @@ static int br_dispatch_one(b200fhe_ctx* c, int variant, int G, int njobs, const 
         default: return br7_launch<8, 8>(c, njobs, arena, ubuf, d_jobs);
         }
     }
+#ifdef B200FHE_WITH_BR8
+    if (variant == 8) return br8_launch(c, njobs, arena, ubuf, d_jobs);
+#endif
     if (variant == 6) return br6_launch(c, njobs, arena, ubuf, d_jobs);
     if (variant == 4) return br4_launch(c, njobs, arena, ubuf, d_jobs);
     if (variant == 3) {
@@ -884,7 +1004,7 @@ static int br_dispatch(b200fhe_ctx* c, int njobs, const torus0_t* arena, uint32_
             return 1;
         if (timing) CK(cudaEventRecord(c->ev_seg[k + 1], c->stream));
         c->seg_variant[k] = seg[k].variant;
-        c->seg_G[k] = (seg[k].variant == 4 || seg[k].variant == 6) ? 1 : seg[k].G;
+        c->seg_G[k] = (seg[k].variant == 4 || seg[k].variant == 6 || seg[k].variant == 8) ? 1 : seg[k].G;
         c->seg_count[k] = seg[k].count;
         first += seg[k].count;
     }
@@ -971,6 +1091,9 @@ int b200fhe_create(b200fhe_ctx** out, int device)
     CK(cudaMalloc(&c->d_tw2i, sizeof(c->tab->tw2i)));
     CK(cudaMemcpyAsync(c->d_tw2f, c->tab->tw2f, sizeof(c->tab->tw2f), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_tw2i, c->tab->tw2i, sizeof(c->tab->tw2i), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMalloc(&c->d_twfull, 2 * sizeof(c->tab->fwd)));
+    CK(cudaMemcpyAsync(c->d_twfull, c->tab->fwd, sizeof(c->tab->fwd), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_twfull + 1024, c->tab->inv, sizeof(c->tab->inv), cudaMemcpyHostToDevice, c->stream));
 #ifndef B200FHE_80BIT
     BlockTw* btw = new BlockTw();
     block_tw_init(*c->tab, *btw);
@@ -998,6 +1121,7 @@ void b200fhe_destroy(b200fhe_ctx* c)
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tw2f);
     cudaFree(c->d_tw2i);
+    cudaFree(c->d_twfull);
 #ifndef B200FHE_80BIT
     cudaFree(c->d_blocktw);
     cudaFree(c->d_block8tw);
@@ -1047,8 +1171,8 @@ int b200fhe_set_kernel_variant(b200fhe_ctx* c, int variant)
 {
     if (!c) return fail("null context");
     if (variant == 0) return b200fhe_set_jobs_per_cta(c, 0);
-    if (variant != 1 && variant != 3 && variant != 4 && variant != 6 && variant != 7)
-        return fail("kernel variant must be 0 (auto), 1, 3, 4, 6 or 7");
+    if (variant != 1 && variant != 3 && variant != 4 && variant != 6 && variant != 7 && variant != 8)
+        return fail("kernel variant must be 0 (auto), 1, 3, 4, 6, 7 or 8");
     c->variant = variant;
     c->autotune = false;
     return 0;
@@ -1261,7 +1385,7 @@ int b200fhe_plan_rotation(int njobs, int* variant, int* jobs_per_cta, int* jobs,
     const int n = nseg < max_segments ? nseg : max_segments;
     for (int k = 0; k < n; k++) {
         if (variant) variant[k] = seg[k].variant;
-        if (jobs_per_cta) jobs_per_cta[k] = (seg[k].variant == 4 || seg[k].variant == 6) ? 1 : seg[k].G;
+        if (jobs_per_cta) jobs_per_cta[k] = (seg[k].variant == 4 || seg[k].variant == 6 || seg[k].variant == 8) ? 1 : seg[k].G;
         if (jobs) jobs[k] = seg[k].count;
     }
     return n;

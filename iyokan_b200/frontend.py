@@ -127,6 +127,8 @@ class Frontend:
                 if name in self.nl.mem and name not in rams and name not in roms:
                     raise FrontendError(f"memory {name!r} is given only in CMUX (TRLWE) form")
         for name in bits:
+            if len(bits[name]) == 0:
+                raise FrontendError(f"request gives an empty bit stream for @{name}")
             if name == "reset":
                 raise FrontendError("@reset cannot be set by the request (iyokan_tfhepp.cpp:284-285)")
             if name not in self.nl.in_ports:

@@ -377,6 +377,12 @@ struct Scheduler {
     std::vector<uint8_t> jobs;
     Scheduler(const b200net& n, int w, double x) : net(n), world(w), exch_ms(x) {}
 
+    // Rotation jobs the busiest rank gets when `total` jobs are cut into `world` contiguous shares of whole gates
+    // (a MUX is two jobs and is not split): every share is filled up to this load, an earlier share may fall one
+    // short of it, so one spare job per earlier rank is budgeted.  The launch plan has cliffs (75 jobs cost one more
+    // launch than 74), so the shares must never exceed what the cost model assumed.
+    size_t share(size_t total) const { return world == 1 ? total : (total + 2 * (size_t)world - 2) / world; }
+
     // cost (ms) of one step with `total` rotation jobs: replicated, or sharded over the ranks
     double step_cost(size_t total, bool* shard) const
     {
@@ -385,7 +391,7 @@ struct Scheduler {
             if (shard) *shard = false;
             return rep;
         }
-        const double shd = b200fhe_plan_ms((int)((total + world - 1) / world)) + exch_ms;
+        const double shd = b200fhe_plan_ms((int)share(total)) + exch_ms;
         if (shard) *shard = shd < rep;
         return shd < rep ? shd : rep;
     }
@@ -456,7 +462,8 @@ struct Scheduler {
                 double best = step_cost(mj, nullptr);
                 size_t best_k = 0;
                 for (size_t pt : points) {
-                    const size_t target = pt * (size_t)world;
+                    // the largest total whose busiest share still fits the capacity point
+                    const size_t target = world == 1 ? pt : pt * (size_t)world - 2 * ((size_t)world - 1);
                     if (target <= mj) continue;
                     // largest prefix of the candidates that fits the target
                     size_t k = std::upper_bound(pre.begin(), pre.end(), target - mj) - pre.begin() - 1;
@@ -501,15 +508,18 @@ void assign_slots(b200net* net, int world)
         st.chunk = 0;
         st.base_shd = next;
         if (!st.shd.empty()) {
-            // contiguous shares balanced by rotation count (a MUX is two rotations)
-            size_t total = 0, run = 0;
-            for (uint32_t g : st.shd) total += std::max(1, bootstraps(net->kind[g]));
-            int r = 1;
-            for (size_t k = 0; k < st.shd.size() && r < world; k++) {
-                run += std::max(1, bootstraps(net->kind[st.shd[k]]));
-                while (r < world && run * world >= total * r) st.cut[r++] = k + 1;
+            // contiguous shares of whole gates, each filled up to the load the cost model assumed (Scheduler::share):
+            // gates without a rotation (NOT / COPY / CONST) ride along for free
+            size_t total = 0;
+            for (uint32_t g : st.shd) total += bootstraps(net->kind[g]);
+            const size_t load = (total + 2 * (size_t)world - 2) / world;
+            size_t k = 0;
+            for (int r = 0; r < world; r++) {
+                st.cut[r] = k;
+                size_t have = 0;
+                while (k < st.shd.size() && (r == world - 1 || have + bootstraps(net->kind[st.shd[k]]) <= load))
+                    have += bootstraps(net->kind[st.shd[k++]]);
             }
-            for (; r <= world; r++) st.cut[r] = st.shd.size();
             st.cut[world] = st.shd.size();
             for (int q = 0; q < world; q++) st.chunk = std::max(st.chunk, st.cut[q + 1] - st.cut[q]);
             for (int q = 0; q < world; q++)

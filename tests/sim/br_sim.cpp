@@ -14,6 +14,7 @@
 #include "../../iyokan_b200/csrc/br4_phases.h"
 #include "../../iyokan_b200/csrc/br6_phases.h"
 #include "../../iyokan_b200/csrc/br7_phases.h"
+#include "../../iyokan_b200/csrc/br8_phases.h"
 #endif
 #include "../../iyokan_b200/csrc/br_phases.h"
 #include "../../iyokan_b200/csrc/brg_phases.h"
@@ -526,6 +527,63 @@ extern "C" void sim_blind_rotate6(const void* jobs_raw, int njobs, const torus0_
 }
 
 
+
+// ---- variant 8: quad-cluster shape (br8_kernel); the four CTAs advance phase by phase, the three DSMEM exchanges
+// become memcpys at the points where the kernel issues the bulk copies ----
+static void sim_br8_cluster(const BrJob* jobs, int job, const torus0_t* arena, const uint32_t* bk_ntt, uint32_t* ubuf,
+                            int n_iter)
+{
+    std::vector<uint8_t> smem[4];
+    Br8Smem sm[4];
+    for (int r = 0; r < 4; r++) {
+        smem[r].assign(Br8Smem::BYTES + 128, 0);
+        sm[r].carve(reinterpret_cast<void*>(((uintptr_t)smem[r].data() + 127) & ~(uintptr_t)127));
+        std::memcpy(sm[r].twf, g_tab.fwd, sizeof(g_tab.fwd));
+        std::memcpy(sm[r].twi, g_tab.inv, sizeof(g_tab.inv));
+        for (int tid = 0; tid < BR8_THREADS; tid++) br8_prologue(sm[r], jobs[job], arena, r >> 1, tid);
+    }
+    auto each = [&](auto fn) {  // fn(rank, q, h, d, t)
+        for (int rr = 0; rr < 4; rr++)
+            for (int k = 0; k < BR8_THREADS; k++) {
+                const int r = ord(rr, 4), tid = ord(k, BR8_THREADS);
+                fn(r, r >> 1, r & 1, tid >> 6, tid & 63);
+            }
+    };
+    for (int i = 0; i < n_iter; i++) {
+        const int par = i & 1;
+        for (int r = 0; r < 4; r++) {  // key quarter of CTA (q, h)
+            const int q = r >> 1, h = r & 1;
+            for (int c = 0; c < LIMBS * ROWS; c++)
+                std::memcpy(sm[r].keyb + c * 512, bk_ntt + (size_t)i * BR4_KEY_WORDS + (size_t)(q * LIMBS * ROWS + c) * N1 + 512 * h, 2048);
+        }
+        each([&](int r, int, int h, int d, int t) { br8_fwd_p1(sm[r], i, h, d, t); });
+        each([&](int r, int, int h, int d, int t) { br8_fwd_p2(sm[r].dig + (size_t)(par * GL + d) * H_WORDS, sm[r].twf, h, t); });
+        each([&](int r, int, int h, int d, int t) { br8_fwd_p3(sm[r].dig + (size_t)(par * GL + d) * H_WORDS, sm[r].twf, h, t); });
+        for (int r = 0; r < 4; r++)  // exchange A: digit half tiles -> CTA r ^ 2
+            std::memcpy(sm[r ^ 2].peer + (size_t)par * GL * H_WORDS, sm[r].dig + (size_t)par * GL * H_WORDS, (size_t)GL * H_WORDS * 4);
+        for (int rr = 0; rr < 4; rr++)
+            for (int k = 0; k < BR8_THREADS; k++) br8_pointwise(sm[ord(rr, 4)], ord(rr, 4) >> 1, par, ord(k, BR8_THREADS));
+        each([&](int r, int, int h, int d, int t) { br8_inv_pA(sm[r].outb + (size_t)d * H_WORDS, sm[r].twi, h, t); });
+        each([&](int r, int, int h, int d, int t) { br8_inv_pB(sm[r].outb + (size_t)d * H_WORDS, sm[r].twi, h, t); });
+        each([&](int r, int, int h, int d, int t) { br8_inv_pC(sm[r].outb + (size_t)d * H_WORDS, h, t); });
+        for (int r = 0; r < 4; r++)  // exchange B: half results -> CTA r ^ 1
+            std::memcpy(sm[r ^ 1].half2, sm[r].outb, (size_t)LIMBS * H_WORDS * 4);
+        each([&](int r, int, int h, int d, int t) { br8_inv_join(sm[r], h, d, t); });
+        for (int r = 0; r < 4; r++)  // exchange C: updated accumulator half -> CTA r ^ 1
+            std::memcpy(sm[r ^ 1].accb + 512 * (r & 1), sm[r].accb + 512 * (r & 1), 2048);
+    }
+    for (int r = 0; r < 4; r++)
+        for (int tid = 0; tid < BR8_THREADS; tid++) br8_epilogue(sm[r], r >> 1, r & 1, tid, ubuf + (size_t)job * U_STRIDE);
+}
+
+extern "C" void sim_blind_rotate8(const void* jobs_raw, int njobs, const torus0_t* arena, const uint32_t* bk_ntt,
+                                  uint32_t* ubuf, int n_iter)
+{
+    sim_init();
+    const BrJob* jobs = reinterpret_cast<const BrJob*>(jobs_raw);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int job = 0; job < njobs; job++) sim_br8_cluster(jobs, job, arena, bk_ntt, ubuf, n_iter);
+}
 
 #endif  // !B200FHE_80BIT
 

@@ -191,11 +191,31 @@ def test_blind_rotate_variant6_bit_exact(sim, keys, bk_ntt_sim):
     assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
 
 
+def test_blind_rotate_variant8_bit_exact(sim, keys, bk_ntt_sim):
+    # quad-cluster shape (br8_phases.h): 4 CTAs per job, every transform cut into two 512-position halves
+    rng = np.random.default_rng(88)
+    n = 3
+    pa, pb = rng.integers(0, 2, n, dtype=np.uint8), rng.integers(0, 2, n, dtype=np.uint8)
+    ca, cb = O.encrypt_bits(21, keys, pa), O.encrypt_bits(22, keys, pb)
+    arena = np.zeros((2 * n, 640), np.uint16)
+    arena[:n, :637], arena[n:, :637] = ca, cb
+    jobs = np.zeros(n, BRJOB)
+    for g in range(n):
+        jobs[g]["in"] = (g, n + g, 0)
+        jobs[g]["sgn"] = (-1, -1, 0)         # NOR: -a - b - mu
+        jobs[g]["off"] = (-(1 << 13)) & 0xFFFF
+    ubuf = np.zeros((n, 1028), np.uint32)
+    sim.sim_blind_rotate8(p(jobs), n, p(arena), p(bk_ntt_sim), p(ubuf), 636)
+    c = (-ca.astype(np.int32) - cb.astype(np.int32)).astype(np.uint16)
+    c[:, 636] -= np.uint16(1 << 13)
+    assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
+
+
 def test_phases_are_thread_order_independent(sim, keys, bk_ntt_sim):
     """The simulator's claim (and the kernels' barrier placement) rests on every phase function being free of
     intra-phase cross-thread communication.  If that holds, running the threads and warps of each phase in
     descending or permuted order must not change a single bit; a read-after-write or write-after-read hazard inside
-    a phase (i.e. a missing barrier) would.  Checked for the five production shapes on 40 CMUX steps."""
+    a phase (i.e. a missing barrier) would.  Checked for the six production shapes on 40 CMUX steps."""
     rng = np.random.default_rng(99)
     n, steps = 2, 40
     ca, cb = O.encrypt_bits(15, keys, rng.integers(0, 2, n, dtype=np.uint8)), O.encrypt_bits(16, keys, rng.integers(0, 2, n, dtype=np.uint8))
@@ -210,7 +230,8 @@ def test_phases_are_thread_order_independent(sim, keys, bk_ntt_sim):
             "br7": lambda u: sim.sim_blind_rotate7(2, p(jobs), n, p(arena), p(bk_ntt_sim), p(u), steps),
             "brg": lambda u: sim.sim_blind_rotate1(2, p(jobs), n, p(arena), p(bk_ntt_sim), p(u), steps),
             "br4": lambda u: sim.sim_blind_rotate4(p(jobs), n, p(arena), p(bk_ntt_sim), p(u), steps),
-            "br6": lambda u: sim.sim_blind_rotate6(p(jobs), n, p(arena), p(bk_ntt_sim), p(u), steps)}
+            "br6": lambda u: sim.sim_blind_rotate6(p(jobs), n, p(arena), p(bk_ntt_sim), p(u), steps),
+            "br8": lambda u: sim.sim_blind_rotate8(p(jobs), n, p(arena), p(bk_ntt_sim), p(u), steps)}
     try:
         ref = None
         for name, run in runs.items():

@@ -200,7 +200,7 @@ def netlist_legs(args, ctx, stream, rank, world, barrier):
     import bench_netlist as BN
     from iyokan_b200.packet import read_eval_key
 
-    names = [x for x in args.netlist_cases.split(",") if x] or (["cahp-pearl-mux", "mux-ram-8-16-16"] if world == 1 else ["cahp-pearl-mux"])
+    names = [x for x in args.netlist_cases.split(",") if x] or (["cahp-pearl-mux", "cahp-ruby-mux", "mux-ram-8-16-16"] if world == 1 else ["cahp-pearl-mux"])
     box = [tempfile.mkdtemp(prefix="b200fhe_net_") if rank == 0 else None]
     if world > 1:
         dist.broadcast_object_list(box, src=0)
@@ -271,7 +271,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-netlist", action="store_true", help="skip the netlist leg (CAHP processor / mux-ram)")
     ap.add_argument("--netlist-cycles", type=int, default=10)
-    ap.add_argument("--netlist-cases", default="", help="comma list; default: cahp-pearl-mux (+ mux-ram-8-16-16 at N=1)")
+    ap.add_argument("--netlist-cases", default="", help="comma list; default: cahp-pearl-mux (+ cahp-ruby-mux, mux-ram-8-16-16 at N=1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -373,8 +373,10 @@ def main():
 
     out_res = ctx.download(ids[3 * n:])
     bits_ok = bool(np.array_equal(O.decrypt_bits(keys, out_res), 1 - (pa & pb)))
-    k = 4
-    exact_ok = bool(np.array_equal(out_res[:k], O.gate_batch(keys, ops[:k], ca[:k], cb[:k])))
+    k = min(n, 64)  # ciphertext-exact against the oracle on a strided sample of the batch (all host threads)
+    pick = np.linspace(0, n - 1, k).astype(np.int64)
+    exact_ok = bool(np.array_equal(out_res[pick], O.gate_batch(keys, ops[pick], ca[pick], cb[pick],
+                                                                nthreads=os.cpu_count() or 1)))
 
     for _ in range(2):
         step_e2e()
@@ -432,6 +434,9 @@ def main():
                          "whole_step_frac": n * BR_KERNEL_BYTES_PER_JOB / (br_ms / 1e3) / 1e9 / peak,
                          "gate_model_frac": (value / world) * BYTES_PER_BOOTSTRAP / (peak * 1e9)},
             "outputs_ok": all_ok,
+            "checks": {"decrypted_bits": f"all {n} gates per rank == NAND of the plaintexts",
+                       "ciphertext_exact": f"{k} gates per rank (strided over the batch) bit-identical to the oracle",
+                       "e2e_equals_resident": "host-buffer result == device-resident result, whole batch"},
         }
         # honest bound of the dominant kernel: the int32 multiply pipe (DRAM is idle: keys sit in L2).  Pipe cycles per
         # CMUX step and job from the SASS of br7_kernel<8,8> (per thread and step: 2100 IMAD x 2 + 1056 IMAD.HI x 4 +

@@ -34,6 +34,28 @@
 
 using namespace b200;
 
+// Per-phase cycle counters of the rotation kernels, debug builds only (-DB200FHE_PHASE_TIMING; scripts/gpu_phase_timing.py):
+// the first and the last warp of CTA 0 add the cycles between consecutive marks.
+#ifdef B200FHE_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[2][32];
+#define PHASE_DECL                                                                                   \
+    const int _pobs = (blockIdx.x == 0 && (threadIdx.x & 31) == 0)                                    \
+                          ? (threadIdx.x == 0 ? 0 : ((int)threadIdx.x == (int)blockDim.x - 32 ? 1 : -1)) \
+                          : -1;                                                                       \
+    long long _pt = clock64();
+#define PHASE_MARK(k)                                          \
+    do {                                                       \
+        if (_pobs >= 0) {                                      \
+            const long long _n = clock64();                    \
+            g_phase_cycles[_pobs][k] += (unsigned long long)(_n - _pt); \
+            _pt = _n;                                          \
+        }                                                      \
+    } while (0)
+#else
+#define PHASE_DECL
+#define PHASE_MARK(k)
+#endif
+
 // =====================================================================================
 // kernels
 // =====================================================================================
@@ -174,12 +196,15 @@ br7_kernel(const BrJob* __restrict__ jobs, int njobs, const torus0_t* __restrict
         const long long t0 = clock64(), wait = (long long)group * skew_cycles;
         while (clock64() - t0 < wait) {}
     }
+    PHASE_DECL
     for (int i = 0; i < n_iter; i++) {
         const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
         uint32_t bk0[BK_COLS][ROWS];
         br7_fwd12_a<G>(sm, i, g, q, lane, accr);
         __syncwarp();
+        PHASE_MARK(0);
         br7_fwd12_c<G>(sm, g, q, lane);
+        PHASE_MARK(1);
         {
             uint32_t x0[32];
             br7_fwd0_a<G>(sm, i, g, q, lane, accr, x0);
@@ -187,18 +212,27 @@ br7_kernel(const BrJob* __restrict__ jobs, int njobs, const torus0_t* __restrict
             br7_fwd0_b<G>(sm, g, q, lane, x0);
         }
         __syncwarp();
+        PHASE_MARK(2);
         br7_fwd0_c<G>(sm, g, q, lane);
+        PHASE_MARK(3);
         pw_load(bk_i, tig, bk0);  // key words of the pointwise stage in flight across the barrier
         if (J == G) __syncthreads(); else named_barrier_sync(1 + group, 64 * J);
+        PHASE_MARK(4);
         br7_pointwise<G, J>(sm, bk_i, g0, tig, bk0);
+        PHASE_MARK(5);
         if (J == G) __syncthreads(); else named_barrier_sync(1 + group, 64 * J);
+        PHASE_MARK(6);
         br7_inv01_a<G>(sm, g, q, lane);
         __syncwarp();
+        PHASE_MARK(7);
         br7_inv01_b<G>(sm, g, q, lane, accr);
+        PHASE_MARK(8);
         br7_inv2_a<G>(sm, g, q, lane);
         __syncwarp();
+        PHASE_MARK(9);
         br7_inv2_b<G>(sm, g, q, lane, accr);
         __syncwarp();
+        PHASE_MARK(10);
     }
     if (valid) br7_epilogue<G>(sm, g, q, lane, ubuf + (size_t)job * U_STRIDE);
 }
@@ -349,43 +383,67 @@ br6_kernel(const BrJob* __restrict__ jobs, int njobs, const torus0_t* __restrict
     cluster_wait();
     cluster_arrive_relaxed();  // phase (B) of "step -1"
 
+    PHASE_DECL
     for (int i = 0; i < n_iter; i++) {
         if (tid == 0)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar_dig)),
                          "r"(GL * TILE_BYTES)
                          : "memory");
         br6_fwd_p1(sm, i, q, d, t);
+        PHASE_MARK(0);
         named_barrier_sync(1 + d, TEAM8_THREADS);
+        PHASE_MARK(1);
         br6_fwd_p2(sm, q, d, t);
+        PHASE_MARK(2);
         named_barrier_sync(1 + d, TEAM8_THREADS);
+        PHASE_MARK(3);
         br6_fwd_p3(sm, q, d, t);
+        PHASE_MARK(4);
         named_barrier_sync(1 + d, TEAM8_THREADS);
+        PHASE_MARK(5);
         br6_fwd_p4(sm, q, d, t);
+        PHASE_MARK(6);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         cluster_wait();    // (B) the peer's pointwise stage of the previous step no longer reads my copies
+        PHASE_MARK(7);
         named_barrier_sync(1 + d, TEAM8_THREADS);
+        PHASE_MARK(8);
         if (t == 0)
             asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              peer_tile),
                          "r"(my_tile), "r"(TILE_BYTES), "r"(peer_bar)
                          : "memory");
         mbar_wait(sm.mbar, (uint32_t)(i & 1));
+        PHASE_MARK(9);
         uint64_t pacc[LIMBS][4];
         named_barrier_sync(7, BR6_THREADS);  // the local teams' tiles are complete
+        PHASE_MARK(10);
         br6_pw_local(sm, q, tid, pacc);
+        PHASE_MARK(11);
         mbar_wait(mbar_dig, (uint32_t)(i & 1));  // the peer's three tiles have landed
+        PHASE_MARK(12);
         br6_pw_finish(sm, q, tid, pacc);
+        PHASE_MARK(13);
         cluster_arrive_relaxed();  // (B) for the next step
         __syncthreads();
+        PHASE_MARK(14);
         if (tid == 0 && i + 1 < n_iter) stage(i + 1);
         br6_inv_pA(sm, d, t);
+        PHASE_MARK(15);
         named_barrier_sync(1 + d, TEAM8_THREADS);
+        PHASE_MARK(16);
         br6_inv_pB(sm, d, t);
+        PHASE_MARK(17);
         named_barrier_sync(1 + d, TEAM8_THREADS);
+        PHASE_MARK(18);
         br6_inv_pC(sm, d, t);
+        PHASE_MARK(19);
         named_barrier_sync(1 + d, TEAM8_THREADS);
+        PHASE_MARK(20);
         br6_inv_pD(sm, d, t);
+        PHASE_MARK(21);
         __syncthreads();
+        PHASE_MARK(22);
     }
     cluster_wait();
     br6_epilogue(sm, q, tid, ubuf + (size_t)job * U_STRIDE);
@@ -1844,3 +1902,16 @@ int b200fhe_test_read_bk_ntt(b200fhe_ctx* c, uint32_t* out_host, size_t first_i,
 }
 
 }  // extern "C"
+
+#ifdef B200FHE_PHASE_TIMING
+// debug builds only: read and clear the per-phase cycle counters (two observer warps x 32 marks)
+extern "C" int b200fhe_debug_phase_cycles(unsigned long long* out, int clear)
+{
+    if (cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 64) != cudaSuccess) return -1;
+    if (clear) {
+        unsigned long long z[64] = {};
+        if (cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif

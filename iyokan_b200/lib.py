@@ -18,7 +18,7 @@ CSRC = Path(__file__).resolve().parent / "csrc"
 FLAVOUR = os.environ.get("B200FHE_FLAVOUR", "")
 if FLAVOUR not in ("", "80"):
     raise ImportError(f"B200FHE_FLAVOUR must be '' (128-bit) or '80', not {FLAVOUR!r}")
-LIB_PATH = CSRC / f"libb200fhe{FLAVOUR}.so"
+LIB_PATH = Path(os.environ["B200FHE_LIB"]) if os.environ.get("B200FHE_LIB") else CSRC / f"libb200fhe{FLAVOUR}.so"  # override: debug builds
 
 N1, TLWE1_LEN = 1024, 1025
 if FLAVOUR == "80":   # TFHEpp include/params/CGGI16.hpp

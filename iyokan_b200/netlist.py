@@ -401,7 +401,10 @@ def bytes_of(bits):
 
 
 class PlainRunner:
-    """Cycle protocol of TFHEppFrontend::go / doPlain (SURVEY.md Appendix B) on the plaintext back-end."""
+    """Cycle protocol of TFHEppFrontend::go / doPlain (SURVEY.md Appendix B) on the plaintext back-end.
+
+    Test helper for netlists made with NetBuilder; the command-line protocol (TOGND bits, write-through RAM images,
+    snapshots, length checks with the reference's messages) is `frontend.Frontend`."""
 
     def __init__(self, nl: Netlist, eng: NetEngine | None = None):
         self.nl, self.eng = nl, eng or NetEngine(nl)
@@ -409,7 +412,10 @@ class PlainRunner:
 
     def set_mem(self, name, bits):
         nodes = self.nl.mem[name]
-        self.v[np.array(nodes)] = np.asarray(bits, np.uint8)[:len(nodes)]
+        bits = np.asarray(bits, np.uint8)
+        if bits.size != len(nodes):
+            raise ValueError(f"memory {name}: {bits.size} bits given, {len(nodes)} cells")
+        self.v[np.array(nodes)] = bits
 
     def get_mem(self, name):
         return self.v[np.array(self.nl.mem[name])].copy()
@@ -439,11 +445,13 @@ class PlainRunner:
                 w = len(self.nl.in_ports[port])
                 self._set_port(port, [stream[(w * c + b) % len(stream)] for b in range(w)])
             self.eng.plain_eval(self.v)
-        return {p: self.v[np.array(nodes)].copy() for p, nodes in self.nl.out_ports.items()}
+        # an unconnected (TOGND) bit of an output port reads 0
+        return {p: np.array([self.v[n] if n >= 0 else 0 for n in nodes], np.uint8) for p, nodes in self.nl.out_ports.items()}
 
 
 class EncryptedRunner:
-    """Same cycle protocol on the GPU back-end (TFHEppFrontend::go, src/iyokan_tfhepp.cpp:465-566).
+    """Same cycle protocol on the GPU back-end (TFHEppFrontend::go, src/iyokan_tfhepp.cpp:465-566).  Like PlainRunner a
+    helper for builder-made netlists and all-gate packets; write-through (CMUX) RAM images are `frontend.Frontend`'s job.
 
     Inputs are CIPHERTEXTS: `inputs[port]` is a TLWE stream [size][637] uint16 (what TFHEPacket.bits holds),
     `rams` / `roms` are [bits][637] arrays (TFHEPacket.ramInTLWE / romInTLWE).  For tests that start from
@@ -466,7 +474,9 @@ class EncryptedRunner:
             raise ValueError("plaintext bits given but no encrypt callback")
         return self.encrypt(np.asarray(x, np.uint8))
 
-    def _set_nodes(self, nodes, ct):
+    def _set_nodes(self, nodes, ct, what=None):
+        if what is not None and len(ct) != len(nodes):
+            raise ValueError(f"memory {what}: {len(ct)} ciphertexts given, {len(nodes)} cells")
         keep = [i for i, n in enumerate(nodes) if n >= 0 and i < len(ct)]
         if keep:
             self.eng.set(np.array([nodes[i] for i in keep], np.uint32), np.ascontiguousarray(ct[keep]))
@@ -474,7 +484,7 @@ class EncryptedRunner:
     def run(self, cycles, inputs=None, rams=None, roms=None):
         inputs = {p: self._ct(v) for p, v in (inputs or {}).items()}
         for name, v in (roms or {}).items():
-            self._set_nodes(self.nl.mem[name], self._ct(v))
+            self._set_nodes(self.nl.mem[name], self._ct(v), what=name)
         has_reset = "reset" in self.nl.in_ports
         if has_reset:
             # reset pass (iyokan_tfhepp.cpp:487-500): reset <- trivial 1, every other input still holds
@@ -487,17 +497,25 @@ class EncryptedRunner:
                 if has_reset:
                     self._set_nodes(self.nl.in_ports["reset"], trivial(0)[None])
                 for name, v in (rams or {}).items():
-                    self._set_nodes(self.nl.mem[name], self._ct(v))
+                    self._set_nodes(self.nl.mem[name], self._ct(v), what=name)
             for port, stream in inputs.items():  # setCircularInputs, iyokan_tfhepp.cpp:274-296
                 w = len(self.nl.in_ports[port])
                 idx = [(w * c + b) % len(stream) for b in range(w)]
                 self._set_nodes(self.nl.in_ports[port], stream[idx])
             self.eng.run()
         self.ctx.sync()
-        return {p: self.eng.get(np.array(nodes, np.uint32)) for p, nodes in self.nl.out_ports.items()}
+        return {p: self._get_nodes(nodes) for p, nodes in self.nl.out_ports.items()}
+
+    def _get_nodes(self, nodes):
+        """Ciphertexts of `nodes`; an unconnected (TOGND, -1) bit reads as the trivial 0 the reference leaves there."""
+        out = np.tile(trivial(0), (len(nodes), 1))
+        keep = [i for i, n in enumerate(nodes) if n >= 0]
+        if keep:
+            out[keep] = self.eng.get(np.array([nodes[i] for i in keep], np.uint32))
+        return out
 
     def get_mem(self, name):
-        return self.eng.get(np.array(self.nl.mem[name], np.uint32))
+        return self._get_nodes(self.nl.mem[name])
 
 
 def run_packet(nl: Netlist, ctx: Context, req, cycles: int | None = None):
@@ -511,6 +529,8 @@ def run_packet(nl: Netlist, ctx: Context, req, cycles: int | None = None):
     for name in list(req.bits):
         if name not in nl.in_ports:
             raise ValueError(f"request packet drives unknown input port @{name}")
+    if nl.write_through:
+        raise ValueError("blueprint declares CMUX RAMs (write-through images): run it through frontend.Frontend")
     runner = EncryptedRunner(nl, ctx)
     rams = {k: v for k, v in req.ram_in_tlwe.items() if k in nl.mem}
     roms = {k: v for k, v in req.rom_in_tlwe.items() if k in nl.mem}

@@ -255,3 +255,21 @@ def test_blueprint_loader_rejects_what_the_reference_rejects(tmp_path):
     (tmp_path / "req.in").write_text("cycles = 1\n")
     assert run_cli("plain", "--blueprint", tmp_path / "both.toml", "-i", tmp_path / "req.in", "-o", tmp_path / "r", "-c", 1) == 1
     assert run_cli("plain", "--blueprint", tmp_path / "nonet.toml", "-i", tmp_path / "req.in", "-o", tmp_path / "r", "-c", 1) == 1
+
+
+def test_external_input_bit_fans_out_to_every_consumer(tmp_path):
+    """One external input bit wired to several sub-networks drives ALL of them in this loader.  The reference keeps one
+    connection per external bit in a map filled in the iteration order of an unordered TOML table
+    (src/iyokan.hpp:1876-1884), so which consumer it drives is unspecified there; blueprints that rely on it are
+    ambiguous in the reference and deterministic here."""
+    import shutil
+
+    shutil.copy(FIX / "upcount2-netlist.json", tmp_path / "n.json")
+    (tmp_path / "two.toml").write_text(
+        '[[file]]\nname = "a"\ntype = "yosys-json"\npath = "n.json"\n[[file]]\nname = "b"\ntype = "yosys-json"\npath = "n.json"\n'
+        '[connect]\n"a/reset" = "@reset"\n"b/reset" = "@reset"\n"@outa[0:1]" = "a/io_q[0:1]"\n"@outb[0:1]" = "b/io_q[0:1]"\n')
+    (tmp_path / "req.in").write_text("cycles = 3\n")
+    assert run_cli("plain", "--blueprint", tmp_path / "two.toml", "-i", tmp_path / "req.in", "-o", tmp_path / "res", "-c", 3,
+                   "--quiet") == 0
+    res = PlainPacket.load(tmp_path / "res")
+    assert word(res.bits["outa"]) == 2 and word(res.bits["outb"]) == 2

@@ -38,22 +38,44 @@ using namespace b200;
 // the first and the last warp of CTA 0 add the cycles between consecutive marks.
 #ifdef B200FHE_PHASE_TIMING
 __device__ unsigned long long g_phase_cycles[2][32];
+__device__ unsigned long long g_cta_ns[1024][4];  // per CTA: kernel entry, loop start, loop end, exit (globaltimer)
+#define CTA_STAMP(k)                                                                    \
+    if (threadIdx.x == 0 && blockIdx.x < 1024) {                                        \
+        unsigned long long _g;                                                          \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_g));                          \
+        g_cta_ns[blockIdx.x][k] = _g;                                                   \
+    }
+// counters stay in registers (32-bit clock differences) and are written once by PHASE_FLUSH: a global read-modify-write
+// per mark would itself cost more than most phases
 #define PHASE_DECL                                                                                   \
     const int _pobs = (blockIdx.x == 0 && (threadIdx.x & 31) == 0)                                    \
                           ? (threadIdx.x == 0 ? 0 : ((int)threadIdx.x == (int)blockDim.x - 32 ? 1 : -1)) \
                           : -1;                                                                       \
-    long long _pt = clock64();
-#define PHASE_MARK(k)                                          \
-    do {                                                       \
-        if (_pobs >= 0) {                                      \
-            const long long _n = clock64();                    \
-            g_phase_cycles[_pobs][k] += (unsigned long long)(_n - _pt); \
-            _pt = _n;                                          \
-        }                                                      \
+    unsigned _pacc[24];                                                                               \
+    const long long _pc0 = clock64();                                                                 \
+    unsigned long long _pg0;                                                                          \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_pg0));                                          \
+    _Pragma("unroll") for (int _k = 0; _k < 24; _k++) _pacc[_k] = 0;                                  \
+    unsigned _pt = (unsigned)clock();
+#define PHASE_MARK(k)                              \
+    do {                                           \
+        const unsigned _n = (unsigned)clock();     \
+        _pacc[k] += _n - _pt;                      \
+        _pt = _n;                                  \
     } while (0)
+#define PHASE_FLUSH                                                                          \
+    if (_pobs >= 0) {                                                                        \
+        _Pragma("unroll") for (int _k = 0; _k < 24; _k++) g_phase_cycles[_pobs][_k] += _pacc[_k]; \
+        unsigned long long _pg1;                                                             \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_pg1));                             \
+        g_phase_cycles[_pobs][30] += (unsigned long long)(clock64() - _pc0); /* loop cycles */ \
+        g_phase_cycles[_pobs][31] += _pg1 - _pg0;                            /* loop ns */     \
+    }
 #else
 #define PHASE_DECL
 #define PHASE_MARK(k)
+#define PHASE_FLUSH
+#define CTA_STAMP(k)
 #endif
 
 // =====================================================================================
@@ -174,17 +196,19 @@ template <int G, int J>
 __global__ void __launch_bounds__(64 * G, 1)
 br7_kernel(const BrJob* __restrict__ jobs, int njobs, const torus0_t* __restrict__ arena,
            const uint32_t* __restrict__ bk_ntt, const tw_t* __restrict__ tw2f_g, const tw_t* __restrict__ tw2i_g,
-           uint32_t* __restrict__ ubuf, int n_iter, int skew_cycles)
+           const uint32_t* __restrict__ r4_g, uint32_t* __restrict__ ubuf, int n_iter, int skew_cycles)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Br7Smem<G> sm;
     sm.carve(smem_raw);
+    CTA_STAMP(0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = warp >> 1, q = warp & 1;
     const int group = g / J, g0 = group * J, tig = tid - 64 * g0;
     for (int k = tid; k < TW2_LEN; k += 64 * G) {
         sm.tw2f[k] = tw2f_g[k];
         sm.tw2i[k] = tw2i_g[k];
     }
+    for (int k = tid; k < R4_WORDS; k += 64 * G) sm.r4[k] = r4_g[k];
     int job = blockIdx.x * G + g;
     const bool valid = job < njobs;
     if (!valid) job = njobs - 1;  // duplicate work, keeps every barrier uniform
@@ -197,6 +221,7 @@ br7_kernel(const BrJob* __restrict__ jobs, int njobs, const torus0_t* __restrict
         while (clock64() - t0 < wait) {}
     }
     PHASE_DECL
+    CTA_STAMP(1);
     for (int i = 0; i < n_iter; i++) {
         const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
         uint32_t bk0[BK_COLS][ROWS];
@@ -234,7 +259,10 @@ br7_kernel(const BrJob* __restrict__ jobs, int njobs, const torus0_t* __restrict
         __syncwarp();
         PHASE_MARK(10);
     }
+    PHASE_FLUSH
+    CTA_STAMP(2);
     if (valid) br7_epilogue<G>(sm, g, q, lane, ubuf + (size_t)job * U_STRIDE);
+    CTA_STAMP(3);
 }
 
 
@@ -445,6 +473,7 @@ br6_kernel(const BrJob* __restrict__ jobs, int njobs, const torus0_t* __restrict
         __syncthreads();
         PHASE_MARK(22);
     }
+    PHASE_FLUSH
     cluster_wait();
     br6_epilogue(sm, q, tid, ubuf + (size_t)job * U_STRIDE);
 }
@@ -709,6 +738,7 @@ struct b200fhe_ctx {
     int br7_skew = 0;      // start delay between consecutive groups, SM cycles
     NttTables* tab = nullptr;
     tw_t* d_tw2f = nullptr;
+    uint32_t* d_r4 = nullptr;       // digit x twiddle tables of the first two forward stages (br7_kernel)
     tw_t* d_tw2i = nullptr;
     tw_t* d_twfull = nullptr;       // [2][1024] psi_rev and inverse (br8_kernel)
 #ifndef B200FHE_80BIT
@@ -908,7 +938,7 @@ static int br7_launch(b200fhe_ctx* c, int njobs, const torus0_t* arena, uint32_t
 {
     const int grid = (njobs + G - 1) / G;
     br7_kernel<G, J><<<grid, 64 * G, Br7Smem<G>::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_tw2f,
-                                                                     c->d_tw2i, ubuf, N0, c->br7_skew);
+                                                                     c->d_tw2i, c->d_r4, ubuf, N0, c->br7_skew);
     CK(cudaGetLastError());
     c->launches++;
     return 0;
@@ -1149,6 +1179,8 @@ int b200fhe_create(b200fhe_ctx** out, int device)
     CK(cudaMalloc(&c->d_tw2i, sizeof(c->tab->tw2i)));
     CK(cudaMemcpyAsync(c->d_tw2f, c->tab->tw2f, sizeof(c->tab->tw2f), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_tw2i, c->tab->tw2i, sizeof(c->tab->tw2i), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMalloc(&c->d_r4, sizeof(c->tab->r4)));
+    CK(cudaMemcpyAsync(c->d_r4, c->tab->r4, sizeof(c->tab->r4), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMalloc(&c->d_twfull, 2 * sizeof(c->tab->fwd)));
     CK(cudaMemcpyAsync(c->d_twfull, c->tab->fwd, sizeof(c->tab->fwd), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_twfull + 1024, c->tab->inv, sizeof(c->tab->inv), cudaMemcpyHostToDevice, c->stream));
@@ -1179,6 +1211,7 @@ void b200fhe_destroy(b200fhe_ctx* c)
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tw2f);
     cudaFree(c->d_tw2i);
+    cudaFree(c->d_r4);
     cudaFree(c->d_twfull);
 #ifndef B200FHE_80BIT
     cudaFree(c->d_blocktw);
@@ -1905,6 +1938,10 @@ int b200fhe_test_read_bk_ntt(b200fhe_ctx* c, uint32_t* out_host, size_t first_i,
 
 #ifdef B200FHE_PHASE_TIMING
 // debug builds only: read and clear the per-phase cycle counters (two observer warps x 32 marks)
+extern "C" int b200fhe_debug_cta_ns(unsigned long long* out)
+{
+    return cudaMemcpyFromSymbol(out, g_cta_ns, sizeof(unsigned long long) * 4096) == cudaSuccess ? 0 : -1;
+}
 extern "C" int b200fhe_debug_phase_cycles(unsigned long long* out, int clear)
 {
     if (cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 64) != cudaSuccess) return -1;

@@ -32,10 +32,11 @@ struct Br7Smem {
     static constexpr int DBUF_WORDS = G * ROWS * STILE_WORDS;
     static constexpr int ABAR_HALFS = G * SLOT_STRIDE;
     static constexpr size_t BYTES =
-        (size_t)DBUF_WORDS * 4 + 2 * (size_t)TW2_LEN * sizeof(tw_t) + (size_t)ABAR_HALFS * 2;
+        (size_t)DBUF_WORDS * 4 + 2 * (size_t)TW2_LEN * sizeof(tw_t) + (size_t)R4_WORDS * 4 + (size_t)ABAR_HALFS * 2;
     uint32_t* dbuf;
     tw_t* tw2f;
     tw_t* tw2i;
+    uint32_t* r4;    // digit x twiddle tables of the first two forward stages (ntt_warp.h fwd_start_r4_group)
     uint16_t* abar;
     B200_HD void carve(void* base)
     {
@@ -46,6 +47,8 @@ struct Br7Smem {
         p += (size_t)TW2_LEN * sizeof(tw_t);
         tw2i = reinterpret_cast<tw_t*>(p);
         p += (size_t)TW2_LEN * sizeof(tw_t);
+        r4 = reinterpret_cast<uint32_t*>(p);
+        p += (size_t)R4_WORDS * 4;
         abar = reinterpret_cast<uint16_t*>(p);
     }
     B200_HD uint32_t* tile(int g, int row) const { return dbuf + (size_t)(g * ROWS + row) * STILE_WORDS; }
@@ -85,7 +88,8 @@ B200_HD uint32_t br7_dv(const uint32_t* acc, uint32_t base, int a, uint32_t accr
     return ((v ^ neg) - neg) - accr_a + (DEC_OFFSET + DEC_ROUND);
 }
 
-// F12a: digits 1 and 2 -> pass 1 (x2) -> column stores (tiles 3q+1, 3q+2 do not overlap the accumulator copy)
+// F12a: digits 1 and 2 -> stages 0,1 by table look-up -> rest of pass 1 (x2) -> column stores (tiles 3q+1, 3q+2 do not
+// overlap the accumulator copy)
 template <int G>
 B200_HD void br7_fwd12_a(const Br7Smem<G>& sm, int i, int g, int q, int lane, const uint32_t (&accr)[32])
 {
@@ -93,14 +97,14 @@ B200_HD void br7_fwd12_a(const Br7Smem<G>& sm, int i, int g, int q, int lane, co
     const uint32_t abar = sm.abar[g * SLOT_STRIDE + i];
     const uint32_t* acc = sm.acc(g, q);
     const uint32_t base = ((uint32_t)lane - abar) & (2u * N1 - 1);
-    constexpr uint32_t mask = (1u << BGBIT) - 1, bias = P - (1u << (BGBIT - 1));
     B200_UNROLL
-    for (int a = 0; a < 32; a++) {
-        const uint32_t dv = br7_dv(acc, base, a, accr[a]);
-        x1[a] = ((dv >> (32 - 2 * BGBIT)) & mask) + bias;
-        x2[a] = ((dv >> (32 - 3 * BGBIT)) & mask) + bias;
+    for (int k = 0; k < 8; k++) {
+        const uint32_t d0 = br7_dv(acc, base, k, accr[k]), d1 = br7_dv(acc, base, k + 8, accr[k + 8]);
+        const uint32_t d2 = br7_dv(acc, base, k + 16, accr[k + 16]), d3 = br7_dv(acc, base, k + 24, accr[k + 24]);
+        fwd_start_r4_group<32 - 2 * BGBIT>(sm.r4, d0, d1, d2, d3, x1[k], x1[k + 8], x1[k + 16], x1[k + 24]);
+        fwd_start_r4_group<32 - 3 * BGBIT>(sm.r4, d0, d1, d2, d3, x2[k], x2[k + 8], x2[k + 16], x2[k + 24]);
     }
-    fwd_pass1_x2(x1, x2);
+    fwd_pass1_tail_x2(x1, x2);
     stile_store_col(sm.tile(g, q * GL + 1), x1, lane);
     stile_store_col(sm.tile(g, q * GL + 2), x2, lane);
 }
@@ -124,10 +128,13 @@ B200_HD void br7_fwd0_a(const Br7Smem<G>& sm, int i, int g, int q, int lane, con
     const uint32_t abar = sm.abar[g * SLOT_STRIDE + i];
     const uint32_t* acc = sm.acc(g, q);
     const uint32_t base = ((uint32_t)lane - abar) & (2u * N1 - 1);
-    constexpr uint32_t mask = (1u << BGBIT) - 1, bias = P - (1u << (BGBIT - 1));
     B200_UNROLL
-    for (int a = 0; a < 32; a++) x0[a] = ((br7_dv(acc, base, a, accr[a]) >> (32 - BGBIT)) & mask) + bias;
-    fwd_pass1(x0);
+    for (int k = 0; k < 8; k++) {
+        const uint32_t d0 = br7_dv(acc, base, k, accr[k]), d1 = br7_dv(acc, base, k + 8, accr[k + 8]);
+        const uint32_t d2 = br7_dv(acc, base, k + 16, accr[k + 16]), d3 = br7_dv(acc, base, k + 24, accr[k + 24]);
+        fwd_start_r4_group<32 - BGBIT>(sm.r4, d0, d1, d2, d3, x0[k], x0[k + 8], x0[k + 16], x0[k + 24]);
+    }
+    fwd_pass1_tail(x0);
 }
 template <int G>
 B200_HD void br7_fwd0_b(const Br7Smem<G>& sm, int g, int q, int lane, const uint32_t (&x0)[32])

@@ -30,6 +30,8 @@ namespace b200 {
 constexpr int TILE_ROW = 36;                 // padded row pitch in words
 constexpr int TILE_WORDS = 32 * TILE_ROW;    // 1152 words = 4608 B per polynomial tile
 constexpr int TW2_LEN = 31 * 32;             // lane-dependent twiddles per direction
+constexpr int R4_DIGITS = 1 << BGBIT;        // entries per table of the table-driven first two forward stages
+constexpr int R4_WORDS = 5 * R4_DIGITS;
 
 B200_HD int tile_idx(int a, int b) { return a * TILE_ROW + b; }
 B200_HD int tile_of_j(int j) { return (j >> 5) * TILE_ROW + (j & 31); }
@@ -43,6 +45,7 @@ struct NttTables {
     tw_t tw2f[TW2_LEN];  // lane-dependent forward table
     tw_t tw2i[TW2_LEN];  // lane-dependent inverse table
     tw_t bk_scale;       // 2^32 * N^-1 mod p: folded into the NTT-domain bootstrapping key
+    uint32_t r4[R4_WORDS];  // products of the 2^Bgbit possible digits with the twiddles of forward stages 0 and 1 (fwd_start_r4)
 };
 
 inline tw_t h_twf_u[32];
@@ -98,6 +101,17 @@ inline void ntt_tables_init(NttTables& t)
             }
     const uint32_t two32 = (uint32_t)((1ull << 32) % P);
     t.bk_scale = make_tw(mod_mul(two32, mod_inv(1024)));
+    // fwd_start_r4: digit field value i stands for the digit i - Bg/2; tables E, A, B, C, D of its products, exact in [0, p)
+    const uint32_t w1 = t.fwd[1].w, w2 = t.fwd[2].w, w3 = t.fwd[3].w;
+    for (uint32_t i = 0; i < (uint32_t)R4_DIGITS; i++) {
+        const uint32_t half = R4_DIGITS / 2, d = i >= half ? i - half : P - (half - i);
+        const uint32_t m31 = mod_mul(mod_mul(w3, w1), d);
+        t.r4[0 * R4_DIGITS + i] = mod_mul(w1, d);
+        t.r4[1 * R4_DIGITS + i] = mod_mul(w2, d);
+        t.r4[2 * R4_DIGITS + i] = mod_mul(mod_mul(w2, w1), d);
+        t.r4[3 * R4_DIGITS + i] = mod_mul(w3, d);
+        t.r4[4 * R4_DIGITS + i] = m31 ? P - m31 : 0u;
+    }
 }
 
 // ---- register stages -------------------------------------------------------------------
@@ -342,6 +356,45 @@ B200_HD void inv_pass2_x2(B200_X2)
     gs_stage2<2, 1>(x0, x1, [](int g) { return twi_u(4 + g); });
     gs_stage2<1, 1>(x0, x1, [](int g) { return twi_u(2 + g); });
     gs_stage2<0, 1>(x0, x1, [](int g) { return twi_u(1 + g); });
+}
+
+// ---- table-driven first two forward stages ------------------------------------------------
+// The inputs of a forward transform are gadget digits: 2^Bgbit possible values.  Stages 0 and 1 only combine four of
+// them (registers k, k+8, k+16, k+24) with the three twiddles w1, w2, w3 = psi_rev[1..3]:
+//   z[k]    = d0 + w1 d2 + w2 d1 + w2 w1 d3        z[k+8]  = d0 + w1 d2 - (w2 d1 + w2 w1 d3)
+//   z[k+16] = d0 - w1 d2 + w3 d1 - w3 w1 d3        z[k+24] = d0 - w1 d2 - (w3 d1 - w3 w1 d3)
+// so the four Shoup multiplications of a group become five look-ups in tables of 2^Bgbit exact residues
+// (NttTables::r4 = E | A | B | C | D; a shared-memory bank holds two entries of a 64-entry table, so a warp-wide look-up
+// is at most two wavefronts).  Outputs are < 4p + Bg/2 < 5p: the bound stage 1 leaves in the lazy-range schedule above,
+// and congruent mod p to what ct_stage<0>, ct_stage<1> produce.  SHIFT = bit position of the digit field in dv.
+template <int SHIFT>
+B200_HD void fwd_start_r4_group(const uint32_t* r4, uint32_t dv0, uint32_t dv1, uint32_t dv2, uint32_t dv3, uint32_t& z0,
+                                uint32_t& z1, uint32_t& z2, uint32_t& z3)
+{
+    constexpr uint32_t M = R4_DIGITS - 1;
+    const uint32_t i0 = (dv0 >> SHIFT) & M, i1 = (dv1 >> SHIFT) & M, i2 = (dv2 >> SHIFT) & M, i3 = (dv3 >> SHIFT) & M;
+    const uint32_t X0 = i0 + (P - R4_DIGITS / 2);
+    const uint32_t E = r4[i2];
+    const uint32_t T1 = r4[R4_DIGITS + i1] + r4[2 * R4_DIGITS + i3];
+    const uint32_t T3 = r4[3 * R4_DIGITS + i1] + r4[4 * R4_DIGITS + i3];
+    const uint32_t u0 = X0 + E, u2 = X0 - E + P;
+    z0 = u0 + T1;
+    z1 = u0 - T1 + P2;
+    z2 = u2 + T3;
+    z3 = u2 - T3 + P2;
+}
+// stages 2..4 of pass 1 (after fwd_start_r4_group filled the registers)
+B200_HD void fwd_pass1_tail(uint32_t (&x)[32])
+{
+    ct_stage<2, 0>(x, [](int g) { return twf_u(4 + g); });
+    ct_stage<3, 1>(x, [](int g) { return twf_u(8 + g); });
+    ct_stage<4, 0>(x, [](int g) { return twf_u(16 + g); });
+}
+B200_HD void fwd_pass1_tail_x2(B200_X2)
+{
+    ct_stage2<2, 0>(x0, x1, [](int g) { return twf_u(4 + g); });
+    ct_stage2<3, 1>(x0, x1, [](int g) { return twf_u(8 + g); });
+    ct_stage2<4, 0>(x0, x1, [](int g) { return twf_u(16 + g); });
 }
 
 // ---- XOR-swizzled tile (br7_kernel): 32 x 32 words with NO row padding.  Element (a, b) lives at

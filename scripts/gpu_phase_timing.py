@@ -29,7 +29,9 @@ NAMES = {
         "key prefetch + cta bar", "pointwise", "cta bar", "inv01_a", "inv01_b", "inv2_a", "inv2_b (+acc)"],
 }
 out = {}
-for variant, nb in ((6, 74), (7, 1184)):
+CASES = [tuple(int(x) for x in c.split(":")) for c in os.environ.get("PT_CASES", "6:74,7:1184").split(",")]
+TAG = os.environ.get("PT_TAG", "")
+for variant, nb in CASES:
     ctx.set_kernel_variant(variant)
     for rep in range(2):
         ctx.gate_batch(ops[:nb], ids[:nb], ids[N:N + nb], None, ids[2 * N:2 * N + nb]); ctx.sync()
@@ -38,13 +40,26 @@ for variant, nb in ((6, 74), (7, 1184)):
     ctx.gate_batch(ops[:nb], ids[:nb], ids[N:N + nb], None, ids[2 * N:2 * N + nb]); ctx.sync()
     ms = ctx.last_batch_ms()[0]
     raw.b200fhe_debug_phase_cycles(buf, 1)
-    cyc = np.array(list(buf), dtype=np.float64).reshape(2, 32) / 636.0
+    rawc = np.array(list(buf), dtype=np.float64).reshape(2, 32)
+    print(f"{TAG} variant {variant}: loop of the first warp = {rawc[0, 30]:.0f} cycles in {rawc[0, 31]:.0f} ns "
+          f"-> {rawc[0, 30] / max(rawc[0, 31], 1) * 1e3:.0f} MHz")
+    if variant == 7:
+        cb = (ctypes.c_ulonglong * 4096)()
+        raw.b200fhe_debug_cta_ns(cb)
+        ct = np.array(list(cb), dtype=np.float64).reshape(1024, 4)[: (nb + 7) // 8]
+        t0 = ct[:, 0].min()
+        for k, nm in enumerate(("kernel entry", "loop start", "loop end", "exit")):
+            print(f"{TAG}   CTA {nm:12s}: min {(ct[:, k].min() - t0) / 1e6:8.3f} ms  max {(ct[:, k].max() - t0) / 1e6:8.3f} ms")
+    cyc = rawc / 636.0
+    cyc[:, 30:] = 0
+    got = ctx.download(ids[2 * N:2 * N + nb])
+    assert np.array_equal(O.decrypt_bits(keys, got), 1 - (pa[:nb] & pb[:nb])), "wrong bits"
     names = NAMES[variant]
-    print(f"variant {variant}, {nb} jobs: {ms:.3f} ms per launch (instrumented build); cycles per CMUX step")
+    print(f"{TAG} variant {variant}, {nb} jobs: {ms:.3f} ms per launch (instrumented build); cycles per CMUX step")
     for k, nm in enumerate(names):
         print(f"  {k:2d} {nm:40s} first warp {cyc[0, k]:8.0f}   last warp {cyc[1, k]:8.0f}")
     print(f"     {'total':40s} first warp {cyc[0].sum():8.0f}   last warp {cyc[1].sum():8.0f}", flush=True)
     out[str(variant)] = {"jobs": nb, "ms": ms, "phases": names, "first_warp": cyc[0, :len(names)].tolist(),
                          "last_warp": cyc[1, :len(names)].tolist()}
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "phase_timing.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"phase_timing{TAG}.json"), "w"), indent=1)

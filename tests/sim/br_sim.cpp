@@ -285,6 +285,7 @@ static void sim_br7_cta(const BrJob* jobs, int njobs, int cta, const torus0_t* a
     sm.carve(smem.data());
     std::memcpy(sm.tw2f, g_tab.tw2f, sizeof(g_tab.tw2f));
     std::memcpy(sm.tw2i, g_tab.tw2i, sizeof(g_tab.tw2i));
+    std::memcpy(sm.r4, g_tab.r4, sizeof(g_tab.r4));
     struct Regs {
         uint32_t accr[32], x0[32];
     };

@@ -760,6 +760,8 @@ struct b200fhe_ctx {
     uint32_t* d_unstage = nullptr;  // [cap][320]
     uint32_t* d_kspart = nullptr;   // [KS_SPLIT_MAX_GATES][KS_SPLIT][2][320] partial sums of the split key switch
     cudaEvent_t ev_staged = nullptr, ev_t[3] = {nullptr, nullptr, nullptr};
+    uint8_t* d_stage = nullptr;  // landing buffer of large uploads (packed rows), repacked into slots on the device
+    size_t stage_bytes = 0;
     bool staged_pending = false, timed = false;
     // per-segment timing of the most recent launch plan (see plan_rotation)
     cudaEvent_t ev_seg[BR_MAX_SEGMENTS + 1] = {};
@@ -1231,6 +1233,7 @@ void b200fhe_destroy(b200fhe_ctx* c)
     cudaFree(c->d_kspart);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     cudaEventDestroy(c->ev_staged);
+    cudaFree(c->d_stage);
     for (auto& e : c->ev_t) cudaEventDestroy(e);
     for (auto& e : c->ev_seg) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -1340,15 +1343,42 @@ static int check_slots(b200fhe_ctx* c, const uint32_t* ids, size_t n)
 }
 
 // copies runs of consecutive slot ids with one strided copy each
+// packed rows [n][TLWE0_LEN] -> slots of SLOT_STRIDE elements (one thread per element)
+__global__ void repack_rows_kernel(const torus0_t* __restrict__ packed, torus0_t* __restrict__ slots, size_t n)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n * TLWE0_LEN) slots[(k / TLWE0_LEN) * SLOT_STRIDE + k % TLWE0_LEN] = packed[k];
+}
+
 int b200fhe_upload(b200fhe_ctx* c, const uint32_t* ids, const torus0_t* host, size_t n)
 {
     if (!c || (n && (!ids || !host))) return fail("null argument");
     if (set_dev(c) || check_slots(c, ids, n)) return 1;
+    constexpr size_t ROW = TLWE0_LEN * sizeof(torus0_t);
     for (size_t i = 0; i < n;) {
         size_t j = i + 1;
         while (j < n && ids[j] == ids[j - 1] + 1) j++;
-        CK(cudaMemcpy2DAsync(c->d_arena + (size_t)ids[i] * SLOT_STRIDE, SLOT_BYTES, host + i * TLWE0_LEN,
-                             TLWE0_LEN * sizeof(torus0_t), TLWE0_LEN * sizeof(torus0_t), j - i, cudaMemcpyHostToDevice, c->stream));
+        const size_t rows = j - i;
+        torus0_t* dst = c->d_arena + (size_t)ids[i] * SLOT_STRIDE;
+        if (rows >= 256) {
+            // a strided 2-D copy of 1274-byte rows runs at ~9 GB/s over PCIe; one contiguous copy (~50 GB/s) into a
+            // landing buffer plus a device-side repack is 4x faster for whole batches
+            if (c->stage_bytes < rows * ROW) {
+                CK(cudaStreamSynchronize(c->stream));
+                cudaFree(c->d_stage);
+                c->d_stage = nullptr;
+                c->stage_bytes = 0;
+                CK(cudaMalloc(&c->d_stage, rows * ROW));
+                c->stage_bytes = rows * ROW;
+            }
+            CK(cudaMemcpyAsync(c->d_stage, host + i * TLWE0_LEN, rows * ROW, cudaMemcpyHostToDevice, c->stream));
+            const size_t elems = rows * TLWE0_LEN;
+            repack_rows_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, c->stream>>>(
+                reinterpret_cast<const torus0_t*>(c->d_stage), dst, rows);
+            CK(cudaGetLastError());
+        } else {
+            CK(cudaMemcpy2DAsync(dst, SLOT_BYTES, host + i * TLWE0_LEN, ROW, ROW, rows, cudaMemcpyHostToDevice, c->stream));
+        }
         i = j;
     }
     return 0;
@@ -1541,6 +1571,9 @@ int b200fhe_gates_host(b200fhe_ctx* c, const uint8_t* opcode, const torus0_t* in
     if (!opcode || !out_host) return fail("null argument");
     if (c->n_slots < 4 * n) return fail("arena too small for b200fhe_gates_host (needs 4*n slots)");
     if (set_dev(c)) return 1;
+    // Copies and evaluation run back to back on the context's stream.  Overlapping them in chunks was measured and is
+    // slower (profiles/r02_host_path.md): the key switch of a 2368-gate chunk streams the 27 MB key through L2 for a
+    // quarter of the gates, which costs more than the 0.6 ms of copies it hides.
     std::vector<uint32_t> ids(4 * n);
     for (size_t i = 0; i < 4 * n; i++) ids[i] = (uint32_t)i;
     const torus0_t* ins[3] = {in0_host, in1_host, in2_host};

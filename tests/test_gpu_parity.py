@@ -169,6 +169,22 @@ def test_empty_and_single_and_ragged_batches(gpu_ctx, keys):
         assert np.array_equal(got, O.gate_batch(keys, ops, ca, cb))
 
 
+def test_large_host_batch_through_the_staged_upload(gpu_ctx, keys):
+    """Uploads of >= 256 contiguous slots land packed in a device buffer and are repacked into slots by a kernel
+    (b200fhe_upload); a mixed-opcode batch of several waves, ragged at the end, decrypts right everywhere and is
+    ciphertext-exact on a strided sample."""
+    n = 2 * 2368 + 77
+    rng = np.random.default_rng(77)
+    names = ["NAND", "XOR", "ANDNY", "MUX", "NOT", "OR"]
+    ops = np.array([O.OPS[names[i]] for i in rng.integers(0, len(names), n)], np.uint8)
+    (pa, pb, pc), (ca, cb, cc) = fresh(keys, n, 78)
+    gpu_ctx.arena_alloc(4 * n)
+    got = gpu_ctx.gates_host(ops, ca, cb, cc)
+    assert np.array_equal(O.decrypt_bits(keys, got), O.plain_gate_vec(ops, pa, pb, pc))
+    pick = np.concatenate([np.arange(0, n, 211), [2367, 2368, 4735, 4736, n - 1]])
+    assert np.array_equal(got[pick], O.gate_batch(keys, ops[pick], ca[pick], cb[pick], cc[pick], nthreads=8))
+
+
 def test_resident_slots_and_dff_tick(gpu_ctx, keys):
     # a 3-stage shift register: Q2 <- Q1 <- Q0 <- D, all ticking at once (iyokan.hpp:1395-1402)
     (bits, _, _), (c, _, _) = fresh(keys, 4, 9)

@@ -610,6 +610,28 @@ ks_kernel(const KsJob* __restrict__ jobs, const uint32_t* __restrict__ ubuf,
     }
 }
 
+// Wide frontiers: eight gates per CTA, one warp per gate, key rows shared through L1 (ks_phases.h)
+__global__ void __launch_bounds__(32 * KS8_GATES, 4)
+ks8_kernel(const KsJob* __restrict__ jobs, int njobs, const uint32_t* __restrict__ ubuf,
+           const uint32_t* __restrict__ ksk_words, torus0_t* __restrict__ arena)
+{
+    __shared__ uint16_t codes[KS8_GATES][N1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gate = blockIdx.x * KS8_GATES + warp;
+    const bool valid = gate < njobs;
+    const KsJob job = jobs[valid ? gate : njobs - 1];  // surplus warps repeat the last gate: barriers stay uniform
+    for (int i = lane; i < N1; i += 32) codes[warp][i] = ks_code(ubuf, job, i);
+    const uint32_t b = ks_b_rounded(ubuf, job);
+    uint32_t lo[2 * KS8_PAIRS], hi[2 * KS8_PAIRS];
+#pragma unroll
+    for (int k = 0; k < 2 * KS8_PAIRS; k++) lo[k] = hi[k] = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < N1; i0 += KS8_SYNC) {
+        ks8_accumulate(ksk_words, codes[warp], i0, i0 + KS8_SYNC, lane, lo, hi);
+        __syncthreads();
+    }
+    if (valid) ks8_store(reinterpret_cast<uint32_t*>(arena + (size_t)job.out * SLOT_STRIDE), lo, hi, b, job.post, lane);
+}
 
 // Narrow frontiers: one key switch split over KS_SPLIT CTAs (256 coefficients each) + a tiny combine
 // kernel, so that a level of a few dozen gates uses all SMs for its key switch as well.
@@ -736,6 +758,7 @@ struct b200fhe_ctx {
     bool autotune = true;  // pick (variant, G) per batch size unless the caller pinned them
     int br7_group = 8;     // jobs per barrier group of br7_kernel (8 = CTA-wide pointwise stage, 4 or 2 = skewed groups)
     int br7_skew = 0;      // start delay between consecutive groups, SM cycles
+    int ks8_min = 1400;    // frontiers of at least this many key switches take ks8_kernel (8 gates per CTA)
     NttTables* tab = nullptr;
     tw_t* d_tw2f = nullptr;
     uint32_t* d_r4 = nullptr;       // digit x twiddle tables of the first two forward stages (br7_kernel)
@@ -1110,6 +1133,9 @@ static int ks_dispatch(b200fhe_ctx* c, size_t nks, const KsJob* d_jobs, const ui
         ks_split_kernel<<<(unsigned)(nks * KS_SPLIT), dim3(KS_THREADS, KS_GROUPS), 0, c->stream>>>(d_jobs, ubuf, ksk, c->d_kspart);
         ks_combine_kernel<<<(unsigned)nks, KS_THREADS, 0, c->stream>>>(d_jobs, ubuf, c->d_kspart, arena);
         c->launches += 2;
+    } else if (nks >= (size_t)c->ks8_min) {
+        ks8_kernel<<<(unsigned)((nks + KS8_GATES - 1) / KS8_GATES), 32 * KS8_GATES, 0, c->stream>>>(d_jobs, (int)nks, ubuf, ksk, arena);
+        c->launches++;
     } else {
         ks_kernel<<<(unsigned)nks, dim3(KS_THREADS, KS_GROUPS), 0, c->stream>>>(d_jobs, ubuf, ksk, arena);
         c->launches++;
@@ -1171,6 +1197,7 @@ int b200fhe_create(b200fhe_ctx** out, int device)
     for (auto& e : c->ev_seg) CK(cudaEventCreate(&e));
     if (const char* e = getenv("B200FHE_BR7_GROUP")) c->br7_group = atoi(e);   // experiment knobs (profiles/r02_br7_groups.md)
     if (const char* e = getenv("B200FHE_BR7_SKEW")) c->br7_skew = atoi(e);
+    if (const char* e = getenv("B200FHE_KS8_MIN")) c->ks8_min = atoi(e);
     c->tab = new NttTables();
     ntt_tables_init(*c->tab);
     // every transfer goes through the context's non-blocking stream: the legacy default stream is not

@@ -120,6 +120,75 @@ B200_HD uint32_t ks_accumulate(const uint32_t* ksk_words, const uint16_t* codes,
     return (r_lo & 0xFFFFu) | (r_hi << 16);
 }
 
+// ---- wide frontiers: eight gates per CTA, one warp per gate (ks8_kernel) -----------------------------------
+// ks_kernel reads every selected key row from L2 once per gate: 8192 gates x 5376 rows x 1280 B = 56 GB per batch, which
+// is what bounds it (9.4 TB/s of L2 reads).  Here a warp owns a gate and walks the coefficients in the same order as the
+// other seven warps of its CTA (and, loosely, the other CTAs of its SM), a block barrier every KS8_SYNC coefficients
+// keeping them together: a key row one warp pulled into L1 serves the others, L2 traffic drops by the number of gates
+// in step on an SM, and what is left is the two integer adds per 32-bit word.
+// Lane l owns the word pairs {2(l + 32c), 2(l + 32c) + 1}, c < KS8_PAIRS: 64-bit loads, 256 contiguous bytes per warp.
+constexpr int KS8_GATES = 8;
+constexpr int KS8_SYNC = 16;
+constexpr int KS8_PAIRS = KS_THREADS / 64;   // 5 (128-bit flavour), 8 (80-bit)
+static_assert(KS_THREADS % 64 == 0, "a key row is a whole number of 64-bit words per lane");
+struct Ks8Pair {
+    uint32_t x, y;
+};
+B200_HD Ks8Pair ks8_load_pair(const uint32_t* row, int w)
+{
+#if defined(__CUDA_ARCH__)
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(row + w));
+    return Ks8Pair{v.x, v.y};
+#else
+    return Ks8Pair{row[w], row[w + 1]};
+#endif
+}
+// coefficients [i0, i1) of one gate; codes = the gate's digit codes.  The rows of KS8_BATCH digits are requested together
+// and added afterwards (a warp that waited for each row in turn would spend an L2 round trip per row); a zero digit
+// requests nothing and adds nothing (the digit is warp-uniform).
+constexpr int KS8_BATCH = 3;
+B200_HD void ks8_accumulate(const uint32_t* ksk_words, const uint16_t* codes, int i0, int i1, int lane,
+                            uint32_t (&lo)[2 * KS8_PAIRS], uint32_t (&hi)[2 * KS8_PAIRS])
+{
+    for (int i = i0; i < i1; i++) {
+        const uint32_t code = codes[i];
+        B200_UNROLL
+        for (int jb = 0; jb < KS_T; jb += KS8_BATCH) {
+            Ks8Pair v[KS8_BATCH][KS8_PAIRS];
+            uint32_t g[KS8_BATCH];
+            B200_UNROLL
+            for (int b = 0; b < KS8_BATCH; b++) {
+                const int j = jb + b;
+                if (j >= KS_T) continue;
+                g[b] = (code >> (2 * (KS_T - 1 - j))) & 3u;
+                if (!g[b]) continue;
+                const uint32_t* row = ksk_words + (size_t)((i * KS_T + j) * 3 + (g[b] - 1)) * KS_THREADS;
+                B200_UNROLL
+                for (int c = 0; c < KS8_PAIRS; c++) v[b][c] = ks8_load_pair(row, 2 * (lane + 32 * c));
+            }
+            B200_UNROLL
+            for (int b = 0; b < KS8_BATCH; b++) {
+                if (jb + b >= KS_T || !g[b]) continue;
+                B200_UNROLL
+                for (int c = 0; c < KS8_PAIRS; c++) {
+                    ks_add(v[b][c].x, lo[2 * c], hi[2 * c]);
+                    ks_add(v[b][c].y, lo[2 * c + 1], hi[2 * c + 1]);
+                }
+            }
+        }
+    }
+}
+B200_HD void ks8_store(uint32_t* out_words, const uint32_t (&lo)[2 * KS8_PAIRS], const uint32_t (&hi)[2 * KS8_PAIRS],
+                       uint32_t b_rounded, uint32_t post, int lane)
+{
+    B200_UNROLL
+    for (int c = 0; c < KS8_PAIRS; c++) {
+        const int w = 2 * (lane + 32 * c);
+        out_words[w] = ks_finish(lo[2 * c], hi[2 * c], b_rounded, post, w);
+        out_words[w + 1] = ks_finish(lo[2 * c + 1], hi[2 * c + 1], b_rounded, post, w + 1);
+    }
+}
+
 // ---- bootstrap-free ops: NOT / COPY / CONST (gate.hpp:32-57) and the DFF tick (iyokan.hpp:1395-1402)
 struct UnaryJob {
     uint32_t src, dst;

@@ -612,6 +612,47 @@ extern "C" void sim_keyswitch(const void* jobs_raw, int njobs, const uint32_t* u
     }
 }
 
+// wide-frontier path: eight gates per CTA, one warp per gate (ks8_kernel)
+extern "C" void sim_keyswitch8(const void* jobs_raw, int njobs, const uint32_t* ubuf, const torus0_t* ksk_dev,
+                               torus0_t* arena)
+{
+    const KsJob* jobs = reinterpret_cast<const KsJob*>(jobs_raw);
+    const int ncta = (njobs + KS8_GATES - 1) / KS8_GATES;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int cta = 0; cta < ncta; cta++) {
+        std::vector<uint16_t> codes((size_t)KS8_GATES * N1);
+        struct Regs {
+            uint32_t lo[2 * KS8_PAIRS], hi[2 * KS8_PAIRS];
+        };
+        std::vector<Regs> regs(32 * KS8_GATES);
+        std::memset(regs.data(), 0, regs.size() * sizeof(Regs));
+        auto jobof = [&](int w) {
+            const int g = cta * KS8_GATES + w;
+            return jobs[g < njobs ? g : njobs - 1];
+        };
+        for (int w = 0; w < KS8_GATES; w++)
+            for (int i = 0; i < N1; i++) codes[(size_t)w * N1 + i] = ks_code(ubuf, jobof(w), i);
+        for (int i0 = 0; i0 < N1; i0 += KS8_SYNC)
+            for (int ww = 0; ww < KS8_GATES; ww++) {
+                const int w = ord(ww, KS8_GATES);
+                for (int l = 0; l < 32; l++) {
+                    Regs& r = regs[w * 32 + ord(l, 32)];
+                    ks8_accumulate(reinterpret_cast<const uint32_t*>(ksk_dev), codes.data() + (size_t)w * N1, i0, i0 + KS8_SYNC,
+                                   ord(l, 32), r.lo, r.hi);
+                }
+            }
+        for (int w = 0; w < KS8_GATES; w++) {
+            if (cta * KS8_GATES + w >= njobs) continue;
+            const KsJob job = jobof(w);
+            for (int l = 0; l < 32; l++) {
+                Regs& r = regs[w * 32 + l];
+                ks8_store(reinterpret_cast<uint32_t*>(arena + (size_t)job.out * SLOT_STRIDE), r.lo, r.hi, ks_b_rounded(ubuf, job),
+                          job.post, l);
+            }
+        }
+    }
+}
+
 // narrow-frontier path: KS_SPLIT CTAs per switch (ks_split_kernel) + ks_combine_kernel
 extern "C" void sim_keyswitch_split(const void* jobs_raw, int njobs, const uint32_t* ubuf, const torus0_t* ksk_dev,
                                     torus0_t* arena)

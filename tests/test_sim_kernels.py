@@ -281,13 +281,18 @@ def test_keyswitch_bit_exact(sim, keys, ksk_dev, golden):
     arena2 = np.full((n, 640), 0xABCD, np.uint16)
     sim.sim_keyswitch_split(p(jobs), n, p(ubuf), p(ksk_dev), p(arena2))
     assert np.array_equal(arena2, arena)
-    # MUX tail: two summed lvl1 samples and + mu after the switch go through both paths alike
+    # wide-frontier path: eight gates per CTA, one warp per gate (the last CTA is ragged unless n is a multiple of 8)
+    arena3 = np.full((n, 640), 0xABCD, np.uint16)
+    sim.sim_keyswitch8(p(jobs), n, p(ubuf), p(ksk_dev), p(arena3))
+    assert np.array_equal(arena3, arena)
+    # MUX tail: two summed lvl1 samples and + mu after the switch go through all paths alike
     mux = np.zeros(1, KSJOB)
     mux["u0"], mux["u1"], mux["out"], mux["post"] = 0, 1, 0, 1 << 13
-    a1, a2 = np.zeros((1, 640), np.uint16), np.zeros((1, 640), np.uint16)
+    a1, a2, a3 = (np.zeros((1, 640), np.uint16) for _ in range(3))
     sim.sim_keyswitch(p(mux), 1, p(ubuf), p(ksk_dev), p(a1))
     sim.sim_keyswitch_split(p(mux), 1, p(ubuf), p(ksk_dev), p(a2))
-    assert np.array_equal(a1, a2) and not np.array_equal(a1[0], arena[0])
+    sim.sim_keyswitch8(p(mux), 1, p(ubuf), p(ksk_dev), p(a3))
+    assert np.array_equal(a1, a2) and np.array_equal(a1, a3) and not np.array_equal(a1[0], arena[0])
 
 
 def run_batch(sim, G, ops, arena, in0, in1, in2, out, bk_ntt_sim, ksk_dev):

@@ -129,6 +129,11 @@ int b200fhe_program_tick(b200fhe_program *prog, const uint32_t *src, const uint3
 int b200fhe_program_exchange(b200fhe_program *prog, size_t first_slot, size_t slots_per_rank);
 int b200fhe_program_finalize(b200fhe_program *prog);
 int b200fhe_program_launch(b200fhe_program *prog); /* asynchronous on the context's stream */
+/* Profiling replay: the same launches issued one recorded step at a time (no graph) with a CUDA event between the
+ * steps; synchronous.  step_ms[k] = device time of the k-th recorded batch / exchange / tick (up to cap entries),
+ * *nsteps = how many were recorded.  What the reference's ProgressGraphMaker samples per node (src/iyokan.hpp:128-278)
+ * is available here per frontier. */
+int b200fhe_program_profile(b200fhe_program *prog, float *step_ms, size_t cap, size_t *nsteps);
 /* any pointer may be NULL.  is_graph = 0 when the capture was refused and the program replays launch by launch */
 int b200fhe_program_info(const b200fhe_program *prog, uint64_t *rotations, uint64_t *launches_per_replay,
                          uint64_t *exchanges, uint64_t *exchanged_slots, int *is_graph, double *model_ms);

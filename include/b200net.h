@@ -86,6 +86,10 @@ size_t b200net_step_gates(const b200net *net, size_t step, int rank, uint32_t *n
 int b200net_step_exchange(const b200net *net, size_t step, uint32_t *first_slot, size_t *slots_per_rank);
 int b200net_schedule_info(const b200net *net, size_t *steps, size_t *collectives, size_t *exchanged_slots,
                           double *model_ms, int *packed);
+/* One evaluation of the clock like b200net_run, but step by step with device timers (b200fhe_program_profile):
+ * step_ms[s] = time of schedule step s on this rank, its all-gather included (up to cap entries).  Synchronous.
+ * Feeds the per-node time / graph dumps of the front end (the reference's ProgressGraphMaker, src/iyokan.hpp:128-278). */
+int b200net_profile_run(b200net *net, float *step_ms, size_t cap);
 
 #ifdef __cplusplus
 }

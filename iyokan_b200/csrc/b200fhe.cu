@@ -1324,6 +1324,23 @@ int b200fhe_load_keys(b200fhe_ctx* c, const uint32_t* bk_raw, const torus0_t* ks
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaFree(d_raw));
     c->keys = true;
+    if (const char* e = getenv("B200FHE_L2_PERSIST"); e && e[0] == '1') {
+        // experiment (profiles/r02_l2_persist.md): pin the NTT-domain bootstrapping key in L2 across waves
+        int max_persist = 0, max_window = 0;
+        CK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device));
+        CK(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device));
+        const size_t set_aside = std::min(bk_ntt_bytes, (size_t)max_persist);
+        CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.base_ptr = c->d_bk_ntt;
+        attr.accessPolicyWindow.num_bytes = std::min(bk_ntt_bytes, (size_t)max_window);
+        attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)set_aside / (double)attr.accessPolicyWindow.num_bytes);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        CK(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        fprintf(stderr, "b200fhe: L2 persisting window %zu MB (set-aside %zu MB, hit ratio %.2f)\n",
+                attr.accessPolicyWindow.num_bytes >> 20, set_aside >> 20, attr.accessPolicyWindow.hitRatio);
+    }
     return calibrate(c);
 }
 
@@ -1670,26 +1687,27 @@ struct b200fhe_program {
     double model_ms = 0.0;
 };
 
-static int program_issue(b200fhe_program* p)
+static int program_issue_step(b200fhe_program* p, const ProgStep& st)
 {
     b200fhe_ctx* c = p->c;
     uint32_t* aw = reinterpret_cast<uint32_t*>(c->d_arena);
-    for (const ProgStep& st : p->steps) {
-        if (st.kind == 2) {
-            if (exchange_issue(c, st.first_slot, st.slots_per_rank)) return 1;
-            continue;
-        }
-        if (st.nun) {  // gather, then scatter: every source is read before any destination is written
-            unary_gather_kernel<<<(unsigned)st.nun, KS_THREADS, 0, c->stream>>>(p->d_un + st.un_off, aw, p->d_unstage);
-            unary_scatter_kernel<<<(unsigned)st.nun, KS_THREADS, 0, c->stream>>>(p->d_un + st.un_off, p->d_unstage, aw);
-            CK(cudaGetLastError());
-            c->launches += 2;
-        }
-        if (st.nbr) {
-            if (br_dispatch(c, (int)st.nbr, c->d_arena, p->d_ubuf, p->d_br + st.br_off, false)) return 1;
-            if (ks_dispatch(c, st.nks, p->d_ks + st.ks_off, p->d_ubuf, c->d_arena)) return 1;
-        }
+    if (st.kind == 2) return exchange_issue(c, st.first_slot, st.slots_per_rank);
+    if (st.nun) {  // gather, then scatter: every source is read before any destination is written
+        unary_gather_kernel<<<(unsigned)st.nun, KS_THREADS, 0, c->stream>>>(p->d_un + st.un_off, aw, p->d_unstage);
+        unary_scatter_kernel<<<(unsigned)st.nun, KS_THREADS, 0, c->stream>>>(p->d_un + st.un_off, p->d_unstage, aw);
+        CK(cudaGetLastError());
+        c->launches += 2;
     }
+    if (st.nbr) {
+        if (br_dispatch(c, (int)st.nbr, c->d_arena, p->d_ubuf, p->d_br + st.br_off, false)) return 1;
+        if (ks_dispatch(c, st.nks, p->d_ks + st.ks_off, p->d_ubuf, c->d_arena)) return 1;
+    }
+    return 0;
+}
+static int program_issue(b200fhe_program* p)
+{
+    for (const ProgStep& st : p->steps)
+        if (program_issue_step(p, st)) return 1;
     return 0;
 }
 
@@ -1901,6 +1919,32 @@ int b200fhe_program_launch(b200fhe_program* p)
         return 0;
     }
     return program_issue(p);
+}
+
+int b200fhe_program_profile(b200fhe_program* p, float* step_ms, size_t cap, size_t* nsteps)
+{
+    if (!p) return fail("null program");
+    if (!p->finalized && b200fhe_program_finalize(p)) return 1;
+    b200fhe_ctx* c = p->c;
+    if (set_dev(c)) return 1;
+    const size_t n = p->steps.size();
+    if (nsteps) *nsteps = n;
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    int rc = 0;
+    CK(cudaEventRecord(ev[0], c->stream));
+    for (size_t k = 0; k < n && !rc; k++) {
+        rc = program_issue_step(p, p->steps[k]);
+        if (!rc && cudaEventRecord(ev[k + 1], c->stream) != cudaSuccess) rc = fail("cudaEventRecord failed");
+    }
+    if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail("cudaStreamSynchronize failed");
+    for (size_t k = 0; k < n && !rc; k++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ev[k], ev[k + 1]) != cudaSuccess) rc = fail("cudaEventElapsedTime failed");
+        if (step_ms && k < cap) step_ms[k] = ms;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
 }
 
 int b200fhe_program_info(const b200fhe_program* p, uint64_t* rotations, uint64_t* launches_per_replay, uint64_t* exchanges,

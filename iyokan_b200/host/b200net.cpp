@@ -84,6 +84,7 @@ struct b200net {
         size_t jobs_rep = 0, jobs_shd = 0;
     };
     std::vector<Step> steps;
+    std::vector<uint8_t> step_records;  // per schedule step: how many program steps (batch, exchange) it recorded
     bool compiled = false, packed = false;
     int rank = 0;
     double model_ms = 0.0;
@@ -587,6 +588,7 @@ int b200net_bind_rank(b200net* net, b200fhe_ctx* ctx, int rank, int world, unsig
         return fail(b200fhe_last_error());
     std::vector<uint8_t> op;
     std::vector<uint32_t> a, b, c, o;
+    net->step_records.clear();
     for (const auto& st : net->steps) {
         op.clear(), a.clear(), b.clear(), c.clear(), o.clear();
         auto add = [&](uint32_t g) {
@@ -600,11 +602,17 @@ int b200net_bind_rank(b200net* net, b200fhe_ctx* ctx, int rank, int world, unsig
         for (uint32_t g : st.rep) add(g);
         if (!st.shd.empty())
             for (size_t k = st.cut[rank]; k < st.cut[rank + 1]; k++) add(st.shd[k]);
-        if (!op.empty() &&
-            b200fhe_program_batch(net->run_prog, op.data(), a.data(), b.data(), c.data(), o.data(), op.size()))
-            return fail(b200fhe_last_error());
-        if (!st.shd.empty() && world > 1 && b200fhe_program_exchange(net->run_prog, st.base_shd, st.chunk))
-            return fail(b200fhe_last_error());
+        uint8_t recorded = 0;
+        if (!op.empty()) {
+            if (b200fhe_program_batch(net->run_prog, op.data(), a.data(), b.data(), c.data(), o.data(), op.size()))
+                return fail(b200fhe_last_error());
+            recorded++;
+        }
+        if (!st.shd.empty() && world > 1) {
+            if (b200fhe_program_exchange(net->run_prog, st.base_shd, st.chunk)) return fail(b200fhe_last_error());
+            recorded++;
+        }
+        net->step_records.push_back(recorded);
     }
     if (!net->tick_src.empty() &&
         b200fhe_program_tick(net->tick_prog, net->tick_src.data(), net->tick_dst.data(), net->tick_src.size()))
@@ -612,6 +620,25 @@ int b200net_bind_rank(b200net* net, b200fhe_ctx* ctx, int rank, int world, unsig
     if (b200fhe_program_finalize(net->run_prog) || b200fhe_program_finalize(net->tick_prog))
         return fail(b200fhe_last_error());
     net->compiled = true;
+    return 0;
+}
+
+int b200net_profile_run(b200net* net, float* step_ms, size_t cap)
+{
+    if (!net || !net->ctx) return fail("netlist is not bound to a context");
+    if (!net->compiled) return fail("b200net_profile_run needs b200net_bind_rank");
+    size_t nrec = 0;
+    for (uint8_t r : net->step_records) nrec += r;
+    std::vector<float> rec(nrec, 0.0f);
+    size_t seen = 0;
+    if (b200fhe_program_profile(net->run_prog, rec.data(), rec.size(), &seen)) return fail(b200fhe_last_error());
+    if (seen != nrec) return fail("recorded steps of the program do not match the schedule");
+    size_t k = 0;
+    for (size_t s = 0; s < net->step_records.size(); s++) {
+        float ms = 0;
+        for (uint8_t r = 0; r < net->step_records[s]; r++) ms += rec[k++];
+        if (step_ms && s < cap) step_ms[s] = ms;
+    }
     return 0;
 }
 

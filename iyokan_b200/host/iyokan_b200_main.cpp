@@ -16,12 +16,21 @@
 //
 // Usage (option names of src/main.cpp:100-175):
 //   iyokan-b200 tfhe --blueprint B.toml --evalkey EK -i req.enc -o res.enc -c N [--skip-reset] [--quiet]
+//                    [--snapshot S] [--dump-prefix P --secret-key SK]
+//                    [--dump-time-csv-prefix P] [--dump-graph-json-prefix P] [--dump-graph-dot-prefix P]
+//   iyokan-b200 tfhe --resume S --evalkey EK -o res.enc -c N [...]
 // Multi-GPU (what `--num-gpu N` asks of the reference, src/iyokan_cufhe.cpp:533): one process per GPU, launched N
 // times with RANK / LOCAL_RANK / WORLD_SIZE in the environment (e.g. by torchrun or scripts/launch_ranks.sh); rank 0
 // publishes the communicator id through the file named by B200FHE_ID_FILE (default /tmp/b200fhe_id_<MASTER_PORT>).
 // Every rank evaluates its share of the static schedule (b200net_bind_rank); rank 0 writes the result packet.
-// Snapshot/resume and the plaintext mode live in the Python front end (python -m iyokan_b200).
+// Snapshot / resume (src/main.cpp:116,160-166; TFHEppFrontend::serialize, iyokan_tfhepp.cpp:568-572) store what this
+// front end needs to continue: blueprint path, cycle counter, the request packet and the ciphertext of every node.
+// The per-cycle dumps (--dump-time-csv-prefix / --dump-graph-json-prefix / --dump-graph-dot-prefix, written by
+// ProgressGraphMaker in the reference, src/iyokan.hpp:128-278, iyokan_tfhepp.cpp:538-555) keep the reference's file
+// formats; a node's start / end are the measured window of the schedule step it was evaluated in (b200net_profile_run),
+// since a frontier, not a gate, is the unit of execution here.  The plaintext mode lives in the Python front end.
 #include <chrono>
+#include <filesystem>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -146,14 +155,52 @@ struct Design {
     }
 };
 
+// what --snapshot stores and --resume reads (cereal portable binary, like every other file of the tool chain)
+struct B200Snapshot {
+    std::string blueprintPath;
+    int currentCycle = 0;
+    TFHEPacket req;
+    uint64_t numNodes = 0;
+    std::vector<TLWELvl0> values;  // ciphertext of every node, in node order
+    template <class Archive>
+    void serialize(Archive& ar)
+    {
+        ar(blueprintPath, currentCycle, req, numNodes, values);
+    }
+};
+
+const char* kindName(uint8_t k)
+{
+    switch (k) {
+    case B200FHE_AND: return "AND";
+    case B200FHE_NAND: return "NAND";
+    case B200FHE_ANDNOT: return "ANDNOT";
+    case B200FHE_OR: return "OR";
+    case B200FHE_NOR: return "NOR";
+    case B200FHE_ORNOT: return "ORNOT";
+    case B200FHE_XOR: return "XOR";
+    case B200FHE_XNOR: return "XNOR";
+    case B200FHE_MUX: return "MUX";
+    case B200FHE_NOT: return "NOT";
+    case B200FHE_CONST1: return "CONSTONE";
+    case B200FHE_CONST0: return "CONSTZERO";
+    case B200NET_DFF: return "DFF";
+    case B200NET_INPUT: return "INPUT";
+    case B200NET_OUTPUT: return "WIRE";
+    default: return "?";
+    }
+}
+
 }  // namespace
 
 int main(int argc, char** argv)
 {
-    std::string blueprintPath, evalkeyPath, inPath, outPath;
+    std::string blueprintPath, evalkeyPath, inPath, outPath, snapshotPath, resumePath, dumpPrefix, secretKeyPath;
+    std::string timeCsvPrefix, graphJsonPrefix, graphDotPrefix;
     int numCycles = -1;
     bool skipReset = false, quiet = false, statsJson = false;
-    if (argc < 2 || std::string(argv[1]) != "tfhe") error::die("usage: iyokan-b200 tfhe --blueprint B --evalkey EK -i IN -o OUT -c N");
+    if (argc < 2 || std::string(argv[1]) != "tfhe")
+        error::die("usage: iyokan-b200 tfhe (--blueprint B -i IN | --resume S) --evalkey EK -o OUT -c N");
     for (int i = 2; i < argc; i++) {
         const std::string a = argv[i];
         auto next = [&]() -> std::string {
@@ -165,6 +212,13 @@ int main(int argc, char** argv)
         else if (a == "-i" || a == "--in") inPath = next();
         else if (a == "-o" || a == "--out") outPath = next();
         else if (a == "-c") numCycles = std::stoi(next());
+        else if (a == "--snapshot") snapshotPath = next();
+        else if (a == "--resume") resumePath = next();
+        else if (a == "--dump-prefix") dumpPrefix = next();
+        else if (a == "--secret-key") secretKeyPath = next();
+        else if (a == "--dump-time-csv-prefix") timeCsvPrefix = next();
+        else if (a == "--dump-graph-json-prefix") graphJsonPrefix = next();
+        else if (a == "--dump-graph-dot-prefix") graphDotPrefix = next();
         else if (a == "--skip-reset") skipReset = true;
         else if (a == "--quiet") quiet = true;
         else if (a == "--stats-json") statsJson = true;  // one JSON line on stdout: clock time, schedule, launches (bench.py)
@@ -172,9 +226,19 @@ int main(int argc, char** argv)
         else if (a == "--cpu" || a == "--gpu" || a == "--num-gpu" || a == "--gpu_num" || a == "--sched") next();  // CPU scheduler knobs
         else error::die("unknown option ", a);
     }
-    if (blueprintPath.empty() || evalkeyPath.empty() || inPath.empty() || outPath.empty())
-        error::die("--blueprint, --evalkey, -i and -o are required");
     if (quiet) spdlog::set_level(spdlog::level::err);
+    if (evalkeyPath.empty() || outPath.empty()) error::die("--evalkey and -o are required");
+    B200Snapshot snap;
+    const bool resumed = !resumePath.empty();
+    if (resumed) {
+        if (!blueprintPath.empty() || !inPath.empty()) error::die("--resume excludes --blueprint and -i");
+        readFromArchive(snap, resumePath);
+        blueprintPath = snap.blueprintPath;
+    } else if (blueprintPath.empty() || inPath.empty()) {
+        error::die("--blueprint and -i are required for a new run");
+    }
+    if (!dumpPrefix.empty() && secretKeyPath.empty()) error::die("--dump-prefix needs --secret-key");
+    const bool profiling = !timeCsvPrefix.empty() || !graphJsonPrefix.empty() || !graphDotPrefix.empty();
 
     // ---- the reference's loader: blueprint, netlists, builtin MUX memories ----
     const NetworkBlueprint bp{blueprintPath};
@@ -212,7 +276,8 @@ int main(int argc, char** argv)
     // ---- keys and request, read by the reference's own (cereal) code ----
     const auto ek = readFromArchive<TFHEpp::EvalKey>(evalkeyPath);
     if (!ek.bklvl01 || !ek.iksklvl10) error::die("EvalKey lacks bklvl01 / iksklvl10 (run iyokan-packet genevalkey)");
-    const auto req = readFromArchive<TFHEPacket>(inPath);
+    const TFHEPacket req = resumed ? snap.req : readFromArchive<TFHEPacket>(inPath);
+    const int startCycle = resumed ? snap.currentCycle : 0;
     if (numCycles < 0) numCycles = req.numCycles.value_or(-1);
     if (numCycles < 0) error::die("the number of cycles is given neither by -c nor by the request packet");
 
@@ -290,8 +355,133 @@ int main(int argc, char** argv)
         if (!bp.atPortWidths().count(name)) error::die("Invalid request packet: unknown port @", name);
     }
 
+    // ---- result packet (makeResPacket, iyokan_tfhepp.cpp:176-227) ----
+    auto get = [&](const std::vector<uint32_t>& nodes) {
+        std::vector<TLWELvl0> vals(nodes.size());
+        if (!nodes.empty()) ck(b200net_get(net, nodes.data(), reinterpret_cast<uint16_t*>(vals.data()), nodes.size()), "b200net_get");
+        return vals;
+    };
+    auto makeRes = [&](int cyclesDone) {
+        TFHEPacket res{{}, {}, {}, {}, {}, cyclesDone};
+        for (const auto& [name, width] : bp.atPortWidths()) {
+            // one entry per port bit, written at its own index (makeResPacket resizes to atPortBit + 1,
+            // iyokan_tfhepp.cpp:182-190); bits tied to ground or left unconnected stay trivial 0
+            std::vector<uint32_t> nodes;
+            std::vector<int> bits;
+            for (int b = 0; b < width; b++)
+                if (const auto port = bp.at(name, b); port && port->portLabel.kind == "output") {
+                    nodes.push_back((uint32_t)d.node(*port));
+                    bits.push_back(b);
+                }
+            if (bits.empty()) continue;
+            std::vector<TLWELvl0> vals(bits.back() + 1, trivial(false));
+            const auto got = get(nodes);
+            for (size_t k = 0; k < bits.size(); k++) vals[bits[k]] = got[k];
+            res.bits.emplace(name, std::move(vals));
+        }
+        for (const auto& ram : bp.builtinRAMs()) {
+            const size_t n = (size_t(1) << ram.inAddrWidth) * ram.outRdataWidth;
+            auto nodes = memNodes(ram.name, "ram", "ramdata", n);
+            // A CMUX RAM is updated during the cycle (its image already holds the last cycle's write); the MUX RAM that
+            // stands in for it keeps that value on the cells' D inputs until the next tick: report those.
+            if (ram.type == blueprint::BuiltinRAM::TYPE::CMUX_MEMORY && cyclesDone > 0)
+                for (auto& v : nodes) v = (uint32_t)d.in0[v];
+            res.ramInTLWE.emplace(ram.name, get(nodes));
+        }
+        return res;
+    };
+
     // ---- cycle protocol (TFHEppFrontend::go) ----
-    if (hasReset && !skipReset) {
+    std::vector<uint32_t> allNodes(d.kind.size());
+    for (size_t i = 0; i < allNodes.size(); i++) allNodes[i] = (uint32_t)i;
+    if (resumed) {
+        if (snap.numNodes != d.kind.size() || snap.values.size() != d.kind.size())
+            error::die("snapshot does not belong to this blueprint (", snap.numNodes, " nodes, the blueprint has ", d.kind.size(), ")");
+        std::vector<uint32_t> nodes;  // wires alias their driver and hold no state of their own
+        std::vector<TLWELvl0> vals;
+        for (size_t i = 0; i < d.kind.size(); i++)
+            if (d.kind[i] != B200NET_OUTPUT) nodes.push_back((uint32_t)i), vals.push_back(snap.values[i]);
+        ck(b200net_restore(net, nodes.data(), reinterpret_cast<const uint16_t*>(vals.data()), nodes.size()), "b200net_restore");
+    }
+    std::optional<TFHEpp::SecretKey> secretKey;
+    if (!dumpPrefix.empty()) secretKey = readFromArchive<TFHEpp::SecretKey>(secretKeyPath);
+    // per-node times of a profiled cycle: the window of the schedule step that evaluated the node
+    const size_t numSteps = b200net_num_steps(net);
+    std::vector<int> stepOfNode(d.kind.size(), -1);
+    if (profiling) {
+        std::vector<uint32_t> buf(d.kind.size());
+        for (size_t st = 0; st < numSteps; st++)
+            for (int r = 0; r < world; r++) {
+                const size_t n = b200net_step_gates(net, st, r, buf.data(), buf.size());
+                for (size_t k = 0; k < n; k++) stepOfNode[buf[k]] = (int)st;
+            }
+    }
+    auto dumpProfile = [&](int cycle, std::chrono::system_clock::time_point t0, const std::vector<float>& stepMs) {
+        using namespace utility;
+        using namespace std::chrono;
+        std::vector<system_clock::time_point> begin(numSteps + 1, t0);
+        for (size_t st = 0; st < numSteps; st++)
+            begin[st + 1] = begin[st] + duration_cast<system_clock::duration>(duration<double, std::milli>(stepMs[st]));
+        // nodes in the order they start: inputs, registers and wires at the beginning of the cycle, then step by step
+        std::vector<uint32_t> order(allNodes);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return stepOfNode[x] < stepOfNode[y]; });
+        std::vector<int> index(d.kind.size());
+        for (size_t k = 0; k < order.size(); k++) index[order[k]] = (int)k;
+        auto startOf = [&](uint32_t v) { return stepOfNode[v] < 0 ? t0 : begin[stepOfNode[v]]; };
+        auto endOf = [&](uint32_t v) { return stepOfNode[v] < 0 ? t0 : begin[stepOfNode[v] + 1]; };
+        auto desc = [&](uint32_t v) { return stepOfNode[v] < 0 ? std::string() : fok("step ", stepOfNode[v]); };
+        if (!timeCsvPrefix.empty()) {  // ProgressGraphMaker::dumpTimeCSV
+            auto os = openOfstream(fok(timeCsvPrefix, "-", cycle, ".csv"));
+            for (uint32_t v : order)
+                *os << "\"" << startOf(v) << "\",\"" << endOf(v) << "\",\"" << index[v] << "\",\"" << v << "\",\"" << kindName(d.kind[v])
+                    << "\",\"" << desc(v) << "\"" << std::endl;
+        }
+        const std::vector<int32_t>* ins[3] = {&d.in0, &d.in1, &d.in2};
+        if (!graphJsonPrefix.empty()) {  // ProgressGraphMaker::dumpJSON
+            picojson::object nodes;
+            for (uint32_t v : order) {
+                picojson::object j;
+                j.emplace("start", fok(startOf(v)));
+                j.emplace("end", fok(endOf(v)));
+                j.emplace("index", (double)index[v]);
+                j.emplace("id", (double)v);
+                j.emplace("kind", std::string(kindName(d.kind[v])));
+                j.emplace("desc", desc(v));
+                nodes.emplace(fok(v), j);
+            }
+            picojson::array edges;
+            int ne = 0;
+            for (uint32_t v : allNodes)
+                for (auto in : ins)
+                    if ((*in)[v] >= 0) {
+                        picojson::object j;
+                        j.emplace("index", (double)ne++);
+                        j.emplace("from", (double)(*in)[v]);
+                        j.emplace("to", (double)v);
+                        edges.emplace_back(j);
+                    }
+            picojson::object root;
+            root.emplace("nodes", nodes);
+            root.emplace("edges", edges);
+            *openOfstream(fok(graphJsonPrefix, "-", cycle, ".json")) << picojson::value(root);
+        }
+        if (!graphDotPrefix.empty()) {  // ProgressGraphMaker::dumpDOT
+            auto os = openOfstream(fok(graphDotPrefix, "-", cycle, ".dot"));
+            *os << "digraph progress_graph_maker {" << std::endl << "node [ shape = record ];" << std::endl;
+            for (uint32_t v : order) {
+                *os << "n" << v << " [label = \"{" << kindName(d.kind[v]);
+                if (stepOfNode[v] >= 0) *os << "|" << desc(v);
+                *os << "}\"];" << std::endl;
+            }
+            *os << std::endl;
+            int ne = 0;
+            for (uint32_t v : allNodes)
+                for (auto in : ins)
+                    if ((*in)[v] >= 0) *os << "n" << (*in)[v] << " -> n" << v << " [label = \"" << ne++ << "\"];" << std::endl;
+            *os << "}" << std::endl;
+        }
+    };
+    if (!resumed && hasReset && !skipReset) {
         set(resetNode(), {trivial(true)});
         ck(b200net_run(net), "b200net_run");
     }
@@ -300,9 +490,12 @@ int main(int argc, char** argv)
     const uint64_t launches0 = b200fhe_launch_count(ctx);
     const auto t0 = std::chrono::steady_clock::now();
     for (int c = 0; c < numCycles; c++) {
+        const int cur = startCycle + c;  // cycles count on across --snapshot / --resume (currentCycle_)
+        if (secretKey && rank == 0)      // dumpDecryptedPacket (iyokan_tfhepp.cpp:298-305): the state BEFORE cycle `cur`
+            writeToArchive(utility::fok(dumpPrefix, "-", cur), makeRes(cur).decrypt(*secretKey));
         ck(b200net_tick(net), "b200net_tick");
-        if (c == 0) {
-            if (hasReset) set(resetNode(), {trivial(false)});
+        if (c == 0 && hasReset) set(resetNode(), {trivial(false)});
+        if (cur == 0) {
             for (const auto& ram : bp.builtinRAMs()) {
                 auto it = req.ramInTLWE.find(ram.name);
                 if (it == req.ramInTLWE.end()) continue;
@@ -319,11 +512,19 @@ int main(int argc, char** argv)
                 const auto port = bp.at(name, b);
                 if (!port || port->portLabel.kind != "input") continue;
                 nodes.push_back((uint32_t)d.node(*port));
-                vals.push_back(stream.at((size_t(width) * c + b) % stream.size()));
+                vals.push_back(stream.at((size_t(width) * cur + b) % stream.size()));
             }
             set(nodes, vals);
         }
-        ck(b200net_run(net), "b200net_run");
+        if (profiling) {
+            std::vector<float> stepMs(numSteps, 0.0f);
+            if (b200fhe_sync(ctx)) error::die("b200fhe_sync: ", b200fhe_last_error());
+            const auto tc = std::chrono::system_clock::now();
+            ck(b200net_profile_run(net, stepMs.data(), stepMs.size()), "b200net_profile_run");
+            if (rank == 0) dumpProfile(cur, tc, stepMs);
+        } else {
+            ck(b200net_run(net), "b200net_run");
+        }
     }
     if (b200fhe_sync(ctx)) error::die("b200fhe_sync: ", b200fhe_last_error());
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -343,39 +544,17 @@ int main(int argc, char** argv)
         std::fflush(stdout);
     }
 
-    // ---- result packet (makeResPacket, iyokan_tfhepp.cpp:176-227) ----
-    auto get = [&](const std::vector<uint32_t>& nodes) {
-        std::vector<TLWELvl0> vals(nodes.size());
-        if (!nodes.empty()) ck(b200net_get(net, nodes.data(), reinterpret_cast<uint16_t*>(vals.data()), nodes.size()), "b200net_get");
-        return vals;
-    };
-    TFHEPacket res{{}, {}, {}, {}, {}, numCycles};
-    for (const auto& [name, width] : bp.atPortWidths()) {
-        // one entry per port bit, written at its own index (makeResPacket resizes to atPortBit + 1,
-        // iyokan_tfhepp.cpp:182-190); bits tied to ground or left unconnected stay trivial 0
-        std::vector<uint32_t> nodes;
-        std::vector<int> bits;
-        for (int b = 0; b < width; b++)
-            if (const auto port = bp.at(name, b); port && port->portLabel.kind == "output") {
-                nodes.push_back((uint32_t)d.node(*port));
-                bits.push_back(b);
-            }
-        if (bits.empty()) continue;
-        std::vector<TLWELvl0> vals(bits.back() + 1, trivial(false));
-        const auto got = get(nodes);
-        for (size_t k = 0; k < bits.size(); k++) vals[bits[k]] = got[k];
-        res.bits.emplace(name, std::move(vals));
-    }
-    for (const auto& ram : bp.builtinRAMs()) {
-        const size_t n = (size_t(1) << ram.inAddrWidth) * ram.outRdataWidth;
-        auto nodes = memNodes(ram.name, "ram", "ramdata", n);
-        // A CMUX RAM is updated during the cycle (its image already holds the last cycle's write); the MUX RAM that
-        // stands in for it keeps that value on the cells' D inputs until the next tick: report those.
-        if (ram.type == blueprint::BuiltinRAM::TYPE::CMUX_MEMORY && numCycles > 0)
-            for (auto& v : nodes) v = (uint32_t)d.in0[v];
-        res.ramInTLWE.emplace(ram.name, get(nodes));
-    }
+    const TFHEPacket res = makeRes(startCycle + numCycles);
     if (rank == 0) writeToArchive(outPath, res);
+    if (!snapshotPath.empty() && rank == 0) {
+        B200Snapshot out;
+        out.blueprintPath = std::filesystem::absolute(blueprintPath).string();
+        out.currentCycle = startCycle + numCycles;
+        out.req = req;
+        out.numNodes = d.kind.size();
+        out.values = get(allNodes);
+        writeToArchive(snapshotPath, out);
+    }
     b200net_destroy(net);
     b200fhe_destroy(ctx);
     return 0;

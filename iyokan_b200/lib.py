@@ -91,6 +91,7 @@ def load() -> ctypes.CDLL:
         "b200fhe_program_exchange": (ci, [vp, sz, sz]),
         "b200fhe_program_finalize": (ci, [vp]),
         "b200fhe_program_launch": (ci, [vp]),
+        "b200fhe_program_profile": (ci, [vp, vp, sz, vp]),
         "b200fhe_program_info": (ci, [vp, vp, vp, vp, vp, vp, vp]),
         "b200fhe_comm_unique_id": (ci, [vp]),
         "b200fhe_comm_init": (ci, [vp, ci, ci, vp]),
@@ -117,7 +118,7 @@ EXPORTS = [
     "b200fhe_last_batch_ms", "b200fhe_last_batch_segments", "b200fhe_plan_rotation", "b200fhe_plan_ms", "b200fhe_plan_table", "b200fhe_stream", "b200fhe_test_bootstrap_lvl1", "b200fhe_test_keyswitch",
     "b200fhe_test_read_bk_ntt",
     "b200fhe_program_create", "b200fhe_program_destroy", "b200fhe_program_batch", "b200fhe_program_tick",
-    "b200fhe_program_exchange", "b200fhe_program_finalize", "b200fhe_program_launch", "b200fhe_program_info",
+    "b200fhe_program_exchange", "b200fhe_program_finalize", "b200fhe_program_launch", "b200fhe_program_profile", "b200fhe_program_info",
     "b200fhe_comm_unique_id", "b200fhe_comm_init", "b200fhe_comm_rank", "b200fhe_comm_world", "b200fhe_exchange",
 ]
 

@@ -213,6 +213,7 @@ def load_net():
             "b200net_num_steps": (sz, [vp]), "b200net_step_jobs": (sz, [vp, sz, vp]),
             "b200net_schedule_info": (ci, [vp, vp, vp, vp, vp, vp]),
             "b200net_step_gates": (sz, [vp, sz, ci, vp, sz]), "b200net_step_exchange": (ci, [vp, sz, vp, vp]),
+            "b200net_profile_run": (ci, [vp, vp, sz]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)
@@ -227,7 +228,7 @@ NET_EXPORTS = [
     "b200net_slot_of", "b200net_num_slots", "b200net_level_slot_base", "b200net_plain_eval", "b200net_plain_tick",
     "b200net_layout", "b200net_bind", "b200net_set", "b200net_restore", "b200net_get", "b200net_tick", "b200net_run", "b200net_run_level_shard",
     "b200net_bind_rank", "b200net_schedule", "b200net_num_steps", "b200net_step_jobs", "b200net_schedule_info",
-    "b200net_step_gates", "b200net_step_exchange",
+    "b200net_step_gates", "b200net_step_exchange", "b200net_profile_run",
 ]
 
 
@@ -372,6 +373,12 @@ class NetEngine:
 
     def run(self):
         self._ck(self.lib.b200net_run(self._h))
+
+    def profile_run(self) -> np.ndarray:
+        """One evaluation of the clock, step by step with device timers: ms per schedule step on this rank."""
+        ms = np.zeros(self.num_steps(), np.float32)
+        self._ck(self.lib.b200net_profile_run(self._h, _p(ms), ms.size))
+        return ms
 
     def run_level_shard(self, level, rank, world):
         self._ck(self.lib.b200net_run_level_shard(self._h, level, rank, world))

@@ -134,6 +134,9 @@ def test_keyswitch_equals_reference_golden(gpu_ctx, golden):
     assert np.array_equal(gpu_ctx.test_keyswitch(u), want)              # narrow frontier: 4 CTAs per switch + combine
     reps = 150 // u.shape[0] + 1                                          # > 148 gates: one CTA per switch
     assert np.array_equal(gpu_ctx.test_keyswitch(np.tile(u, (reps, 1))), np.tile(want, (reps, 1)))
+    reps = 1403 // u.shape[0] + 1                                         # >= 1400: eight gates per CTA (ks8_kernel), ragged last CTA
+    rows = np.tile(u, (reps, 1))[:1403]
+    assert np.array_equal(gpu_ctx.test_keyswitch(rows), np.tile(want, (reps, 1))[:1403])
 
 
 def test_every_opcode_bit_exact_vs_oracle(gpu_ctx, keys):

@@ -91,17 +91,18 @@ B200_HD void br4_fwd_p1(const Br4Smem& sm, int i, int q, int d, int t)
     const uint32_t abar = sm.abar[i];
     const uint32_t* acc = sm.acc(q);
     const uint32_t base = ((uint32_t)t - abar) & (2u * N1 - 1);
-    const int sh = 32 - (d + 1) * BGBIT;
-    uint32_t x[16];
+    uint32_t dv[16], x[16];
     B200_UNROLL
     for (int a = 0; a < 16; a++) {
         const uint32_t m = (base + 64u * a) & (2u * N1 - 1);
         const uint32_t v = acc[m & (N1 - 1)];
         const uint32_t neg = 0u - ((m >> NBIT) & 1u);
-        const uint32_t diff = ((v ^ neg) - neg) - acc[64 * a + t] + (DEC_OFFSET + DEC_ROUND);
-        x[a] = ((diff >> sh) & ((1u << BGBIT) - 1)) + (P - (1u << (BGBIT - 1)));
+        dv[a] = ((v ^ neg) - neg) - acc[64 * a + t] + (DEC_OFFSET + DEC_ROUND);
     }
-    blk_fwd_p1(x);
+    // the team's digit is uniform per warp: one instantiation of the table-driven start per bit field
+    if (d == 0) blk_fwd_p1_digits<32 - BGBIT>(sm.tw->r4, dv, x);
+    else if (d == 1) blk_fwd_p1_digits<32 - 2 * BGBIT>(sm.tw->r4, dv, x);
+    else blk_fwd_p1_digits<32 - 3 * BGBIT>(sm.tw->r4, dv, x);
     blk_store_p1(sm.in_tile(q * GL + d), x, t);
 }
 B200_HD void br4_fwd_p2(const Br4Smem& sm, int q, int d, int t)

@@ -70,17 +70,18 @@ B200_HD void br6_fwd_p1(const Br6Smem& sm, int i, int q, int d, int t)
     const uint32_t abar = sm.abar[i];
     const uint32_t* acc = sm.accb;
     const uint32_t base = ((uint32_t)t - abar) & (2u * N1 - 1);
-    const int sh = 32 - (d + 1) * BGBIT;
-    uint32_t x[8];
+    uint32_t dv[8], x[8];
     B200_UNROLL
     for (int a = 0; a < 8; a++) {
         const uint32_t m = (base + 128u * a) & (2u * N1 - 1);
         const uint32_t v = acc[m & (N1 - 1)];
         const uint32_t neg = 0u - ((m >> NBIT) & 1u);
-        const uint32_t diff = ((v ^ neg) - neg) - acc[128 * a + t] + (DEC_OFFSET + DEC_ROUND);
-        x[a] = ((diff >> sh) & ((1u << BGBIT) - 1)) + (P - (1u << (BGBIT - 1)));
+        dv[a] = ((v ^ neg) - neg) - acc[128 * a + t] + (DEC_OFFSET + DEC_ROUND);
     }
-    blk8_fwd_p1(x);
+    // the team's digit is uniform per warp: three instantiations of the table-driven start, one per bit field
+    if (d == 0) blk8_fwd_p1_digits<32 - BGBIT>(sm.tw->r4, dv, x);
+    else if (d == 1) blk8_fwd_p1_digits<32 - 2 * BGBIT>(sm.tw->r4, dv, x);
+    else blk8_fwd_p1_digits<32 - 3 * BGBIT>(sm.tw->r4, dv, x);
     blk8_store_p1(sm.in_tile(q * GL + d), x, t);
 }
 B200_HD void br6_fwd_p2(const Br6Smem& sm, int q, int d, int t) { blk8_fwd_p2(sm.in_tile(q * GL + d), sm.tw->q2f, t); }

@@ -34,12 +34,14 @@ B200_HD int bt_pad(int j) { return j + ((j >> 6) << 2); }
 struct BlockTw {
     tw_t p2f[BT_P2_LEN], p2i[BT_P2_LEN];
     tw_t p3f[BT_P3_LEN], p3i[BT_P3_LEN];
+    uint32_t r4[R4_WORDS];  // digit x twiddle tables of forward stages 0 and 1 (ntt_warp.h fwd_start_r4_group)
 };
 
 // p2[A*15 + (2^ls - 1) + g] = psi_rev[(16 << ls) + (A << ls) + g]      (stage 4 + ls, g < 2^ls)
 // p3[m*3] = psi_rev[256 + m],  p3[m*3 + 1 + h] = psi_rev[512 + 2m + h]  (stages 8 and 9)
 inline void block_tw_init(const NttTables& t, BlockTw& b)
 {
+    for (int k = 0; k < R4_WORDS; k++) b.r4[k] = t.r4[k];
     for (int A = 0; A < 16; A++)
         for (int ls = 0; ls < 4; ls++)
             for (int g = 0; g < (1 << ls); g++) {
@@ -97,6 +99,17 @@ B200_HD void blk_fwd_p1(uint32_t (&x)[16])  // x[a] = value at j = 64a + t
 {
     ct_stage_n<16, 0, 0>(x, [](int g) { return twf_u(1 + g); });
     ct_stage_n<16, 1, 0>(x, [](int g) { return twf_u(2 + g); });
+    ct_stage_n<16, 2, 0>(x, [](int g) { return twf_u(4 + g); });
+    ct_stage_n<16, 3, 1>(x, [](int g) { return twf_u(8 + g); });
+}
+// pass 1 on gadget digits still in their bit field of dv[a] (coefficient 64a + t): stages 0 and 1 by table look-up
+// (groups {a0, a0+4, a0+8, a0+12}), stages 2 and 3 as usual
+template <int SHIFT>
+B200_HD void blk_fwd_p1_digits(const uint32_t* r4, const uint32_t (&dv)[16], uint32_t (&x)[16])
+{
+    B200_UNROLL
+    for (int a0 = 0; a0 < 4; a0++)
+        fwd_start_r4_group<SHIFT>(r4, dv[a0], dv[a0 + 4], dv[a0 + 8], dv[a0 + 12], x[a0], x[a0 + 4], x[a0 + 8], x[a0 + 12]);
     ct_stage_n<16, 2, 0>(x, [](int g) { return twf_u(4 + g); });
     ct_stage_n<16, 3, 1>(x, [](int g) { return twf_u(8 + g); });
 }

@@ -34,10 +34,13 @@ struct Block8Tw {
     tw_t q2f[B8_Q2_LEN], q2i[B8_Q2_LEN];
     tw_t q3f[B8_Q3_LEN], q3i[B8_Q3_LEN];
     tw_t q4f[BT_P3_LEN], q4i[BT_P3_LEN];  // [m][3]: psi_rev[256 + m], psi_rev[512 + 2m], psi_rev[512 + 2m + 1]
+    uint32_t r4[R4_WORDS];                // digit x twiddle tables of forward stages 0 and 1 (ntt_warp.h fwd_start_r4_group)
 };
+static_assert(R4_WORDS % 4 == 0, "keeps the table block a multiple of 16 bytes");
 
 inline void block8_tw_init(const NttTables& t, Block8Tw& b)
 {
+    for (int k = 0; k < R4_WORDS; k++) b.r4[k] = t.r4[k];
     for (int U = 0; U < 8; U++)
         for (int ls = 0; ls < 3; ls++)
             for (int g = 0; g < (1 << ls); g++) {  // stage 3 + ls: psi_rev[(8 << ls) + (U << ls) + g]
@@ -67,6 +70,15 @@ B200_HD void blk8_fwd_p1(uint32_t (&x)[8])  // x[a] at j = 128a + t
 {
     ct_stage_n<8, 0, 0>(x, [](int g) { return twf_u(1 + g); });
     ct_stage_n<8, 1, 0>(x, [](int g) { return twf_u(2 + g); });
+    ct_stage_n<8, 2, 0>(x, [](int g) { return twf_u(4 + g); });
+}
+// pass 1 when the inputs are gadget digits still sitting in their bit field of dv[a] (coefficient 128a + t): stages 0 and 1
+// by table look-up (pairs (a, a+4) then (a, a+2): the groups are {a0, a0+2, a0+4, a0+6}), stage 2 as usual
+template <int SHIFT>
+B200_HD void blk8_fwd_p1_digits(const uint32_t* r4, const uint32_t (&dv)[8], uint32_t (&x)[8])
+{
+    fwd_start_r4_group<SHIFT>(r4, dv[0], dv[2], dv[4], dv[6], x[0], x[2], x[4], x[6]);
+    fwd_start_r4_group<SHIFT>(r4, dv[1], dv[3], dv[5], dv[7], x[1], x[3], x[5], x[7]);
     ct_stage_n<8, 2, 0>(x, [](int g) { return twf_u(4 + g); });
 }
 B200_HD void blk8_store_p1(uint32_t* tile, const uint32_t (&x)[8], int t)

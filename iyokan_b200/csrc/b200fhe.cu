@@ -758,7 +758,9 @@ struct b200fhe_ctx {
     bool autotune = true;  // pick (variant, G) per batch size unless the caller pinned them
     int br7_group = 8;     // jobs per barrier group of br7_kernel (8 = CTA-wide pointwise stage, 4 or 2 = skewed groups)
     int br7_skew = 0;      // start delay between consecutive groups, SM cycles
-    int ks8_min = 1400;    // frontiers of at least this many key switches take ks8_kernel (8 gates per CTA)
+    // frontiers of at least this many key switches take ks8_kernel (8 gates per CTA).  80-bit flavour: never - its 2048-byte
+    // rows double the registers per lane and the shape measured slower than ks_kernel (11.5 against 9.3 ms per 8192 gates)
+    int ks8_min = T0_BITS == 16 ? 1400 : 0x7fffffff;
     NttTables* tab = nullptr;
     tw_t* d_tw2f = nullptr;
     uint32_t* d_r4 = nullptr;       // digit x twiddle tables of the first two forward stages (br7_kernel)

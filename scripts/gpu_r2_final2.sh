@@ -13,3 +13,4 @@ timeout 1500 python bench.py --steps 20 --warmup 5 2> gpurun_out/r02_bench.err |
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-netlist > gpurun_out/r02_ncu_bench.log 2>&1
 ls -la gpurun_out | tail -12
+NGPU=1 bash scripts/sweep_params.sh --steps 3 2>/dev/null | cut -c1-200

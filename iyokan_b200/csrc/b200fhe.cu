@@ -23,6 +23,9 @@
 #include "br4_phases.h"
 #include "br6_phases.h"
 #include "br7_phases.h"
+#ifdef B200FHE_WITH_BR9
+#include "br9_phases.h"  // 4-point cluster experiment: measured slower than br6_kernel (profiles/r02_br9.md), not in the default build
+#endif
 #ifdef B200FHE_WITH_BR8
 #include "br8_phases.h"  // quad-cluster experiment: measured slower than br6_kernel (profiles/r02_br8.md), not in the default build
 #endif
@@ -478,7 +481,98 @@ br6_kernel(const BrJob* __restrict__ jobs, int njobs, const torus0_t* __restrict
     br6_epilogue(sm, q, tid, ubuf + (size_t)job * U_STRIDE);
 }
 
+#ifdef B200FHE_WITH_BR9
+// 4-point cluster shape (br9_phases.h): the same cluster protocol as br6_kernel, transforms in five two-stage passes of
+// 256 threads - 24 warps per SM
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BR9_THREADS, 1)
+br9_kernel(const BrJob* __restrict__ jobs, int njobs, const torus0_t* __restrict__ arena,
+           const uint32_t* __restrict__ bk_ntt, const Block4Tw* __restrict__ tw_g, uint32_t* __restrict__ ubuf, int n_iter)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Br9Smem sm;
+    sm.carve(smem_raw);
+    const int tid = threadIdx.x, d = tid >> 8, t = tid & 255;
+    const int q = (int)cluster_ctarank();
+    const int job = blockIdx.x >> 1;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tw_g);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(sm.tw);
+        for (int k = tid; k < (int)(sizeof(Block4Tw) / 4); k += BR9_THREADS) dst[k] = src[k];
+    }
+    uint64_t* mbar_dig = sm.mbar + 1;  // counts the bytes of the three digit tiles the peer copies in per step
+    if (tid == 0) {
+        mbar_init(sm.mbar, 1);
+        mbar_init(mbar_dig, 1);
+    }
+    const BrJob jb = jobs[job];
+    br9_prologue(sm, jb, arena, q, tid);
+    __syncthreads();
+    const uint32_t* key0 = bk_ntt + (size_t)q * BR6_KEY_WORDS;  // columns 3q..3q+2 of step 0
+    auto stage = [&](int i) {
+        constexpr uint32_t BYTES = BR6_KEY_WORDS * 4;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(sm.mbar)), "r"(BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(sm.keyb)),
+                     "l"(key0 + (size_t)i * BR4_KEY_WORDS), "r"(BYTES), "r"(smem_u32(sm.mbar))
+                     : "memory");
+    };
+    constexpr uint32_t TILE_BYTES = B8_WORDS * 4;
+    const uint32_t my_tile = smem_u32(sm.in_tile(q * GL + d));
+    uint32_t peer_tile, peer_bar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_tile) : "r"(my_tile), "r"((uint32_t)(q ^ 1)));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_bar) : "r"(smem_u32(mbar_dig)), "r"((uint32_t)(q ^ 1)));
+    if (tid == 0 && n_iter > 0) stage(0);
+    cluster_arrive();  // both CTAs have initialised their barriers before anyone copies into the other
+    cluster_wait();
+    cluster_arrive_relaxed();  // phase (B) of "step -1"
 
+    for (int i = 0; i < n_iter; i++) {
+        if (tid == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar_dig)),
+                         "r"(GL * TILE_BYTES)
+                         : "memory");
+        br9_fwd_p1(sm, i, q, d, t);
+        named_barrier_sync(1 + d, TEAM4_THREADS);
+        br9_fwd_p2(sm, q, d, t);
+        named_barrier_sync(1 + d, TEAM4_THREADS);
+        br9_fwd_p3(sm, q, d, t);
+        named_barrier_sync(1 + d, TEAM4_THREADS);
+        br9_fwd_p4(sm, q, d, t);
+        named_barrier_sync(1 + d, TEAM4_THREADS);
+        br9_fwd_p5(sm, q, d, t);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        cluster_wait();    // (B) the peer's pointwise stage of the previous step no longer reads my copies
+        named_barrier_sync(1 + d, TEAM4_THREADS);
+        if (t == 0)
+            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             peer_tile),
+                         "r"(my_tile), "r"(TILE_BYTES), "r"(peer_bar)
+                         : "memory");
+        mbar_wait(sm.mbar, (uint32_t)(i & 1));
+        uint64_t pacc[LIMBS][4];
+        named_barrier_sync(7, BR9_THREADS);  // the local teams' tiles are complete
+        br6_pw_local(sm, q, tid, pacc);
+        mbar_wait(mbar_dig, (uint32_t)(i & 1));  // the peer's three tiles have landed
+        br6_pw_finish(sm, q, tid, pacc);
+        cluster_arrive_relaxed();  // (B) for the next step
+        __syncthreads();
+        if (tid == 0 && i + 1 < n_iter) stage(i + 1);
+        br9_inv_pA(sm, d, t);
+        named_barrier_sync(1 + d, TEAM4_THREADS);
+        br9_inv_pB(sm, d, t);
+        named_barrier_sync(1 + d, TEAM4_THREADS);
+        br9_inv_pC(sm, d, t);
+        named_barrier_sync(1 + d, TEAM4_THREADS);
+        br9_inv_pD(sm, d, t);
+        named_barrier_sync(1 + d, TEAM4_THREADS);
+        br9_inv_pE(sm, d, t);
+        __syncthreads();
+    }
+    cluster_wait();
+    br9_epilogue(sm, q, tid, ubuf + (size_t)job * U_STRIDE);
+}
+#endif  // B200FHE_WITH_BR9
 
 #ifdef B200FHE_WITH_BR8
 // ---- quad-cluster shape: one job per 4-CTA cluster, CTA (q, h) = polynomial q, transform half h (br8_phases.h) ----
@@ -769,6 +863,9 @@ struct b200fhe_ctx {
 #ifndef B200FHE_80BIT
     BlockTw* d_blocktw = nullptr;   // team-NTT twiddles (br4_kernel)
     Block8Tw* d_block8tw = nullptr; // 128-thread team NTT (br6_kernel)
+#ifdef B200FHE_WITH_BR9
+    Block4Tw* d_block4tw = nullptr; // 256-thread team NTT (br9_kernel)
+#endif
 #endif
     uint32_t* d_bk_ntt = nullptr;   // [636][6][6][1024]
     torus0_t* d_ksk = nullptr;      // [1024][t][3][SLOT_STRIDE]
@@ -990,6 +1087,16 @@ static int br8_launch(b200fhe_ctx* c, int njobs, const torus0_t* arena, uint32_t
 }
 #endif
 
+#ifdef B200FHE_WITH_BR9
+static int br9_launch(b200fhe_ctx* c, int njobs, const torus0_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
+{
+    br9_kernel<<<2 * njobs, BR9_THREADS, Br9Smem::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_block4tw, ubuf, N0);
+    CK(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+#endif
+
 static int br6_launch(b200fhe_ctx* c, int njobs, const torus0_t* arena, uint32_t* ubuf, const BrJob* d_jobs)
 {
     br6_kernel<<<2 * njobs, BR6_THREADS, Br6Smem::BYTES, c->stream>>>(d_jobs, njobs, arena, c->d_bk_ntt, c->d_block8tw, ubuf, N0);
@@ -1014,6 +1121,9 @@ static int set_kernel_attrs()
     CK(cudaFuncSetAttribute(br7_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br7Smem<8>::BYTES));
     CK(cudaFuncSetAttribute(br4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br4Smem::BYTES));
     CK(cudaFuncSetAttribute(br6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br6Smem::BYTES));
+#ifdef B200FHE_WITH_BR9
+    CK(cudaFuncSetAttribute(br9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br9Smem::BYTES));
+#endif
 #ifdef B200FHE_WITH_BR8
     CK(cudaFuncSetAttribute(br8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Br8Smem::BYTES));
 #endif
@@ -1043,6 +1153,9 @@ static int br_dispatch_one(b200fhe_ctx* c, int variant, int G, int njobs, const 
     if (variant == 8) return br8_launch(c, njobs, arena, ubuf, d_jobs);
 #endif
     if (variant == 6) return br6_launch(c, njobs, arena, ubuf, d_jobs);
+#ifdef B200FHE_WITH_BR9
+    if (variant == 9) return br9_launch(c, njobs, arena, ubuf, d_jobs);
+#endif
     if (variant == 4) return br4_launch(c, njobs, arena, ubuf, d_jobs);
     if (variant == 3) {
         switch (G) {
@@ -1052,7 +1165,7 @@ static int br_dispatch_one(b200fhe_ctx* c, int variant, int G, int njobs, const 
         default: return fail("variant 3 supports 2, 4 or 6 jobs per CTA");
         }
     }
-    return fail("kernel variant must be 1, 3, 4, 6 or 7");
+    return fail("kernel variant must be 1, 3, 4, 6 or 7 (8 and 9 are experiments: build with -DB200FHE_WITH_BR8 / _BR9)");
 #else
     return fail("the 80-bit flavour carries the generic shape only (variant 1)");
 #endif
@@ -1119,7 +1232,7 @@ static int br_dispatch(b200fhe_ctx* c, int njobs, const torus0_t* arena, uint32_
             return 1;
         if (timing) CK(cudaEventRecord(c->ev_seg[k + 1], c->stream));
         c->seg_variant[k] = seg[k].variant;
-        c->seg_G[k] = (seg[k].variant == 4 || seg[k].variant == 6 || seg[k].variant == 8) ? 1 : seg[k].G;
+        c->seg_G[k] = (seg[k].variant == 4 || seg[k].variant == 6 || seg[k].variant == 8 || seg[k].variant == 9) ? 1 : seg[k].G;
         c->seg_count[k] = seg[k].count;
         first += seg[k].count;
     }
@@ -1230,6 +1343,14 @@ int b200fhe_create(b200fhe_ctx** out, int device)
 #ifndef B200FHE_80BIT
     delete btw;
     delete b8tw;
+#ifdef B200FHE_WITH_BR9
+    Block4Tw* b4tw = new Block4Tw();
+    block4_tw_init(*c->tab, *b4tw);
+    CK(cudaMalloc(&c->d_block4tw, sizeof(Block4Tw)));
+    CK(cudaMemcpyAsync(c->d_block4tw, b4tw, sizeof(Block4Tw), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    delete b4tw;
+#endif
 #endif
     *out = c;
     return 0;
@@ -1247,6 +1368,9 @@ void b200fhe_destroy(b200fhe_ctx* c)
 #ifndef B200FHE_80BIT
     cudaFree(c->d_blocktw);
     cudaFree(c->d_block8tw);
+#ifdef B200FHE_WITH_BR9
+    cudaFree(c->d_block4tw);
+#endif
 #endif
     cudaFree(c->d_bk_ntt);
     cudaFree(c->d_ksk);
@@ -1294,8 +1418,8 @@ int b200fhe_set_kernel_variant(b200fhe_ctx* c, int variant)
 {
     if (!c) return fail("null context");
     if (variant == 0) return b200fhe_set_jobs_per_cta(c, 0);
-    if (variant != 1 && variant != 3 && variant != 4 && variant != 6 && variant != 7 && variant != 8)
-        return fail("kernel variant must be 0 (auto), 1, 3, 4, 6, 7 or 8");
+    if (variant != 1 && variant != 3 && variant != 4 && variant != 6 && variant != 7 && variant != 8 && variant != 9)
+        return fail("kernel variant must be 0 (auto), 1, 3, 4, 6, 7, 8 or 9");
     c->variant = variant;
     c->autotune = false;
     return 0;
@@ -1552,7 +1676,7 @@ int b200fhe_plan_rotation(int njobs, int* variant, int* jobs_per_cta, int* jobs,
     const int n = nseg < max_segments ? nseg : max_segments;
     for (int k = 0; k < n; k++) {
         if (variant) variant[k] = seg[k].variant;
-        if (jobs_per_cta) jobs_per_cta[k] = (seg[k].variant == 4 || seg[k].variant == 6 || seg[k].variant == 8) ? 1 : seg[k].G;
+        if (jobs_per_cta) jobs_per_cta[k] = (seg[k].variant == 4 || seg[k].variant == 6 || seg[k].variant == 8 || seg[k].variant == 9) ? 1 : seg[k].G;
         if (jobs) jobs[k] = seg[k].count;
     }
     return n;

@@ -94,7 +94,8 @@ B200_HD void br6_fwd_p4(const Br6Smem& sm, int q, int d, int t) { blk8_fwd_p4(sm
 // shared-memory wavefronts (key 576 + digits 216 per step), not by the multiplies, and eight busy
 // warps already saturate them.
 constexpr int BR6_PW_THREADS = N1 / 4;  // 256
-B200_HD void br6_pw_rows(const Br6Smem& sm, int m, int row0, uint64_t (&acc)[LIMBS][4])
+template <class SM>  // Br6Smem or Br9Smem: same tiles, same key layout
+B200_HD void br6_pw_rows(const SM& sm, int m, int row0, uint64_t (&acc)[LIMBS][4])
 {
     const int toff = b8_quad(m);
     B200_UNROLL
@@ -110,14 +111,16 @@ B200_HD void br6_pw_rows(const Br6Smem& sm, int m, int row0, uint64_t (&acc)[LIM
         }
     }
 }
-B200_HD void br6_pw_local(const Br6Smem& sm, int q, int tid, uint64_t (&acc)[LIMBS][4])
+template <class SM>
+B200_HD void br6_pw_local(const SM& sm, int q, int tid, uint64_t (&acc)[LIMBS][4])
 {
     if (tid >= BR6_PW_THREADS) return;
     B200_UNROLL
     for (int l = 0; l < LIMBS; l++) acc[l][0] = acc[l][1] = acc[l][2] = acc[l][3] = 0;
     br6_pw_rows(sm, tid, q * GL, acc);
 }
-B200_HD void br6_pw_finish(const Br6Smem& sm, int q, int tid, uint64_t (&acc)[LIMBS][4])
+template <class SM>
+B200_HD void br6_pw_finish(const SM& sm, int q, int tid, uint64_t (&acc)[LIMBS][4])
 {
     if (tid >= BR6_PW_THREADS) return;
     br6_pw_rows(sm, tid, (q ^ 1) * GL, acc);

@@ -20,6 +20,7 @@
 #include "../../iyokan_b200/csrc/brg_phases.h"
 #include "../../iyokan_b200/csrc/gate_jobs.h"
 #include "../../iyokan_b200/csrc/ks_phases.h"
+#include "../../iyokan_b200/csrc/br9_phases.h"
 
 using namespace b200;
 
@@ -27,6 +28,7 @@ static NttTables g_tab;
 #ifndef B200FHE_80BIT
 static BlockTw g_btw;
 static Block8Tw g_b8tw;
+static Block4Tw g_b4tw;
 #endif
 static bool g_init = false;
 
@@ -44,6 +46,7 @@ extern "C" void sim_init()
 #ifndef B200FHE_80BIT
         block_tw_init(g_tab, g_btw);
         block8_tw_init(g_tab, g_b8tw);
+        block4_tw_init(g_tab, g_b4tw);
 #endif
         g_init = true;
     }
@@ -528,6 +531,62 @@ extern "C" void sim_blind_rotate6(const void* jobs_raw, int njobs, const torus0_
 }
 
 
+
+// ---- variant 9: cluster shape with 4-point threads (br9_kernel): br6's protocol, five two-stage passes of 256 threads ----
+static void sim_br9_cluster(const BrJob* jobs, int job, const torus0_t* arena, const uint32_t* bk_ntt, uint32_t* ubuf,
+                            int n_iter)
+{
+    std::vector<uint8_t> smem[2] = {std::vector<uint8_t>(Br9Smem::BYTES + 128), std::vector<uint8_t>(Br9Smem::BYTES + 128)};
+    Br9Smem sm[2];
+    for (int q = 0; q < 2; q++) {
+        sm[q].carve(reinterpret_cast<void*>(((uintptr_t)smem[q].data() + 127) & ~(uintptr_t)127));
+        std::memcpy(sm[q].tw, &g_b4tw, sizeof(Block4Tw));
+        for (int tid = 0; tid < BR9_THREADS; tid++) br9_prologue(sm[q], jobs[job], arena, q, tid);
+    }
+    auto each = [&](auto fn) {
+        for (int qq = 0; qq < 2; qq++)
+            for (int k = 0; k < BR9_THREADS; k++) {
+                const int q = ord(qq, 2), tid = ord(k, BR9_THREADS);
+                fn(q, tid >> 8, tid & 255);
+            }
+    };
+    std::vector<uint64_t> pacc((size_t)2 * BR9_THREADS * LIMBS * 4);
+    auto acc_of = [&](int q, int tid) -> uint64_t(&)[LIMBS][4] {
+        return *reinterpret_cast<uint64_t(*)[LIMBS][4]>(pacc.data() + ((size_t)q * BR9_THREADS + tid) * LIMBS * 4);
+    };
+    for (int i = 0; i < n_iter; i++) {
+        for (int q = 0; q < 2; q++)
+            std::memcpy(sm[q].keyb, bk_ntt + (size_t)i * BR4_KEY_WORDS + (size_t)q * BR6_KEY_WORDS, (size_t)BR6_KEY_WORDS * 4);
+        each([&](int q, int d, int t) { br9_fwd_p1(sm[q], i, q, d, t); });
+        each([&](int q, int d, int t) { br9_fwd_p2(sm[q], q, d, t); });
+        each([&](int q, int d, int t) { br9_fwd_p3(sm[q], q, d, t); });
+        each([&](int q, int d, int t) { br9_fwd_p4(sm[q], q, d, t); });
+        each([&](int q, int d, int t) { br9_fwd_p5(sm[q], q, d, t); });
+        for (int q = 0; q < 2; q++)
+            for (int d = 0; d < GL; d++)
+                std::memcpy(sm[q ^ 1].in_tile(q * GL + d), sm[q].in_tile(q * GL + d), (size_t)B8_WORDS * 4);
+        for (int q = 0; q < 2; q++)
+            for (int k = 0; k < BR9_THREADS; k++) br6_pw_local(sm[q], q, ord(k, BR9_THREADS), acc_of(q, ord(k, BR9_THREADS)));
+        for (int q = 0; q < 2; q++)
+            for (int k = 0; k < BR9_THREADS; k++) br6_pw_finish(sm[q], q, ord(k, BR9_THREADS), acc_of(q, ord(k, BR9_THREADS)));
+        each([&](int q, int d, int t) { br9_inv_pA(sm[q], d, t); });
+        each([&](int q, int d, int t) { br9_inv_pB(sm[q], d, t); });
+        each([&](int q, int d, int t) { br9_inv_pC(sm[q], d, t); });
+        each([&](int q, int d, int t) { br9_inv_pD(sm[q], d, t); });
+        each([&](int q, int d, int t) { br9_inv_pE(sm[q], d, t); });
+    }
+    for (int q = 0; q < 2; q++)
+        for (int tid = 0; tid < BR9_THREADS; tid++) br9_epilogue(sm[q], q, tid, ubuf + (size_t)job * U_STRIDE);
+}
+
+extern "C" void sim_blind_rotate9(const void* jobs_raw, int njobs, const torus0_t* arena, const uint32_t* bk_ntt,
+                                  uint32_t* ubuf, int n_iter)
+{
+    sim_init();
+    const BrJob* jobs = reinterpret_cast<const BrJob*>(jobs_raw);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int job = 0; job < njobs; job++) sim_br9_cluster(jobs, job, arena, bk_ntt, ubuf, n_iter);
+}
 
 // ---- variant 8: quad-cluster shape (br8_kernel); the four CTAs advance phase by phase, the three DSMEM exchanges
 // become memcpys at the points where the kernel issues the bulk copies ----

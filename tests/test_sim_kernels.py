@@ -191,6 +191,26 @@ def test_blind_rotate_variant6_bit_exact(sim, keys, bk_ntt_sim):
     assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
 
 
+def test_blind_rotate_variant9_bit_exact(sim, keys, bk_ntt_sim):
+    # cluster shape with 4-point threads (br9_phases.h, ntt_block4.h): 256-thread teams, five two-stage passes
+    rng = np.random.default_rng(99)
+    n = 3
+    pa, pb = rng.integers(0, 2, n, dtype=np.uint8), rng.integers(0, 2, n, dtype=np.uint8)
+    ca, cb = O.encrypt_bits(31, keys, pa), O.encrypt_bits(32, keys, pb)
+    arena = np.zeros((2 * n, 640), np.uint16)
+    arena[:n, :637], arena[n:, :637] = ca, cb
+    jobs = np.zeros(n, BRJOB)
+    for g in range(n):
+        jobs[g]["in"] = (g, n + g, 0)
+        jobs[g]["sgn"] = (-1, -1, 0)         # NOR: -a - b - mu
+        jobs[g]["off"] = (-(1 << 13)) & 0xFFFF
+    ubuf = np.zeros((n, 1028), np.uint32)
+    sim.sim_blind_rotate9(p(jobs), n, p(arena), p(bk_ntt_sim), p(ubuf), 636)
+    c = (-ca.astype(np.int32) - cb.astype(np.int32)).astype(np.uint16)
+    c[:, 636] -= np.uint16(1 << 13)
+    assert np.array_equal(ubuf[:, :1025], O.bootstrap_to_lvl1(keys, c))
+
+
 def test_blind_rotate_variant8_bit_exact(sim, keys, bk_ntt_sim):
     # quad-cluster shape (br8_phases.h): 4 CTAs per job, every transform cut into two 512-position halves
     rng = np.random.default_rng(88)

@@ -11,8 +11,10 @@ __global__ void k(unsigned* out, unsigned a0, unsigned b0)
 {
     unsigned x[CHAINS], y[CHAINS];
     unsigned long long w[CHAINS];
+    double f[CHAINS];
+    const double fa = 1.0 + 1e-9 * a0, fb = 1e-7 * b0;
 #pragma unroll
-    for (int i = 0; i < CHAINS; i++) { x[i] = a0 + threadIdx.x + i; y[i] = b0 * (i + 1); w[i] = x[i]; }
+    for (int i = 0; i < CHAINS; i++) { x[i] = a0 + threadIdx.x + i; y[i] = b0 * (i + 1); w[i] = x[i]; f[i] = (double)(threadIdx.x + i); }
     for (int it = 0; it < ITER; it++) {
 #pragma unroll
         for (int i = 0; i < CHAINS; i++) {
@@ -32,6 +34,17 @@ __global__ void k(unsigned* out, unsigned a0, unsigned b0)
                 asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(x[i]), "r"(y[i]));
                 asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(b0));
             }
+            if (OP == 11) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(f[i]) : "d"(fa), "d"(fb));  // FP64 pipe alone
+            if (OP == 12) {  // does the FP64 pipe run beside the integer-multiply pipe?  one DFMA per IMAD.WIDE
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(x[i]), "r"(y[i]));
+                asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(f[i]) : "d"(fa), "d"(fb));
+            }
+            if (OP == 13) {  // the conversions an FP64 pointwise stage would need: u32 -> f64 and back
+                double t;
+                asm volatile("cvt.rn.f64.u32 %0, %1;" : "=d"(t) : "r"(x[i]));
+                asm volatile("cvt.rzi.u32.f64 %0, %1;" : "=r"(x[i]) : "d"(t));
+            }
+            if (OP == 14) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(x[i]), "r"(y[i]));  // IMAD.WIDE alone
             if (OP == 3) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));
             if (OP == 4) { asm volatile("sub.u32 %0, %1, %2;" : "=r"(y[i]) : "r"(x[i]), "r"(b0)); asm volatile("min.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i])); }
             if (OP == 5) { asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(b0)); asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(b0)); }
@@ -49,7 +62,7 @@ __global__ void k(unsigned* out, unsigned a0, unsigned b0)
     }
     unsigned s = 0;
 #pragma unroll
-    for (int i = 0; i < CHAINS; i++) s += x[i] + y[i] + (unsigned)w[i] + (unsigned)(w[i] >> 32);
+    for (int i = 0; i < CHAINS; i++) s += x[i] + y[i] + (unsigned)w[i] + (unsigned)(w[i] >> 32) + (unsigned)(long long)f[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
@@ -88,5 +101,9 @@ int main()
     run<6>("IMAD.HI + 2 IADD", 3);
     run<7>("SHF", 1);
     run<8>("Shoup butterfly (5 instr)", 5);
+    run<14>("IMAD.WIDE (acc64) alone", 1);
+    run<11>("DFMA alone", 1);
+    run<12>("IMAD.WIDE + DFMA (1:1)", 2);
+    run<13>("cvt u32->f64 + f64->u32", 2);
     return 0;
 }

@@ -6,6 +6,23 @@
 #include "../../iyokan_b200/csrc/ntt_warp.h"
 using namespace b200;
 
+// 32 x 32 transpose (register index <-> lane) with warp shuffles only: five exchange rounds of 16 SHFL + 32 SEL.
+// north_star names warp-shuffle butterflies; this is what replacing the warp-private tile by shuffles costs.
+__device__ __forceinline__ void transpose_shfl(uint32_t (&x)[32], int lane)
+{
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) {
+        const bool up = (lane & k) != 0;
+#pragma unroll
+        for (int a = 0; a < 32; a++) {
+            if (a & k) continue;
+            const uint32_t send = up ? x[a] : x[a | k];
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, k);
+            if (up) x[a] = recv; else x[a | k] = recv;
+        }
+    }
+}
+
 template <int MODE>
 __global__ void k(uint32_t* out, const tw_t* tw2f_g, const tw_t* tw2i_g, int iters)
 {
@@ -29,6 +46,10 @@ __global__ void k(uint32_t* out, const tw_t* tw2f_g, const tw_t* tw2i_g, int ite
             fwd_pass1(x); tile_store_col(tile, x, lane); __syncwarp();
             tile_load_row(tile, x, lane); fwd_pass2(x, tw2f, lane); tile_store_row(tile, x, lane); __syncwarp();
             tile_load_col(tile, x, lane);
+        }
+        if (MODE == 6) {  // full forward transform, both transposes by shuffles instead of the tile
+            fwd_pass1(x); transpose_shfl(x, lane);
+            fwd_pass2(x, tw2f, lane); transpose_shfl(x, lane);
         }
         if (MODE == 5) {  // full inverse transform with tile traffic, as in phase I
             tile_load_row(tile, x, lane); inv_pass1(x, tw2i, lane); tile_store_row(tile, x, lane); __syncwarp();
@@ -78,5 +99,6 @@ int main()
     run<3>("inv_pass2 (regs, const twiddles)", 1, f, i);
     run<4>("forward NTT + tile traffic", 2, f, i);
     run<5>("inverse NTT + tile traffic", 2, f, i);
+    run<6>("forward NTT + shuffle transposes", 2, f, i);
     return 0;
 }

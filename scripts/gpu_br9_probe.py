@@ -1,5 +1,7 @@
 """br9_kernel (cluster shape with 4-point threads) against br6_kernel on the GPU: parity vs the oracle, launch time vs number of jobs."""
 import os, sys
+# needs the experiment build: bash scripts/build_experiment_lib.sh (the shipped library does not contain this kernel)
+os.environ.setdefault("B200FHE_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "iyokan_b200", "csrc", "libb200fhe_exp.so"))
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

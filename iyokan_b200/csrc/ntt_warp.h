@@ -30,7 +30,11 @@ namespace b200 {
 constexpr int TILE_ROW = 36;                 // padded row pitch in words
 constexpr int TILE_WORDS = 32 * TILE_ROW;    // 1152 words = 4608 B per polynomial tile
 constexpr int TW2_LEN = 31 * 32;             // lane-dependent twiddles per direction
-constexpr int R4_DIGITS = 1 << BGBIT;        // entries per table of the table-driven first two forward stages
+// entries per table of the table-driven first two forward stages: one per digit value.  Only the 6-bit gadget of the
+// 128-bit set uses them (five 64-entry tables); for wider gadgets the tables are stubs and fwd_start_r4_group must not be
+// called (the 80-bit flavour compiles the specialised phase headers only for the simulator and runs brg_kernel alone)
+constexpr bool R4_ENABLED = BGBIT <= 6;
+constexpr int R4_DIGITS = R4_ENABLED ? (1 << BGBIT) : 4;
 constexpr int R4_WORDS = 5 * R4_DIGITS;
 
 B200_HD int tile_idx(int a, int b) { return a * TILE_ROW + b; }

@@ -376,7 +376,7 @@ class NetEngine:
 
     def profile_run(self) -> np.ndarray:
         """One evaluation of the clock, step by step with device timers: ms per schedule step on this rank."""
-        ms = np.zeros(self.num_steps(), np.float32)
+        ms = np.zeros(self.num_steps, np.float32)
         self._ck(self.lib.b200net_profile_run(self._h, _p(ms), ms.size))
         return ms
 

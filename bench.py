@@ -440,10 +440,10 @@ def main():
         }
         # honest bound of the dominant kernel: the int32 multiply pipe (DRAM is idle: keys sit in L2).  Pipe cycles per
         # CMUX step and job from the SASS of br7_kernel<8,8> (scripts/sass_count.py, profiles/r02_sass_count.txt; per thread
-        # and step: 1903 IMAD x 2 + 960 IMAD.HI x 4 + 576 IMAD.WIDE x 4 + 287 IMAD.IADD/SHL/MOV x 2 cycles = 10,524 per warp;
+        # and step: 1897 IMAD x 2 + 960 IMAD.HI x 4 + 576 IMAD.WIDE x 4 + 177 IMAD.IADD/SHL/MOV x 2 cycles = 10,292 per warp;
         # 16 warps on 4 schedulers, 8 jobs per SM)
         sm_hz = 1e6 * ((clocks or {}).get("sm_mhz") or 1965.0)
-        pipe_cycles_per_rotation = 636 * 10524 * 4 / 8
+        pipe_cycles_per_rotation = 636 * 10292 * 4 / 8
         alu_peak = 148 * sm_hz / pipe_cycles_per_rotation
         line["roofline"]["alu"] = {"bound": "int32 multiply pipe (fmaheavy), 148 SMs at the sampled SM clock",
                                    "pipe_cycles_per_rotation": pipe_cycles_per_rotation, "peak": alu_peak,

@@ -228,20 +228,23 @@ br7_kernel(const BrJob* __restrict__ jobs, int njobs, const torus0_t* __restrict
     for (int i = 0; i < n_iter; i++) {
         const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
         uint32_t bk0[BK_COLS][ROWS];
-        br7_fwd12_a<G>(sm, i, g, q, lane, accr);
-        __syncwarp();
-        PHASE_MARK(0);
-        br7_fwd12_c<G>(sm, g, q, lane);
-        PHASE_MARK(1);
-        {
-            uint32_t x0[32];
-            br7_fwd0_a<G>(sm, i, g, q, lane, accr, x0);
-            __syncwarp();  // last read of the accumulator copy that shares tile 3q with digit 0
-            br7_fwd0_b<G>(sm, g, q, lane, x0);
+        {  // one rotated difference, kept in registers: digit 0 first (x1 passes leave room for it), then digits 1 and 2
+            uint32_t dv[32];
+            {
+                uint32_t x0[32];
+                br7_fwd0_a<G>(sm, i, g, q, lane, accr, dv, x0);
+                __syncwarp();  // last read of the accumulator copy that shares tile 3q with digit 0
+                br7_fwd0_b<G>(sm, g, q, lane, x0);
+            }
+            __syncwarp();
+            PHASE_MARK(0);
+            br7_fwd0_c<G>(sm, g, q, lane);
+            PHASE_MARK(1);
+            br7_fwd12_a<G>(sm, g, q, lane, dv);
+            __syncwarp();
+            PHASE_MARK(2);
         }
-        __syncwarp();
-        PHASE_MARK(2);
-        br7_fwd0_c<G>(sm, g, q, lane);
+        br7_fwd12_c<G>(sm, g, q, lane);
         PHASE_MARK(3);
         pw_load(bk_i, tig, bk0);  // key words of the pointwise stage in flight across the barrier
         if (J == G) __syncthreads(); else named_barrier_sync(1 + group, 64 * J);

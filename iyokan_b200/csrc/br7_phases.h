@@ -9,15 +9,16 @@
 //     8 jobs x 6 tiles = 192 KB + twiddles + mod-switched a_i = 222,720 B of the 227 KB per CTA;
 //   * a warp runs two of its three transforms in lock step and the third alone (x2 + x1 instead of
 //     x3), so accumulator (32) + data (64) registers fit the 128-register budget of 512 threads.
-// Digit 0 shares its tile with the natural-order accumulator copy, therefore it is transformed LAST
-// (its rotated difference is recomputed from the still-intact copy) and limb 2 is inverted last.
+// Digit 0 shares its tile with the natural-order accumulator copy; the rotated difference is computed once, kept in
+// registers across digit 0's (x1) passes and reused for digits 1 and 2; limb 2 is inverted last.  The first two forward
+// stages are table look-ups on the 6-bit digits (ntt_warp.h fwd_start_r4_group).
 //
 // Step sequence (phases separated by __syncwarp unless noted):
-//   F12a  rotated difference -> digits 1,2 -> pass 1 (x2) -> column stores into tiles 3q+1, 3q+2
-//   F12c  row loads -> pass 2 (x2) -> row stores
-//   F0a   rotated difference again -> digit 0 -> pass 1            (last read of the accumulator copy)
+//   F0a   rotated difference (kept) -> digit 0 -> pass 1            (only read of the accumulator copy)
 //   F0b   column store into tile 3q
-//   F0c   row load -> pass 2 -> row store          ; __syncthreads ; pointwise ; __syncthreads
+//   F0c   row load -> pass 2 -> row store
+//   F12a  digits 1,2 from the kept difference -> pass 1 (x2) -> column stores into tiles 3q+1, 3q+2
+//   F12c  row loads -> pass 2 (x2) -> row stores   ; __syncthreads ; pointwise ; __syncthreads
 //   I01a  row loads of limbs 0,1 -> inverse pass 1 (x2) -> row stores
 //   I01b  column loads -> inverse pass 2 (x2) -> lift, acc += v0 + (v1 << 11)
 //   I2a   row load of limb 2 -> inverse pass 1 -> row store
@@ -88,26 +89,6 @@ B200_HD uint32_t br7_dv(const uint32_t* acc, uint32_t base, int a, uint32_t accr
     return ((v ^ neg) - neg) - accr_a + (DEC_OFFSET + DEC_ROUND);
 }
 
-// F12a: digits 1 and 2 -> stages 0,1 by table look-up -> rest of pass 1 (x2) -> column stores (tiles 3q+1, 3q+2 do not
-// overlap the accumulator copy)
-template <int G>
-B200_HD void br7_fwd12_a(const Br7Smem<G>& sm, int i, int g, int q, int lane, const uint32_t (&accr)[32])
-{
-    uint32_t x1[32], x2[32];
-    const uint32_t abar = sm.abar[g * SLOT_STRIDE + i];
-    const uint32_t* acc = sm.acc(g, q);
-    const uint32_t base = ((uint32_t)lane - abar) & (2u * N1 - 1);
-    B200_UNROLL
-    for (int k = 0; k < 8; k++) {
-        const uint32_t d0 = br7_dv(acc, base, k, accr[k]), d1 = br7_dv(acc, base, k + 8, accr[k + 8]);
-        const uint32_t d2 = br7_dv(acc, base, k + 16, accr[k + 16]), d3 = br7_dv(acc, base, k + 24, accr[k + 24]);
-        fwd_start_r4_group<32 - 2 * BGBIT>(sm.r4, d0, d1, d2, d3, x1[k], x1[k + 8], x1[k + 16], x1[k + 24]);
-        fwd_start_r4_group<32 - 3 * BGBIT>(sm.r4, d0, d1, d2, d3, x2[k], x2[k + 8], x2[k + 16], x2[k + 24]);
-    }
-    fwd_pass1_tail_x2(x1, x2);
-    stile_store_col(sm.tile(g, q * GL + 1), x1, lane);
-    stile_store_col(sm.tile(g, q * GL + 2), x2, lane);
-}
 // F12c
 template <int G>
 B200_HD void br7_fwd12_c(const Br7Smem<G>& sm, int g, int q, int lane)
@@ -119,22 +100,6 @@ B200_HD void br7_fwd12_c(const Br7Smem<G>& sm, int g, int q, int lane)
     fwd_pass2_x2(x1, x2, sm.tw2f, lane);
     stile_store_row(t, x1, lane);
     stile_store_row(t + STILE_WORDS, x2, lane);
-}
-// F0a: digit 0 -> pass 1; registers returned so the caller can __syncwarp before the store
-template <int G>
-B200_HD void br7_fwd0_a(const Br7Smem<G>& sm, int i, int g, int q, int lane, const uint32_t (&accr)[32],
-                        uint32_t (&x0)[32])
-{
-    const uint32_t abar = sm.abar[g * SLOT_STRIDE + i];
-    const uint32_t* acc = sm.acc(g, q);
-    const uint32_t base = ((uint32_t)lane - abar) & (2u * N1 - 1);
-    B200_UNROLL
-    for (int k = 0; k < 8; k++) {
-        const uint32_t d0 = br7_dv(acc, base, k, accr[k]), d1 = br7_dv(acc, base, k + 8, accr[k + 8]);
-        const uint32_t d2 = br7_dv(acc, base, k + 16, accr[k + 16]), d3 = br7_dv(acc, base, k + 24, accr[k + 24]);
-        fwd_start_r4_group<32 - BGBIT>(sm.r4, d0, d1, d2, d3, x0[k], x0[k + 8], x0[k + 16], x0[k + 24]);
-    }
-    fwd_pass1_tail(x0);
 }
 template <int G>
 B200_HD void br7_fwd0_b(const Br7Smem<G>& sm, int g, int q, int lane, const uint32_t (&x0)[32])
@@ -149,6 +114,38 @@ B200_HD void br7_fwd0_c(const Br7Smem<G>& sm, int g, int q, int lane)
     stile_load_row(t, x0, lane);
     fwd_pass2(x0, sm.tw2f, lane);
     stile_store_row(t, x0, lane);
+}
+
+// F0a: the rotated difference is computed ONCE and kept in registers (dv); digit 0 -> stages 0,1 by table look-up -> rest
+// of pass 1.  Digit 0 goes first because its x1 passes leave room for the 32 registers of dv; x0 is returned so the caller
+// can __syncwarp (last read of the accumulator copy that shares tile 3q with digit 0) before the store.
+template <int G>
+B200_HD void br7_fwd0_a(const Br7Smem<G>& sm, int i, int g, int q, int lane, const uint32_t (&accr)[32], uint32_t (&dv)[32],
+                        uint32_t (&x0)[32])
+{
+    const uint32_t abar = sm.abar[g * SLOT_STRIDE + i];
+    const uint32_t* acc = sm.acc(g, q);
+    const uint32_t base = ((uint32_t)lane - abar) & (2u * N1 - 1);
+    B200_UNROLL
+    for (int a = 0; a < 32; a++) dv[a] = br7_dv(acc, base, a, accr[a]);
+    B200_UNROLL
+    for (int k = 0; k < 8; k++)
+        fwd_start_r4_group<32 - BGBIT>(sm.r4, dv[k], dv[k + 8], dv[k + 16], dv[k + 24], x0[k], x0[k + 8], x0[k + 16], x0[k + 24]);
+    fwd_pass1_tail(x0);
+}
+// F12a: digits 1 and 2 from the kept difference -> table look-up -> rest of pass 1 (x2) -> column stores
+template <int G>
+B200_HD void br7_fwd12_a(const Br7Smem<G>& sm, int g, int q, int lane, const uint32_t (&dv)[32])
+{
+    uint32_t x1[32], x2[32];
+    B200_UNROLL
+    for (int k = 0; k < 8; k++) {
+        fwd_start_r4_group<32 - 2 * BGBIT>(sm.r4, dv[k], dv[k + 8], dv[k + 16], dv[k + 24], x1[k], x1[k + 8], x1[k + 16], x1[k + 24]);
+        fwd_start_r4_group<32 - 3 * BGBIT>(sm.r4, dv[k], dv[k + 8], dv[k + 16], dv[k + 24], x2[k], x2[k + 8], x2[k + 16], x2[k + 24]);
+    }
+    fwd_pass1_tail_x2(x1, x2);
+    stile_store_col(sm.tile(g, q * GL + 1), x1, lane);
+    stile_store_col(sm.tile(g, q * GL + 2), x2, lane);
 }
 
 // Jobs g0 .. g0+J-1 of the CTA form a barrier group of 64*J threads that runs its own pointwise stage:

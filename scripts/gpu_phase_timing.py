@@ -25,7 +25,7 @@ NAMES = {
     6: ["fwd_p1", "bar", "fwd_p2", "bar", "fwd_p3", "bar", "fwd_p4", "fence+cluster_wait", "team bar", "copy issue+key wait",
         "cta bar", "pw_local", "wait peer tiles", "pw_finish", "arrive+cta bar", "inv_pA", "bar", "inv_pB", "bar", "inv_pC",
         "bar", "inv_pD", "cta bar"],
-    7: ["fwd12_a (rotate, digits 1-2, pass 1)", "fwd12_c (pass 2)", "fwd0_a+b (digit 0, pass 1)", "fwd0_c (pass 2)",
+    7: ["fwd0_a+b (rotate, digit 0, pass 1)", "fwd0_c (pass 2)", "fwd12_a (digits 1-2, pass 1)", "fwd12_c (pass 2)",
         "key prefetch + cta bar", "pointwise", "cta bar", "inv01_a", "inv01_b", "inv2_a", "inv2_b (+acc)"],
 }
 out = {}

@@ -278,6 +278,7 @@ extern "C" void sim_blind_rotate3(int G, const void* jobs_raw, int njobs, const 
 }
 
 // ---- variant 7: 16-warp throughput shape on swizzled tiles (br7_kernel) ----
+
 template <int G, int J>
 static void sim_br7_cta(const BrJob* jobs, int njobs, int cta, const torus0_t* arena, const uint32_t* bk_ntt,
                         uint32_t* ubuf, int n_iter)
@@ -290,7 +291,7 @@ static void sim_br7_cta(const BrJob* jobs, int njobs, int cta, const torus0_t* a
     std::memcpy(sm.tw2i, g_tab.tw2i, sizeof(g_tab.tw2i));
     std::memcpy(sm.r4, g_tab.r4, sizeof(g_tab.r4));
     struct Regs {
-        uint32_t accr[32], x0[32];
+        uint32_t accr[32], x0[32], dv[32];
     };
     std::vector<Regs> regs(T);
     auto jobof = [&](int g) {
@@ -303,14 +304,14 @@ static void sim_br7_cta(const BrJob* jobs, int njobs, int cta, const torus0_t* a
     for (int i = 0; i < n_iter; i++) {
         for (int ww = 0; ww < W; ww++) {
             const int w = ord(ww, W), g = w >> 1, q = w & 1;
-            for (int l = 0; l < 32; l++) br7_fwd12_a<G>(sm, i, g, q, ord(l, 32), regs[w * 32 + ord(l, 32)].accr);
-            for (int l = 0; l < 32; l++) br7_fwd12_c<G>(sm, g, q, ord(l, 32));
             for (int l = 0; l < 32; l++) {
                 Regs& r = regs[w * 32 + ord(l, 32)];
-                br7_fwd0_a<G>(sm, i, g, q, ord(l, 32), r.accr, r.x0);
+                br7_fwd0_a<G>(sm, i, g, q, ord(l, 32), r.accr, r.dv, r.x0);
             }
             for (int l = 0; l < 32; l++) br7_fwd0_b<G>(sm, g, q, ord(l, 32), regs[w * 32 + ord(l, 32)].x0);
             for (int l = 0; l < 32; l++) br7_fwd0_c<G>(sm, g, q, ord(l, 32));
+            for (int l = 0; l < 32; l++) br7_fwd12_a<G>(sm, g, q, ord(l, 32), regs[w * 32 + ord(l, 32)].dv);
+            for (int l = 0; l < 32; l++) br7_fwd12_c<G>(sm, g, q, ord(l, 32));
         }
         const uint32_t* bk_i = bk_ntt + (size_t)i * BK_COLS * ROWS * N1;
         for (int t = 0; t < T; t++) {  // barrier groups of J jobs, each with its own pointwise stage

@@ -109,7 +109,7 @@ def test_blind_rotate_variant3_bit_exact(sim, keys, bk_ntt_sim, G):
 
 @pytest.mark.parametrize("G", [2, 8, 84, 82])   # 84 / 82: eight jobs per CTA in barrier groups of 4 / 2
 def test_blind_rotate_variant7_bit_exact(sim, keys, bk_ntt_sim, G):
-    # 16-warp throughput shape (br7_phases.h): swizzled tiles, x2 + x1 interleave, digit 0 / limb 2 last
+    # 16-warp throughput shape (br7_phases.h): swizzled tiles, x1 + x2 interleave, one rotated difference kept in registers
     rng = np.random.default_rng(70 + G)
     n = 9 if G > 8 else 3  # ragged last CTA
     pa, pb = rng.integers(0, 2, n, dtype=np.uint8), rng.integers(0, 2, n, dtype=np.uint8)

@@ -29,6 +29,13 @@
  * All pointers are plain host pointers unless the name says "dev".  The library is not
  * thread-safe per context; Iyokan calls it from its single scheduler thread
  * (src/iyokan_tfhepp.cpp:28-47).  One context = one GPU = (in multi-GPU runs) one process.
+ *
+ * Environment read by the library (all optional; none changes results, only how the work is launched):
+ *   B200FHE_NO_CALIBRATE=1   keep the compiled-in launch-plan table instead of timing one wave per shape at key load
+ *   B200FHE_NO_GRAPH=1       replay programs launch by launch instead of as one CUDA graph
+ *   B200FHE_KS8_MIN=n        frontier width from which the key switch takes eight gates per CTA (default 1400)
+ *   B200FHE_NCCL_LIB=path    NCCL library to dlopen for b200fhe_comm_* (default libnccl.so.2)
+ *   B200FHE_BR7_GROUP / B200FHE_BR7_SKEW / B200FHE_L2_PERSIST   experiment knobs kept for the measurements under profiles/
  */
 #ifndef B200FHE_H
 #define B200FHE_H
